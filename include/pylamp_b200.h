@@ -1,0 +1,161 @@
+/* pylamp_b200.h -- C ABI of libpylamp_b200.so: PyLamp's per-timestep hot path on B200 (sm_100a).
+ *
+ * The reference (larskaislaniemi/PyLamp) has no FFI: its boundary is the set of module-level
+ * Python functions that pylamp2.py calls.  Each entry point below replaces one of them (the
+ * reference file:line is cited per function); the Python modules in pylamp_b200/ keep the
+ * reference's names and signatures and reach these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every `d_` pointer is DEVICE memory, every `h_` pointer HOST memory.
+ *   - all floating point is IEEE fp64 (the reference is NumPy float64 throughout).
+ *   - grid fields are row-major [i (z)][j (x)], x fastest, with a leading dimension `ld >= nxx`
+ *     in doubles (ld == nxx reproduces the reference's C-contiguous layout).
+ *   - marker coordinates `d_tr_x` are (M,2) [z,x] pairs exactly like the reference's tr_x;
+ *     marker properties are passed as separate columns (SoA), one device pointer per column.
+ *   - every function returns 0 on success, non-zero on error; plb_last_error() gives the text.
+ *     No exceptions cross the boundary.  Work is enqueued on the context's stream; functions
+ *     that return values through `h_` pointers synchronise that stream.
+ */
+#ifndef PYLAMP_B200_H
+#define PYLAMP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plb_ctx plb_ctx;
+typedef struct plb_stokes plb_stokes;
+typedef struct plb_diff plb_diff;
+
+/* averaging schemes and interpolation methods: pylamp_trac.py:11-22 */
+#define PLB_AVG_ARITHMETIC 1
+#define PLB_AVG_GEOMETRIC 2
+#define PLB_AVG_WEIGHTED 4
+#define PLB_METHOD_NEAREST 8
+#define PLB_METHOD_LINEAR 16
+#define PLB_METHOD_VELDIV 32
+/* Stokes wall types pylamp_stokes.py:17-20; heat wall types pylamp_diff.py:12-13 */
+#define PLB_BC_NOSLIP 0
+#define PLB_BC_FREESLIP 1
+#define PLB_BC_CYCLIC 2
+#define PLB_BC_FLOWTHRU 4
+#define PLB_BC_FIXTEMP 0
+#define PLB_BC_FIXFLOW 1
+#define PLB_MAX_FIELDS 8
+
+/* ---- context ------------------------------------------------------------------------- */
+int plb_ctx_create(int device, plb_ctx** out);
+void plb_ctx_destroy(plb_ctx* ctx);
+/* run on an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+int plb_ctx_set_stream(plb_ctx* ctx, void* cuda_stream);
+int plb_ctx_sync(plb_ctx* ctx);
+const char* plb_last_error(plb_ctx* ctx);
+/* number of CUDA kernels this library has launched on the context so far */
+long long plb_launch_count(plb_ctx* ctx);
+const char* plb_version(void);
+
+/* ---- markers -> grid: pylamp_trac.trac2grid, pylamp_trac.py:161-318 -------------------- */
+/* h_out[4] = min z, max z, min x, max x over the markers (the ghost-node extension test of
+ * pylamp_trac.py:207-217 is a global min/max).  Synchronises. */
+int plb_marker_minmax(plb_ctx* ctx, long long M, const double* d_tr_x, double* h_out);
+/* Average k marker columns to one target grid.  d_axis_z/d_axis_x are the (already ghost-
+ * extended) target axes of length nze/nxe; the result is cropped to rows [crop_z0, crop_z0+nz)
+ * and columns [crop_x0, crop_x0+nxx) and written to d_out[f] (nz x ld).  h_scheme[f] is the
+ * reference's avgscheme bit-flag.  Empty nodes give 0/0 = NaN like the reference (:268). */
+int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
+                  const double* const* h_fields, const int* h_scheme,
+                  const double* d_axis_z, int nze, const double* d_axis_x, int nxe,
+                  int crop_z0, int crop_x0, int nz, int nxx, int ld, double* const* h_out);
+
+/* ---- grid -> markers: pylamp_trac.grid2trac, pylamp_trac.py:30-158 ---------------------- */
+/* method = PLB_METHOD_{NEAREST,LINEAR,VELDIV}.  Writes k output columns (SoA, length M).
+ * Markers outside the grid get `defval` and are counted into *h_n_outside (synchronises). */
+int plb_grid2trac(plb_ctx* ctx, long long M, const double* d_tr_x, int method, int k,
+                  const double* const* h_fields, const double* d_grid_z, int nz,
+                  const double* d_grid_x, int nxx, int ld, double defval,
+                  double* const* h_out, long long* h_n_outside);
+
+/* ---- marker advection: pylamp_trac.RK (order 4), pylamp_trac.py:321-388 ----------------- */
+/* d_vz_c/d_vx_c: cell-centred velocities with BC ring, (nzc x ld) with nzc = nz+1, nxc = nxx+1;
+ * d_gc_z/d_gc_x their coordinates.  x+ = x + (1/6) dt (k1+k2+k3+k4) (the reference's weights);
+ * d_v_out = (x+ - x)/dt.  d_x_out, d_v_out are (M,2). */
+int plb_rk4(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_vz_c,
+            const double* d_vx_c, const double* d_gc_z, int nzc, const double* d_gc_x, int nxc,
+            int ld, double dt, double* d_x_out, double* d_v_out);
+
+/* ---- driver-inline marker steps of pylamp2.py ------------------------------------------ */
+/* fence, pylamp2.py:558-572 (fence enabled, no FLOWTHRU/CYCLIC): x<=0 -> eps, x>=L -> L-eps */
+int plb_fence(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps);
+/* cell index + per-cell count, pylamp2.py:588-593.  BIT-EXACT parity item: ielem =
+ * floor((nz-1)*z/Lz) with IEEE mul then div, kelem = ielem*(nxx-1)+jelem (int64);
+ * d_count[(nz-1)*(nxx-1)] int64.  d_kelem may be NULL. */
+int plb_cell_index_count(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, int nxx,
+                         double Lz, double Lx, long long* d_kelem, long long* d_count);
+/* marker property update, pylamp2.py:291-303 (columns of tr_f) */
+int plb_update_properties(plb_ctx* ctx, long long M, int tdep_rho, int tdep_eta, double Tref,
+                          double etamin, double etamax, const double* d_T, const double* d_rho0,
+                          const double* d_alpha, const double* d_Ea, const double* d_eta0,
+                          double* d_rho, double* d_eta);
+/* cell-centre velocities + BC ghost ring, pylamp2.py:491-545; outputs (nz+1) x ldc */
+int plb_centre_velocities(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_vz,
+                          const double* d_vx, const int* h_bc, int ldc, double* d_vz_c,
+                          double* d_vx_c);
+/* subgrid diffusion marker update, pylamp2.py:471-476:  Tsg = Told-(Told-T)*exp(-d*dt/tau),
+ * d_dT = Tsg - T (stage 1);  T = Tsg - back (stage 2, after trac2grid/grid2trac of d_dT) */
+int plb_subgrid_stage1(plb_ctx* ctx, long long M, double dt, double dz, double dx,
+                       const double* d_Told, const double* d_T, const double* d_cp,
+                       const double* d_rho, const double* d_k, double* d_Tsg, double* d_dT);
+int plb_subgrid_stage2(plb_ctx* ctx, long long M, const double* d_Tsg, const double* d_back,
+                       double* d_T);
+/* max over a field region / generic reductions used by the dt selection, pylamp2.py:339-366.
+ * h_out = max of a (nz x nxx, ld) field (signed max, quirk 6).  Synchronises. */
+int plb_field_max(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_f, double* h_out);
+/* max over nodes of 2*kz/(rho*cp): pylamp2.py:340-341.  Synchronises. */
+int plb_max_diffusivity2(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_kz,
+                         const double* d_rho, const double* d_cp, double* h_out);
+
+/* ---- Stokes operator: pylamp_stokes.makeStokesMatrix, pylamp_stokes.py:104-563 ----------- */
+/* Matrix-free operator in the reference's exact DOF layout and row scaling, including ghost,
+ * wall, corner and anchor rows.  h_grid_z/h_grid_x: node coordinates (any rectilinear spacing);
+ * h_bc[4] indexed DIM*wall+dir = [z=0, x=0, z=L, x=L].  Supported: z-walls NOSLIP|FREESLIP,
+ * x-walls FREESLIP (the reference itself is singular for NOSLIP x-walls). */
+int plb_stokes_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_z,
+                      const double* h_grid_x, const int* h_bc, plb_stokes** out);
+void plb_stokes_destroy(plb_stokes* op);
+/* bind coefficient fields (nz x ld, device; must stay alive) and compute Kcont/Kbond
+ * (pylamp_stokes.py:116-122) on the device.  gz, gx: gravity G (pylamp_const.py:21). */
+int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_etan,
+                          const double* d_rho, double gz, double gx);
+/* h_out[2] = {Kcont, Kbond}.  Synchronises. */
+int plb_stokes_scaling(plb_stokes* op, double* h_out);
+/* rhs in the reference's interleaved layout, length 3*nz*nxx (pylamp_stokes.py:429, 490) */
+int plb_stokes_rhs(plb_stokes* op, double* d_rhs);
+/* y = A x, both interleaved [vz,vx,P] per node, length 3*nz*nxx (what A_ref @ x gives) */
+int plb_stokes_apply(plb_stokes* op, const double* d_x, double* d_y);
+/* replaces scipy.sparse.linalg.spsolve(csc_matrix(A), rhs) at pylamp2.py:360: solves A x = rhs
+ * (rhs from plb_stokes_rhs) with preconditioned Krylov + geometric multigrid.  x interleaved.
+ * rtol on the scaled true residual.  Returns non-zero if not converged within maxit. */
+int plb_stokes_solve(plb_stokes* op, double rtol, int maxit, double* d_x, int* h_iters,
+                     double* h_relres);
+/* x2vp, pylamp_stokes.py:86-101: de-interleave into three (nz x ld) planes */
+int plb_x2vp(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_x, double* d_vz,
+             double* d_vx, double* d_p);
+
+/* ---- energy operator: pylamp_diff.makeDiffusionMatrix, pylamp_diff.py:85-183 -------------- */
+int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_z,
+                    const double* h_grid_x, const double* h_gridmp_z, const double* h_gridmp_x,
+                    const int* h_bc, const double* h_bcvalue, plb_diff** out);
+void plb_diff_destroy(plb_diff* op);
+int plb_diff_set_coeffs(plb_diff* op, const double* d_T, const double* d_kz, const double* d_kx,
+                        const double* d_cp, const double* d_rho, const double* d_H, double tstep);
+/* rhs / apply / solve on (nz x nxx) vectors stored with the leading dimension ld */
+int plb_diff_rhs(plb_diff* op, double* d_rhs);
+int plb_diff_apply(plb_diff* op, const double* d_x, double* d_y);
+/* replaces spsolve at pylamp2.py:419 */
+int plb_diff_solve(plb_diff* op, double rtol, int maxit, double* d_x, int* h_iters,
+                   double* h_relres);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
