@@ -46,7 +46,8 @@ typedef struct plb_diff plb_diff;
 /* ---- context ------------------------------------------------------------------------- */
 int plb_ctx_create(int device, plb_ctx** out);
 void plb_ctx_destroy(plb_ctx* ctx);
-/* run on an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+/* run on an existing cudaStream_t (e.g. torch's current stream); 0 = CUDA's default stream.
+ * A fresh context owns a private non-blocking stream until this is called. */
 int plb_ctx_set_stream(plb_ctx* ctx, void* cuda_stream);
 int plb_ctx_sync(plb_ctx* ctx);
 const char* plb_last_error(plb_ctx* ctx);
@@ -61,10 +62,13 @@ int plb_marker_minmax(plb_ctx* ctx, long long M, const double* d_tr_x, double* h
 /* Average k marker columns to one target grid.  d_axis_z/d_axis_x are the (already ghost-
  * extended) target axes of length nze/nxe; the result is cropped to rows [crop_z0, crop_z0+nz)
  * and columns [crop_x0, crop_x0+nxx) and written to d_out[f] (nz x ld).  h_scheme[f] is the
- * reference's avgscheme bit-flag.  Empty nodes give 0/0 = NaN like the reference (:268). */
+ * reference's avgscheme bit-flag.  Empty nodes give 0/0 = NaN like the reference (:268).
+ * z0/zlen/x0/xlen = axis[0] and axis[-1]-axis[0] as the host computed them (the cell lookup
+ * floor((n-1)*(x-z0)/zlen) must round exactly like NumPy's, pylamp_trac.py:222-227). */
 int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
                   const double* const* h_fields, const int* h_scheme,
                   const double* d_axis_z, int nze, const double* d_axis_x, int nxe,
+                  double z0, double zlen, double x0, double xlen,
                   int crop_z0, int crop_x0, int nz, int nxx, int ld, double* const* h_out);
 
 /* ---- grid -> markers: pylamp_trac.grid2trac, pylamp_trac.py:30-158 ---------------------- */
@@ -72,8 +76,8 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
  * Markers outside the grid get `defval` and are counted into *h_n_outside (synchronises). */
 int plb_grid2trac(plb_ctx* ctx, long long M, const double* d_tr_x, int method, int k,
                   const double* const* h_fields, const double* d_grid_z, int nz,
-                  const double* d_grid_x, int nxx, int ld, double defval,
-                  double* const* h_out, long long* h_n_outside);
+                  const double* d_grid_x, int nxx, int ld, double z0, double zlen, double x0,
+                  double xlen, double defval, double* const* h_out, long long* h_n_outside);
 
 /* ---- marker advection: pylamp_trac.RK (order 4), pylamp_trac.py:321-388 ----------------- */
 /* d_vz_c/d_vx_c: cell-centred velocities with BC ring, (nzc x ld) with nzc = nz+1, nxc = nxx+1;
@@ -81,7 +85,8 @@ int plb_grid2trac(plb_ctx* ctx, long long M, const double* d_tr_x, int method, i
  * d_v_out = (x+ - x)/dt.  d_x_out, d_v_out are (M,2). */
 int plb_rk4(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_vz_c,
             const double* d_vx_c, const double* d_gc_z, int nzc, const double* d_gc_x, int nxc,
-            int ld, double dt, double* d_x_out, double* d_v_out);
+            int ld, double z0, double zlen, double x0, double xlen, double dt, double* d_x_out,
+            double* d_v_out);
 
 /* ---- driver-inline marker steps of pylamp2.py ------------------------------------------ */
 /* fence, pylamp2.py:558-572 (fence enabled, no FLOWTHRU/CYCLIC): x<=0 -> eps, x>=L -> L-eps */
@@ -93,7 +98,8 @@ int plb_cell_index_count(plb_ctx* ctx, long long M, const double* d_tr_x, int nz
                          double Lz, double Lx, long long* d_kelem, long long* d_count);
 /* marker property update, pylamp2.py:291-303 (columns of tr_f) */
 int plb_update_properties(plb_ctx* ctx, long long M, int tdep_rho, int tdep_eta, double Tref,
-                          double etamin, double etamax, const double* d_T, const double* d_rho0,
+                          double etamin, double etamax, double gasr, const double* d_T,
+                          const double* d_rho0,
                           const double* d_alpha, const double* d_Ea, const double* d_eta0,
                           double* d_rho, double* d_eta);
 /* cell-centre velocities + BC ghost ring, pylamp2.py:491-545; outputs (nz+1) x ldc */

@@ -1,0 +1,168 @@
+"""ctypes binding of libpylamp_b200.so (the C-ABI of include/pylamp_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing, or no CUDA device is
+visible when a context is requested, this module raises.
+"""
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+_c_double_p = C.POINTER(C.c_double)
+VP = C.c_void_p          # device pointers travel as integers (tensor.data_ptr())
+LL = C.c_longlong
+I = C.c_int
+D = C.c_double
+PP = C.POINTER(C.c_void_p)   # host array of device pointers
+IP = C.POINTER(C.c_int)
+DP = C.POINTER(C.c_double)   # host doubles
+
+_PROTOS = {
+    "plb_version": (C.c_char_p, []),
+    "plb_ctx_create": (I, [I, C.POINTER(VP)]),
+    "plb_ctx_destroy": (None, [VP]),
+    "plb_ctx_set_stream": (I, [VP, VP]),
+    "plb_ctx_sync": (I, [VP]),
+    "plb_last_error": (C.c_char_p, [VP]),
+    "plb_launch_count": (LL, [VP]),
+    "plb_marker_minmax": (I, [VP, LL, VP, DP]),
+    "plb_trac2grid": (I, [VP, LL, VP, I, PP, IP, VP, I, VP, I, D, D, D, D, I, I, I, I, I, PP]),
+    "plb_grid2trac": (I, [VP, LL, VP, I, I, PP, VP, I, VP, I, I, D, D, D, D, D, PP,
+                          C.POINTER(LL)]),
+    "plb_rk4": (I, [VP, LL, VP, VP, VP, VP, I, VP, I, I, D, D, D, D, D, VP, VP]),
+    "plb_fence": (I, [VP, LL, VP, D, D, D]),
+    "plb_cell_index_count": (I, [VP, LL, VP, I, I, D, D, VP, VP]),
+    "plb_update_properties": (I, [VP, LL, I, I, D, D, D, D, VP, VP, VP, VP, VP, VP, VP]),
+    "plb_centre_velocities": (I, [VP, I, I, I, VP, VP, IP, I, VP, VP]),
+    "plb_subgrid_stage1": (I, [VP, LL, D, D, D, VP, VP, VP, VP, VP, VP, VP]),
+    "plb_subgrid_stage2": (I, [VP, LL, VP, VP, VP]),
+    "plb_field_max": (I, [VP, I, I, I, VP, DP]),
+    "plb_max_diffusivity2": (I, [VP, I, I, I, VP, VP, VP, DP]),
+    "plb_stokes_create": (I, [VP, I, I, I, DP, DP, IP, C.POINTER(VP)]),
+    "plb_stokes_destroy": (None, [VP]),
+    "plb_stokes_set_coeffs": (I, [VP, VP, VP, VP, D, D]),
+    "plb_stokes_scaling": (I, [VP, DP]),
+    "plb_stokes_rhs": (I, [VP, VP]),
+    "plb_stokes_apply": (I, [VP, VP, VP]),
+    "plb_stokes_solve": (I, [VP, D, I, VP, IP, DP]),
+    "plb_x2vp": (I, [VP, I, I, I, VP, VP, VP, VP]),
+    "plb_diff_create": (I, [VP, I, I, I, DP, DP, DP, DP, IP, DP, C.POINTER(VP)]),
+    "plb_diff_destroy": (None, [VP]),
+    "plb_diff_set_coeffs": (I, [VP, VP, VP, VP, VP, VP, VP, D]),
+    "plb_diff_rhs": (I, [VP, VP]),
+    "plb_diff_apply": (I, [VP, VP, VP]),
+    "plb_diff_solve": (I, [VP, D, I, VP, IP, DP]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class PlbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.lib_path()
+        if not os.path.exists(path):
+            raise PlbError(
+                "libpylamp_b200.so not found at %s -- run `python -m pylamp_b200.build` "
+                "(there is no CPU fallback)" % path)
+        lib = C.CDLL(path)
+        for name, (res, args) in _PROTOS.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                continue          # reported by exported_symbols()/tests, raised on first use
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def exported(name):
+    try:
+        getattr(load(), name)
+        return True
+    except AttributeError:
+        return False
+
+
+class Context:
+    """One plb_ctx per GPU: stream, scratch and error text."""
+
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise PlbError("pylamp_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = load()
+        self.device = int(device)
+        h = VP()
+        rc = self.lib.plb_ctx_create(self.device, C.byref(h))
+        if rc != 0:
+            raise PlbError("plb_ctx_create(device=%d) failed with %d" % (device, rc))
+        self.h = h
+        # run on torch's current stream so that torch allocations/copies order with our kernels
+        self.torch_device = torch.device("cuda", self.device)
+        stream = torch.cuda.current_stream(self.torch_device)
+        self.check(self.lib.plb_ctx_set_stream(self.h, VP(stream.cuda_stream)))
+
+    def check(self, rc):
+        if rc != 0:
+            raise PlbError(self.lib.plb_last_error(self.h).decode() or "error %d" % rc)
+
+    def call(self, name, *args):
+        self.check(getattr(self.lib, name)(self.h, *args))
+
+    def sync(self):
+        self.check(self.lib.plb_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.plb_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.plb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    import torch
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx
+
+
+def ptr_array(tensors):
+    """Host array of device pointers from a list of tensors (kept alive by the caller)."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def dbl_array(vals):
+    return (C.c_double * len(vals))(*[float(v) for v in vals])

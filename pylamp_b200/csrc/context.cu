@@ -42,6 +42,7 @@ void plb_ctx_destroy(plb_ctx* ctx) {
 }
 
 int plb_ctx_set_stream(plb_ctx* ctx, void* cuda_stream) {
+    // the handle is used as given; 0 is CUDA's default stream (what torch uses unless told otherwise)
     if (!ctx) return 1;
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -49,12 +50,7 @@ int plb_ctx_set_stream(plb_ctx* ctx, void* cuda_stream) {
         cudaStreamDestroy(ctx->stream);
         ctx->own_stream = false;
     }
-    if (cuda_stream == nullptr) {
-        PLB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
-    } else {
-        ctx->stream = (cudaStream_t)cuda_stream;
-    }
+    ctx->stream = (cudaStream_t)cuda_stream;
     return 0;
 }
 

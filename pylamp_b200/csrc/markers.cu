@@ -1,0 +1,597 @@
+// markers.cu -- marker-in-cell kernels: marker->grid averaging, grid->marker interpolation,
+// RK4 advection with Meyer-Jenny conservative velocity interpolation, fence, cell index/count,
+// marker property update, subgrid-diffusion marker stages.
+//
+// Reference behaviour restated (never copied): pylamp_trac.py:30-158 (grid2trac), :161-318
+// (trac2grid), :321-388 (RK); pylamp2.py:291-303, :471-476, :558-572, :588-593.
+#include "common.cuh"
+
+namespace {
+
+// floor((n-1)*(x-lmin)/len) with IEEE multiply then divide and no FMA contraction, so that the
+// cell a marker falls into is bit-identical to NumPy's (pylamp_trac.py:46-47, :226-227;
+// pylamp2.py:588-589).
+__device__ __forceinline__ long long cell_of(double x, double lmin, double len, int n) {
+    double t = __ddiv_rn(__dmul_rn((double)(n - 1), __dsub_rn(x, lmin)), len);
+    return (long long)floor(t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// min/max of marker coordinates
+// ---------------------------------------------------------------------------------------------
+__global__ void k_minmax_init(double* out) {
+    out[0] = out[2] = 1e300;
+    out[1] = out[3] = -1e300;
+}
+
+__global__ void __launch_bounds__(256) k_marker_minmax(long long M, const double2* __restrict__ x,
+                                                      double* out) {
+    double zmin = 1e300, zmax = -1e300, xmin = 1e300, xmax = -1e300;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        double2 p = x[m];
+        zmin = fmin(zmin, p.x), zmax = fmax(zmax, p.x);
+        xmin = fmin(xmin, p.y), xmax = fmax(xmax, p.y);
+    }
+    zmin = warp_min(zmin), zmax = warp_max(zmax), xmin = warp_min(xmin), xmax = warp_max(xmax);
+    __shared__ double s[4][8];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) s[0][w] = zmin, s[1][w] = zmax, s[2][w] = xmin, s[3][w] = xmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) {
+            s[0][0] = fmin(s[0][0], s[0][i]), s[1][0] = fmax(s[1][0], s[1][i]);
+            s[2][0] = fmin(s[2][0], s[2][i]), s[3][0] = fmax(s[3][0], s[3][i]);
+        }
+        atomic_min_double(out + 0, s[0][0]), atomic_max_double(out + 1, s[1][0]);
+        atomic_min_double(out + 2, s[2][0]), atomic_max_double(out + 3, s[3][0]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trac2grid: scatter phase + finalise phase
+// ---------------------------------------------------------------------------------------------
+struct T2GArgs {
+    const double* f[PLB_MAX_FIELDS];
+    double* acc[PLB_MAX_FIELDS];   // accumulation planes nze x nxe
+    double* out[PLB_MAX_FIELDS];
+    int scheme[PLB_MAX_FIELDS];
+    double* wsum;                  // sum of weights (weighted schemes)
+    double* cnt;                   // marker count per node (unweighted schemes)
+    const double* axz;
+    const double* axx;
+    int nze, nxe;
+    double z0, zlen, x0, xlen;
+    int k;
+};
+
+// Warp-aggregated scatter: contiguous lanes of a warp that fall in the same cell (the common
+// case once the markers are cell-ordered) are combined by a segmented shuffle reduction, so
+// only the first lane of each run issues the global fp64 reductions.  Correct for any order.
+__device__ __forceinline__ double seg_reduce(double v, int lane, int run_end) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o <= run_end) v += t;
+    }
+    return v;
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; base < M; base += stride) {
+        long long m = base + lane;
+        bool valid = m < M;
+        long long cell = -1 - lane;          // invalid lanes form runs of their own
+        double w[4] = {0, 0, 0, 0};
+        double v[K];
+#pragma unroll
+        for (int f = 0; f < K; f++) v[f] = 0;
+        long long ie = 0, je = 0;
+        if (valid) {
+            double2 p = trx[m];
+            ie = cell_of(p.x, a.z0, a.zlen, a.nze);
+            je = cell_of(p.y, a.x0, a.xlen, a.nxe);
+            if (ie < 0 || ie > a.nze - 2 || je < 0 || je > a.nxe - 2) {
+                valid = false;               // cannot happen after the ghost extension
+            } else {
+                double gz0 = a.axz[ie], gz1 = a.axz[ie + 1], gx0 = a.axx[je], gx1 = a.axx[je + 1];
+                double az = (p.x - gz0) / (gz1 - gz0);      // pylamp_trac.py:247
+                double ax = (p.y - gx0) / (gx1 - gx0);
+                double bz = 1 - az, bx = 1 - ax;            // :249
+                w[0] = (1 - ax) * (1 - az);                 // node (i  , j  )   :252
+                w[1] = (1 - ax) * (1 - bz);                 // node (i+1, j  )
+                w[2] = (1 - bx) * (1 - az);                 // node (i  , j+1)
+                w[3] = (1 - bx) * (1 - bz);                 // node (i+1, j+1)
+                cell = ie * a.nxe + je;
+#pragma unroll
+                for (int f = 0; f < K; f++) {
+                    double val = a.f[f][m];
+                    v[f] = (a.scheme[f] & PLB_AVG_ARITHMETIC) ? val : log(val);
+                }
+            }
+        }
+        long long prev = __shfl_up_sync(full, cell, 1);
+        bool head = (lane == 0) || (prev != cell);
+        unsigned heads = __ballot_sync(full, head);
+        unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
+        int run_end = after ? lane + __ffs(after) - 1 : 31;
+        bool emit = head && valid;
+        long long n00 = ie * a.nxe + je;
+        long long idx[4] = {n00, n00 + a.nxe, n00 + 1, n00 + a.nxe + 1};
+        if (a.wsum) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double s = seg_reduce(w[c], lane, run_end);
+                if (emit) atomicAdd(a.wsum + idx[c], s);
+            }
+        }
+        if (a.cnt) {
+            double s = seg_reduce(valid ? 1.0 : 0.0, lane, run_end);
+            if (emit) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) atomicAdd(a.cnt + idx[c], s);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < K; f++) {
+            if (a.scheme[f] & PLB_AVG_WEIGHTED) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    double s = seg_reduce(v[f] * w[c], lane, run_end);
+                    if (emit) atomicAdd(a.acc[f] + idx[c], s);
+                }
+            } else {
+                double s = seg_reduce(v[f], lane, run_end);
+                if (emit) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) atomicAdd(a.acc[f] + idx[c], s);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_t2g_finalise(T2GArgs a, int cz0, int cx0, int nz, int nxx, int ld) {
+    long long n = (long long)nz * nxx;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / nxx), j = (int)(t % nxx);
+        long long src = (long long)(i + cz0) * a.nxe + (j + cx0);
+        for (int f = 0; f < a.k; f++) {
+            int sc = a.scheme[f];
+            double den = (sc & PLB_AVG_WEIGHTED) ? a.wsum[src] : a.cnt[src];
+            double s = a.acc[f][src];
+            double r;
+            if ((sc & PLB_AVG_GEOMETRIC) && !(sc & PLB_AVG_ARITHMETIC)) {
+                if (isinf(s)) s = 0;                 // pylamp_trac.py:301
+                r = exp(s / den);                    // :304, :306
+            } else {
+                r = s / den;                         // :281, :287
+            }
+            a.out[f][(long long)i * ld + j] = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid2trac
+// ---------------------------------------------------------------------------------------------
+struct G2TGrid {
+    const double* gz;
+    const double* gx;
+    int nz, nxx, ld;
+    double z0, zlen, x0, xlen;
+};
+
+struct Cell {
+    long long ie, je;
+    double dzn, dxn;      // normalised local coordinates (pylamp_trac.py:89-90)
+    double dz0, dz1, dx0, dx1;
+    bool bad;
+};
+
+__device__ __forceinline__ Cell locate(const G2TGrid& g, double z, double x) {
+    Cell c;
+    c.ie = cell_of(z, g.z0, g.zlen, g.nz);
+    c.je = cell_of(x, g.x0, g.xlen, g.nxx);
+    // the reference tests ie > n-1 (pylamp_trac.py:52); ie == n-1 would index past the axis
+    // there (NumPy raises), so it is treated as outside as well
+    c.bad = (c.ie < 0) || (c.ie > g.nz - 2) || (c.je < 0) || (c.je > g.nxx - 2);
+    if (c.bad) c.ie = 0, c.je = 0;
+    c.dz0 = z - g.gz[c.ie];
+    c.dz1 = -(z - g.gz[c.ie + 1]);
+    c.dx0 = x - g.gx[c.je];
+    c.dx1 = -(x - g.gx[c.je + 1]);
+    c.dxn = c.dx0 / (c.dx0 + c.dx1);
+    c.dzn = c.dz0 / (c.dz0 + c.dz1);
+    return c;
+}
+
+__device__ __forceinline__ double bilin(const double* __restrict__ f, int ld, const Cell& c) {
+    const double* p = f + c.ie * ld + c.je;
+    double f00 = __ldg(p), f01 = __ldg(p + 1), f10 = __ldg(p + ld), f11 = __ldg(p + ld + 1);
+    return (1 - c.dxn) * (1 - c.dzn) * f00 + c.dxn * (1 - c.dzn) * f01 +
+           (1 - c.dxn) * c.dzn * f10 + c.dxn * c.dzn * f11;               // :92-96
+}
+
+// Meyer & Jenny (2004) divergence-conserving correction, pylamp_trac.py:98-154
+__device__ __forceinline__ void veldiv(const double* __restrict__ fz, const double* __restrict__ fx,
+                                       const G2TGrid& g, const Cell& c, double& vz, double& vx) {
+    const double* pz = fz + c.ie * g.ld + c.je;
+    const double* px = fx + c.ie * g.ld + c.je;
+    double z00 = __ldg(pz), z01 = __ldg(pz + 1), z10 = __ldg(pz + g.ld), z11 = __ldg(pz + g.ld + 1);
+    double x00 = __ldg(px), x01 = __ldg(px + 1), x10 = __ldg(px + g.ld), x11 = __ldg(px + g.ld + 1);
+    double hz = g.gz[c.ie + 1] - g.gz[c.ie];
+    double hx = g.gx[c.je + 1] - g.gx[c.je];
+    double c10 = (0.5 * hx / hz) * (z00 - z10 + z11 - z01);
+    double c20 = (0.5 * hz / hx) * (x00 - x01 + x11 - x10);
+    double w00 = (1 - c.dxn) * (1 - c.dzn), w01 = c.dxn * (1 - c.dzn), w10 = (1 - c.dxn) * c.dzn,
+           w11 = c.dxn * c.dzn;
+    double ux = w00 * x00 + w01 * x01 + w10 * x10 + w11 * x11;
+    double uz = w00 * z00 + w01 * z01 + w10 * z10 + w11 * z11;
+    vx = ux + c.dxn * (1 - c.dxn) * c10;
+    vz = uz + c.dzn * (1 - c.dzn) * c20;
+}
+
+struct G2TArgs {
+    const double* f[PLB_MAX_FIELDS];
+    double* out[PLB_MAX_FIELDS];
+    int k;
+};
+
+__global__ void __launch_bounds__(256)
+k_grid2trac(long long M, const double2* __restrict__ trx, int method, G2TGrid g, G2TArgs a,
+            double defval, unsigned long long* n_outside) {
+    unsigned long long bad_local = 0;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        double2 p = trx[m];
+        Cell c = locate(g, p.x, p.y);
+        if (c.bad) {
+            bad_local++;
+            for (int f = 0; f < a.k; f++) a.out[f][m] = defval;
+            continue;
+        }
+        if (method & PLB_METHOD_NEAREST) {                 // :77-85
+            double d[4] = {c.dz0 * c.dz0 + c.dx0 * c.dx0, c.dz0 * c.dz0 + c.dx1 * c.dx1,
+                           c.dz1 * c.dz1 + c.dx0 * c.dx0, c.dz1 * c.dz1 + c.dx1 * c.dx1};
+            int best = 0;
+            for (int q = 1; q < 4; q++)
+                if (d[q] < d[best]) best = q;
+            long long off = (c.ie + best / 2) * g.ld + c.je + best % 2;
+            for (int f = 0; f < a.k; f++) a.out[f][m] = a.f[f][off];
+        } else if (method & PLB_METHOD_LINEAR) {
+            for (int f = 0; f < a.k; f++) a.out[f][m] = bilin(a.f[f], g.ld, c);
+        } else {                                           // VELDIV, fields = (vz, vx)
+            double vz, vx;
+            veldiv(a.f[0], a.f[1], g, c, vz, vx);
+            a.out[0][m] = vz;
+            a.out[1][m] = vx;
+        }
+    }
+    bad_local = __reduce_add_sync(0xffffffffu, (unsigned)bad_local);
+    if ((threadIdx.x & 31) == 0 && bad_local) atomicAdd(n_outside, bad_local);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RK4 with the reference's (1/6)(k1+k2+k3+k4) update, pylamp_trac.py:347-388
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vel_at(const double* __restrict__ fz, const double* __restrict__ fx,
+                                       const G2TGrid& g, double z, double x, double& vz, double& vx) {
+    Cell c = locate(g, z, x);
+    if (c.bad) {
+        vz = 0, vx = 0;                                    // defval=0, :361
+        return;
+    }
+    veldiv(fz, fx, g, c, vz, vx);
+}
+
+__global__ void __launch_bounds__(256)
+k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ fz,
+      const double* __restrict__ fx, G2TGrid g, double dt, double2* __restrict__ xout,
+      double2* __restrict__ vout) {
+    const double hdt = 0.5 * dt;
+    const double sixth_dt = (1.0 / 6.0) * dt;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        double2 p = trx[m];
+        double k1z, k1x, k2z, k2x, k3z, k3x, k4z, k4x;
+        vel_at(fz, fx, g, p.x, p.y, k1z, k1x);
+        vel_at(fz, fx, g, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
+        vel_at(fz, fx, g, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
+        vel_at(fz, fx, g, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
+        double2 q;
+        q.x = p.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // :385 (unweighted sum)
+        q.y = p.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
+        xout[m] = q;
+        if (vout) {
+            double2 v;
+            v.x = (q.x - p.x) / dt;                           // :386
+            v.y = (q.y - p.y) / dt;
+            vout[m] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fence, cell index + count, property update, subgrid stages
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fence(long long M, double2* __restrict__ trx, double Lz, double Lx, double eps) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        double2 p = trx[m];
+        bool ch = false;
+        if (p.x <= 0) p.x = eps, ch = true;
+        if (p.x >= Lz) p.x = Lz - eps, ch = true;
+        if (p.y <= 0) p.y = eps, ch = true;
+        if (p.y >= Lx) p.y = Lx - eps, ch = true;
+        if (ch) trx[m] = p;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cell_index_count(long long M, const double2* __restrict__ trx, int nz, int nxx, double Lz,
+                   double Lx, long long* __restrict__ kelem, unsigned long long* __restrict__ count) {
+    const long long ncell = (long long)(nz - 1) * (nxx - 1);
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        double2 p = trx[m];
+        // pylamp2.py:588-589: floor((n-1)*x/L) -- multiply, then divide
+        long long ie = (long long)floor(__ddiv_rn(__dmul_rn((double)(nz - 1), p.x), Lz));
+        long long je = (long long)floor(__ddiv_rn(__dmul_rn((double)(nxx - 1), p.y), Lx));
+        long long k = ie * (nxx - 1) + je;
+        if (kelem) kelem[m] = k;
+        if (count && k >= 0 && k < ncell) atomicAdd(count + k, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_update_properties(long long M, int tdep_rho, int tdep_eta, double Tref, double etamin,
+                    double etamax, double gasr, const double* __restrict__ T,
+                    const double* __restrict__ rho0, const double* __restrict__ alpha,
+                    const double* __restrict__ Ea, const double* __restrict__ eta0,
+                    double* __restrict__ rho, double* __restrict__ eta) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        if (tdep_rho) {
+            rho[m] = 1.0 / ((alpha[m] * (T[m] - Tref) + 1) / rho0[m]);        // pylamp2.py:294
+        } else {
+            rho[m] = rho0[m];
+        }
+        if (tdep_eta) {
+            double e = eta0[m] * exp(Ea[m] / (gasr * T[m]) - Ea[m] / (gasr * Tref));   // :298
+            if (e < etamin) e = etamin;
+            if (e > etamax) e = etamax;
+            eta[m] = e;
+        } else {
+            eta[m] = eta0[m];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_subgrid1(long long M, double dt, double fac, const double* __restrict__ Told,
+           const double* __restrict__ T, const double* __restrict__ cp,
+           const double* __restrict__ rho, const double* __restrict__ k, double* __restrict__ Tsg,
+           double* __restrict__ dT) {
+    const double d = 0.5;                                                      // pylamp2.py:472
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        double tau = cp[m] * rho[m] / (k[m] * fac);                            // :473
+        double tsg = Told[m] - (Told[m] - T[m]) * exp(-d * dt / tau);          // :474
+        Tsg[m] = tsg;
+        dT[m] = tsg - T[m];                                                    // :475
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_sub(long long M, const double* __restrict__ a, const double* __restrict__ b,
+      double* __restrict__ out) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x)
+        out[m] = a[m] - b[m];
+}
+
+template <int K>
+void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& a) {
+    int threads = 256;
+    int grid = plb_grid_for(ctx, M, threads, 8);
+    k_t2g_scatter<K><<<grid, threads, 0, ctx->stream>>>(M, x, a);
+}
+
+}  // namespace
+
+extern "C" {
+
+int plb_marker_minmax(plb_ctx* ctx, long long M, const double* d_tr_x, double* h_out) {
+    if (!ctx || M <= 0) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (plb_ws_reserve(ctx, 64)) return 2;
+    double* d = (double*)ctx->ws;
+    k_minmax_init<<<1, 1, 0, ctx->stream>>>(d);
+    PLB_LAUNCHED(ctx);
+    k_marker_minmax<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d);
+    PLB_LAUNCHED(ctx);
+    PLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, d, 4 * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // order: zmin, zmax, xmin, xmax
+    for (int i = 0; i < 4; i++) h_out[i] = ctx->h_pinned[i];
+    return 0;
+}
+
+int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
+                  const double* const* h_fields, const int* h_scheme, const double* d_axis_z,
+                  int nze, const double* d_axis_x, int nxe, double z0, double zlen, double x0,
+                  double xlen, int crop_z0, int crop_x0, int nz, int nxx, int ld,
+                  double* const* h_out) {
+    if (!ctx) return 1;
+    if (k < 1 || k > PLB_MAX_FIELDS) PLB_FAIL(ctx, "plb_trac2grid: k=%d out of range 1..%d", k, PLB_MAX_FIELDS);
+    if (crop_z0 + nz > nze || crop_x0 + nxx > nxe) PLB_FAIL(ctx, "plb_trac2grid: crop outside extended grid");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    T2GArgs a;
+    memset(&a, 0, sizeof(a));
+    bool any_w = false, any_c = false;
+    for (int f = 0; f < k; f++) {
+        int sc = h_scheme[f];
+        if (!(sc & (PLB_AVG_ARITHMETIC | PLB_AVG_GEOMETRIC)))
+            PLB_FAIL(ctx, "plb_trac2grid: invalid averaging scheme %d", sc);
+        (sc & PLB_AVG_WEIGHTED) ? any_w = true : any_c = true;
+        a.f[f] = h_fields[f];
+        a.out[f] = h_out[f];
+        a.scheme[f] = sc;
+    }
+    size_t plane = (size_t)nze * nxe;
+    size_t nplanes = k + (any_w ? 1 : 0) + (any_c ? 1 : 0);
+    if (plb_ws_reserve(ctx, nplanes * plane * sizeof(double))) return 2;
+    double* w = (double*)ctx->ws;
+    for (int f = 0; f < k; f++) a.acc[f] = w + (size_t)f * plane;
+    size_t nxt = k;
+    if (any_w) a.wsum = w + (nxt++) * plane;
+    if (any_c) a.cnt = w + (nxt++) * plane;
+    a.axz = d_axis_z, a.axx = d_axis_x, a.nze = nze, a.nxe = nxe;
+    a.z0 = z0, a.zlen = zlen, a.x0 = x0, a.xlen = xlen, a.k = k;
+    PLB_CUDA(ctx, cudaMemsetAsync(w, 0, nplanes * plane * sizeof(double), ctx->stream));
+    if (M > 0) {
+        const double2* x = (const double2*)d_tr_x;
+        switch (k) {
+            case 1: launch_scatter<1>(ctx, M, x, a); break;
+            case 2: launch_scatter<2>(ctx, M, x, a); break;
+            case 3: launch_scatter<3>(ctx, M, x, a); break;
+            case 4: launch_scatter<4>(ctx, M, x, a); break;
+            case 5: launch_scatter<5>(ctx, M, x, a); break;
+            case 6: launch_scatter<6>(ctx, M, x, a); break;
+            case 7: launch_scatter<7>(ctx, M, x, a); break;
+            default: launch_scatter<8>(ctx, M, x, a); break;
+        }
+        PLB_LAUNCHED(ctx);
+    }
+    k_t2g_finalise<<<plb_grid_for(ctx, (long long)nz * nxx, 256, 8), 256, 0, ctx->stream>>>(
+        a, crop_z0, crop_x0, nz, nxx, ld);
+    PLB_LAUNCHED(ctx);
+    return 0;
+}
+
+int plb_grid2trac(plb_ctx* ctx, long long M, const double* d_tr_x, int method, int k,
+                  const double* const* h_fields, const double* d_grid_z, int nz,
+                  const double* d_grid_x, int nxx, int ld, double z0, double zlen, double x0,
+                  double xlen, double defval, double* const* h_out, long long* h_n_outside) {
+    if (!ctx) return 1;
+    if (k < 1 || k > PLB_MAX_FIELDS) PLB_FAIL(ctx, "plb_grid2trac: k=%d out of range", k);
+    if (!(method & (PLB_METHOD_NEAREST | PLB_METHOD_LINEAR | PLB_METHOD_VELDIV)))
+        PLB_FAIL(ctx, "plb_grid2trac: unknown method %d", method);
+    if ((method & PLB_METHOD_VELDIV) && !(method & (PLB_METHOD_NEAREST | PLB_METHOD_LINEAR)) && k != 2)
+        PLB_FAIL(ctx, "grid2trac(): method INTERP_METHOD_VELDIV only works in 2D and expects field to be (vz,vx)");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (plb_ws_reserve(ctx, 64)) return 2;
+    unsigned long long* d_bad = (unsigned long long*)ctx->ws;
+    PLB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->stream));
+    G2TGrid g = {d_grid_z, d_grid_x, nz, nxx, ld, z0, zlen, x0, xlen};
+    G2TArgs a;
+    memset(&a, 0, sizeof(a));
+    a.k = k;
+    for (int f = 0; f < k; f++) a.f[f] = h_fields[f], a.out[f] = h_out[f];
+    if (M > 0) {
+        k_grid2trac<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
+            M, (const double2*)d_tr_x, method, g, a, defval, d_bad);
+        PLB_LAUNCHED(ctx);
+    }
+    if (h_n_outside) {
+        unsigned long long* hp = (unsigned long long*)ctx->h_pinned;
+        PLB_CUDA(ctx, cudaMemcpyAsync(hp, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *h_n_outside = (long long)*hp;
+    }
+    return 0;
+}
+
+int plb_rk4(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_vz_c,
+            const double* d_vx_c, const double* d_gc_z, int nzc, const double* d_gc_x, int nxc,
+            int ld, double z0, double zlen, double x0, double xlen, double dt, double* d_x_out,
+            double* d_v_out) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    G2TGrid g = {d_gc_z, d_gc_x, nzc, nxc, ld, z0, zlen, x0, xlen};
+    if (M > 0) {
+        k_rk4<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
+            M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, dt, (double2*)d_x_out, (double2*)d_v_out);
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int plb_fence(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (M > 0) {
+        k_fence<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, (double2*)d_tr_x, Lz, Lx, eps);
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int plb_cell_index_count(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, int nxx,
+                         double Lz, double Lx, long long* d_kelem, long long* d_count) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d_count)
+        PLB_CUDA(ctx, cudaMemsetAsync(d_count, 0, (size_t)(nz - 1) * (nxx - 1) * sizeof(long long),
+                                      ctx->stream));
+    if (M > 0) {
+        k_cell_index_count<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
+            M, (const double2*)d_tr_x, nz, nxx, Lz, Lx, d_kelem, (unsigned long long*)d_count);
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int plb_update_properties(plb_ctx* ctx, long long M, int tdep_rho, int tdep_eta, double Tref,
+                          double etamin, double etamax, double gasr, const double* d_T,
+                          const double* d_rho0, const double* d_alpha, const double* d_Ea,
+                          const double* d_eta0, double* d_rho, double* d_eta) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (M > 0) {
+        k_update_properties<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
+            M, tdep_rho, tdep_eta, Tref, etamin, etamax, gasr, d_T, d_rho0, d_alpha, d_Ea, d_eta0,
+            d_rho, d_eta);
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int plb_subgrid_stage1(plb_ctx* ctx, long long M, double dt, double dz, double dx,
+                       const double* d_Told, const double* d_T, const double* d_cp,
+                       const double* d_rho, const double* d_k, double* d_Tsg, double* d_dT) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double fac = (2 / dx) * (2 / dx) + (2 / dz) * (2 / dz);                    // pylamp2.py:473
+    if (M > 0) {
+        k_subgrid1<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, dt, fac, d_Told, d_T, d_cp,
+                                                                       d_rho, d_k, d_Tsg, d_dT);
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int plb_subgrid_stage2(plb_ctx* ctx, long long M, const double* d_Tsg, const double* d_back,
+                       double* d_T) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (M > 0) {
+        k_sub<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, d_Tsg, d_back, d_T);   // :480
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""Device-resident wrappers for the driver-inline steps of the reference loop body
+(pylamp2.py:291-303, :339-366, :471-480, :491-545, :558-572, :588-593).  All arguments are torch
+CUDA float64 tensors; everything runs in the CUDA library (no CPU path)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .pylamp_const import EPS, GASR, IX, IZ
+
+
+def _ctx(t):
+    return _lib.default_context(t.device.index)
+
+
+def cell_index_count(tr_x, nx, L, want_kelem=True):
+    """kelem (M,) int64 and per-cell count ((nz-1)*(nxx-1),) int64 -- pylamp2.py:588-593."""
+    ctx = _ctx(tr_x)
+    M = tr_x.shape[0]
+    nz, nxx = int(nx[IZ]), int(nx[IX])
+    kelem = torch.empty(M, dtype=torch.int64, device=tr_x.device) if want_kelem else None
+    count = torch.empty((nz - 1) * (nxx - 1), dtype=torch.int64, device=tr_x.device)
+    ctx.call("plb_cell_index_count", M, tr_x.data_ptr(), nz, nxx, float(L[IZ]), float(L[IX]),
+             kelem.data_ptr() if want_kelem else None, count.data_ptr())
+    return kelem, count
+
+
+def fence(tr_x, L, eps=EPS):
+    """In-place fence to [eps, L-eps] -- pylamp2.py:558-572 (no FLOWTHRU / CYCLIC walls)."""
+    _ctx(tr_x).call("plb_fence", tr_x.shape[0], tr_x.data_ptr(), float(L[IZ]), float(L[IX]), float(eps))
+
+
+def update_properties(T, rho0, alpha, Ea, eta0, tdep_rho, tdep_eta, Tref, etamin, etamax,
+                      rho_out=None, eta_out=None):
+    """rho(T), eta(T) on markers -- pylamp2.py:291-303."""
+    ctx = _ctx(T)
+    rho = rho_out if rho_out is not None else torch.empty_like(T)
+    eta = eta_out if eta_out is not None else torch.empty_like(T)
+    ctx.call("plb_update_properties", T.shape[0], int(bool(tdep_rho)), int(bool(tdep_eta)),
+             float(Tref), float(etamin), float(etamax), float(GASR), T.data_ptr(), rho0.data_ptr(),
+             alpha.data_ptr(), Ea.data_ptr(), eta0.data_ptr(), rho.data_ptr(), eta.data_ptr())
+    return rho, eta
+
+
+def centre_velocities(vz, vx, bc):
+    """(nz+1, nxx+1) cell-centre velocities with the BC ghost ring -- pylamp2.py:491-545."""
+    ctx = _ctx(vz)
+    nz, nxx = vz.shape
+    vzc = torch.empty((nz + 1, nxx + 1), dtype=torch.float64, device=vz.device)
+    vxc = torch.empty_like(vzc)
+    ctx.call("plb_centre_velocities", nz, nxx, vz.stride(0), vz.data_ptr(), vx.data_ptr(),
+             _lib.int_array(bc), nxx + 1, vzc.data_ptr(), vxc.data_ptr())
+    return vzc, vxc
+
+
+def field_max(f):
+    """Signed maximum of a 2-D field (np.max of pylamp2.py:364, quirk 6)."""
+    out = C.c_double(0)
+    _ctx(f).call("plb_field_max", f.shape[0], f.shape[1], f.stride(0), f.data_ptr(), C.byref(out))
+    return out.value
+
+
+def max_diffusivity2(kz, rho, cp):
+    """max(2*kz/(rho*cp)) -- pylamp2.py:340."""
+    out = C.c_double(0)
+    _ctx(kz).call("plb_max_diffusivity2", kz.shape[0], kz.shape[1], kz.stride(0), kz.data_ptr(),
+                  rho.data_ptr(), cp.data_ptr(), C.byref(out))
+    return out.value
+
+
+def subgrid_stage1(dt, dz, dx, Told, T, cp, rho, k):
+    """Tsg, dT of pylamp2.py:472-475."""
+    Tsg, dT = torch.empty_like(T), torch.empty_like(T)
+    _ctx(T).call("plb_subgrid_stage1", T.shape[0], float(dt), float(dz), float(dx), Told.data_ptr(),
+                 T.data_ptr(), cp.data_ptr(), rho.data_ptr(), k.data_ptr(), Tsg.data_ptr(),
+                 dT.data_ptr())
+    return Tsg, dT
+
+
+def subgrid_stage2(Tsg, back, T_out):
+    """T = Tsg - back, pylamp2.py:480."""
+    _ctx(Tsg).call("plb_subgrid_stage2", Tsg.shape[0], Tsg.data_ptr(), back.data_ptr(), T_out.data_ptr())

@@ -1,0 +1,170 @@
+"""GPU parity: marker kernels (trac2grid / grid2trac / RK / fence / cell index+count / property
+update / centre velocities) through the C-ABI versus the oracle and the committed golden vectors
+of the unmodified reference.
+
+Tolerances: cell indices and per-cell counts BIT-EXACT; grid2trac / RK positions 1e-10 relative
+(north_star) -- in practice ~1e-15; trac2grid sums differ from np.add.at only by fp64 summation
+order (atomics), asserted to 1e-12 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pylamp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    from pylamp_b200 import pylamp_trac
+    return pylamp_trac
+
+
+def _rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+def test_trac2grid_golden(T, golden_kernels):
+    g = golden_kernels
+    nx, L = list(g["nx"]), list(g["L"])
+    grid, mesh, gridmp, meshmp = O.make_grids(nx, L)
+    gf = [np.zeros(nx) for _ in range(6)]
+    T.trac2grid(g["tr_x"], g["tr_vals"], mesh, grid, gf, nx, avgscheme=list(g["t2g_nodes_scheme"]))
+    ref = g["t2g_nodes"]
+    assert np.array_equal(np.isnan(np.array(gf)), np.isnan(ref))
+    assert np.allclose(np.array(gf), ref, rtol=1e-12, atol=0, equal_nan=True)
+    targets = {"cc": ([gridmp[0], gridmp[1]], meshmp),
+               "zmid": ([gridmp[0], grid[1]], [meshmp[0], mesh[1]]),
+               "xmid": ([grid[0], gridmp[1]], [mesh[0], meshmp[1]])}
+    for name, (gr, m) in targets.items():
+        gf = [np.zeros(nx) for _ in range(2)]
+        T.trac2grid(g["tr_x"], g["tr_vals"][:, :2], m, gr, gf, nx, avgscheme=[6, 2])
+        assert np.allclose(np.array(gf), g["t2g_" + name], rtol=1e-12, atol=0, equal_nan=True), name
+
+
+def test_grid2trac_rk_golden(T, golden_kernels, capsys):
+    g = golden_kernels
+    nx, L = list(g["nx"]), list(g["L"])
+    grid, mesh, gridmp, meshmp = O.make_grids(nx, L)
+    F = list(g["g2t_fields"])
+    M = g["tr_x"].shape[0]
+    for m, name in ((16, "linear"), (8, "nearest")):
+        a = np.zeros((M, 2))
+        T.grid2trac(g["tr_x"], a, grid, F, nx, method=m)
+        assert np.allclose(a, g["g2t_" + name], rtol=1e-13, atol=1e-300)
+        a = np.zeros((M, 2))
+        T.grid2trac(g["g2t_x_outside"], a, grid, F, nx, method=m, defval=-7.5)
+        assert np.allclose(a, g["g2t_" + name + "_outside"], rtol=1e-13, atol=1e-300)
+    with pytest.raises(Exception, match="stopOnError"):
+        T.grid2trac(g["g2t_x_outside"], np.zeros((M, 2)), grid, F, nx, stopOnError=True)
+    with pytest.raises(Exception, match="VELDIV"):
+        T.grid2trac(g["tr_x"], np.zeros((M, 1)), grid, F[:1], nx, method=32)
+    a = np.zeros((M, 2))
+    T.grid2trac(g["tr_x"], a, [g["rk_grid_z"], g["rk_grid_x"]], list(g["rk_vels"]),
+                [nx[0] + 1, nx[1] + 1], defval=0, method=32)
+    assert np.allclose(a, g["g2t_veldiv"], rtol=1e-12, atol=1e-300)
+    v, x = T.RK(g["tr_x"], [g["rk_grid_z"], g["rk_grid_x"]], list(g["rk_vels"]), nx, float(g["rk_tstep"]))
+    assert _rel(x, g["rk_x"]) < 1e-10 and np.allclose(x, g["rk_x"], rtol=1e-10, atol=0)
+    assert _rel(v, g["rk_vel"]) < 1e-9
+    with pytest.raises(Exception, match="don't know"):
+        T.RK(g["tr_x"], None, None, nx, 1.0, order=3)
+
+
+def test_strided_view_written_in_place(T, golden_kernels):
+    """pylamp2.py:445 passes tr_f[IPROC::NPROC] style views: the result must land in the view."""
+    g = golden_kernels
+    nx, L = list(g["nx"]), list(g["L"])
+    grid = O.make_grids(nx, L)[0]
+    M = g["tr_x"].shape[0]
+    big = np.full((M, 3), -1.0)
+    T.grid2trac(g["tr_x"][::2], big[::2, 1:3], grid, list(g["g2t_fields"]), nx, method=16)
+    assert np.allclose(big[::2, 1:3], g["g2t_linear"][::2], rtol=1e-13)
+    assert np.all(big[1::2] == -1.0) and np.all(big[:, 0] == -1.0)
+
+
+@pytest.mark.parametrize("nxL", [([17, 9], [2.0, 0.5]), ([201, 41], [1.0, 0.2]), ([1025, 1025], [1e6, 1e6])])
+def test_cell_index_count_bit_exact(nxL):
+    from pylamp_b200 import markers
+    nx, L = nxL
+    rng = np.random.default_rng(5)
+    x = rng.random((300000, 2)) * L
+    # adversarial positions: exactly on nodes and one ulp either side
+    nodes = np.linspace(0, L[0], nx[0])[1:-1]
+    k = min(len(nodes), 1000)
+    x[:k, 0] = nodes[:k]
+    x[k:2 * k, 0] = np.nextafter(nodes[:k], 0)
+    x[2 * k:3 * k, 0] = np.nextafter(nodes[:k], np.inf)
+    kelem, count = O.cell_index_count(x, nx, L)
+    kd, cd = markers.cell_index_count(torch.as_tensor(x).cuda(), nx, L)
+    assert np.array_equal(kd.cpu().numpy(), kelem)
+    assert np.array_equal(cd.cpu().numpy(), count)
+
+
+def test_fence_properties_centre(golden_kernels):
+    from pylamp_b200 import markers
+    g = golden_kernels
+    rng = np.random.default_rng(2)
+    L = [1.0, 0.2]
+    x = (rng.random((50000, 2)) * 1.2 - 0.1) * L
+    x[:10] = 0.0
+    x[10:20] = L
+    ref = x.copy()
+    O.fence(ref, np.zeros((x.shape[0], O.NFTRAC)), L, [1, 1, 1, 1])
+    xd = torch.as_tensor(x).cuda()
+    markers.fence(xd, L)
+    assert np.array_equal(xd.cpu().numpy(), ref)
+    # property update, pylamp2.py:291-303
+    M = 20000
+    tr_f = np.zeros((M, O.NFTRAC))
+    tr_f[:, O.TR_TMP] = rng.uniform(273, 1900, M)
+    tr_f[:, O.TR_RH0] = rng.uniform(2500, 3400, M)
+    tr_f[:, O.TR_ALP] = 3.5e-5
+    tr_f[:, O.TR_ACE] = rng.uniform(0, 300e3, M)
+    tr_f[:, O.TR_ET0] = 10 ** rng.uniform(18, 22, M)
+    for tr, te in ((True, True), (False, False)):
+        ref = tr_f.copy()
+        O.update_properties(ref, tr, te, 1623, 1e17, 1e23)
+        cols = {k: torch.as_tensor(np.ascontiguousarray(tr_f[:, k])).cuda()
+                for k in (O.TR_TMP, O.TR_RH0, O.TR_ALP, O.TR_ACE, O.TR_ET0)}
+        rho, eta = markers.update_properties(cols[O.TR_TMP], cols[O.TR_RH0], cols[O.TR_ALP],
+                                             cols[O.TR_ACE], cols[O.TR_ET0], tr, te, 1623, 1e17, 1e23)
+        assert np.allclose(rho.cpu().numpy(), ref[:, O.TR_RHO], rtol=1e-14)
+        assert np.allclose(eta.cpu().numpy(), ref[:, O.TR_ETA], rtol=1e-12)
+    # centre velocities + ring
+    nx = list(g["nx"])
+    gridmp = O.make_grids(nx, list(g["L"]))[2]
+    for bc in ([1, 1, 1, 1], [0, 1, 0, 1], [1, 1, 0, 1]):
+        ng, vels = O.centre_velocities(list(g["rk_newvel"]), gridmp, nx, bc)
+        vz, vx = markers.centre_velocities(torch.as_tensor(g["rk_newvel"][0]).cuda(),
+                                           torch.as_tensor(g["rk_newvel"][1]).cuda(), bc)
+        assert np.array_equal(vz.cpu().numpy(), vels[0]) and np.array_equal(vx.cpu().numpy(), vels[1])
+
+
+def test_large_random_cloud_vs_oracle(T):
+    """1025^2-node grid, 4 M markers: trac2grid (all four staggered targets) + RK vs the oracle."""
+    rng = np.random.default_rng(3)
+    nx, L = [513, 385], [1.0, 0.75]
+    grid, mesh, gridmp, meshmp = O.make_grids(nx, L)
+    M = 2_000_000
+    x = rng.random((M, 2)) * L
+    f = np.stack([rng.uniform(1, 2, M), 10 ** rng.uniform(18, 24, M)], axis=1)
+    for gr, sch in (([grid[0], grid[1]], [5, 6]), ([gridmp[0], gridmp[1]], [1, 2]),
+                    ([gridmp[0], grid[1]], [5, 6]), ([grid[0], gridmp[1]], [5, 6])):
+        ref = [np.zeros(nx), np.zeros(nx)]
+        O.trac2grid(x, f, None, gr, ref, nx, avgscheme=sch)
+        out = [np.zeros(nx), np.zeros(nx)]
+        T.trac2grid(x, f, None, gr, out, nx, avgscheme=sch)
+        for a, b in zip(out, ref):
+            assert np.array_equal(np.isnan(a), np.isnan(b))
+            assert np.allclose(a, b, rtol=1e-11, atol=0, equal_nan=True)
+    # divergence-free-ish velocity field, RK
+    zc, xc = np.meshgrid(np.arange(nx[0]) / (nx[0] - 1), np.arange(nx[1]) / (nx[1] - 1), indexing="ij")
+    newvel = [np.sin(np.pi * zc) * np.cos(np.pi * xc), -np.cos(np.pi * zc) * np.sin(np.pi * xc)]
+    ng, vels = O.centre_velocities(newvel, gridmp, nx, [1, 1, 1, 1])
+    dt = 0.67 * (L[0] / (nx[0] - 1))
+    vr, xr = O.RK(x, ng, vels, nx, dt)
+    vg, xg = T.RK(x, ng, vels, nx, dt)
+    assert np.allclose(xg, xr, rtol=1e-10, atol=0)
+    assert _rel(vg, vr) < 1e-9
