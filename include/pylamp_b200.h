@@ -139,10 +139,22 @@ int plb_stokes_rhs(plb_stokes* op, double* d_rhs);
 /* y = A x, both interleaved [vz,vx,P] per node, length 3*nz*nxx (what A_ref @ x gives) */
 int plb_stokes_apply(plb_stokes* op, const double* d_x, double* d_y);
 /* replaces scipy.sparse.linalg.spsolve(csc_matrix(A), rhs) at pylamp2.py:360: solves A x = rhs
- * (rhs from plb_stokes_rhs) with preconditioned Krylov + geometric multigrid.  x interleaved.
- * rtol on the scaled true residual.  Returns non-zero if not converged within maxit. */
-int plb_stokes_solve(plb_stokes* op, double rtol, int maxit, double* d_x, int* h_iters,
-                     double* h_relres);
+ * with flexible GCR + geometric multigrid.  d_rhs: interleaved right-hand side (NULL = the
+ * system's own, as plb_stokes_rhs gives).  x interleaved like the reference's solution vector.
+ * rtol is on the true residual in the viscosity-scaled norm (rows weighted by 1/sqrt|diag| resp.
+ * sqrt(eta)/Kcont).  Returns non-zero (and still writes x) if not converged within maxit. */
+int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit, double* d_x,
+                     int* h_iters, double* h_relres);
+/* solver tuning: "nu" (Chebyshev steps per smoothing, default 3), "gcr_m" (truncation window, 30),
+ * "coarsen_wide" (1: 4x4-cell viscosity averaging, stable with sharp contrasts; 0: 2x2),
+ * "cheb_ratio" (8), "dense_max" (largest coarse level solved by a dense inverse, 640),
+ * "nu_coarse" (60), "reorth" (0/1 second Gram-Schmidt pass) */
+int plb_stokes_set_param(plb_stokes* op, const char* name, double value);
+/* test hook: one multigrid V-cycle x = V(b) on the velocity block; b, x are two planes
+ * [vz | vx] of nz*nxx doubles each */
+int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2);
+/* h_out[3] = {Krylov iterations, V-cycles, final scaled relative residual} of the last solve */
+int plb_stokes_last_stats(plb_stokes* op, double* h_out);
 /* x2vp, pylamp_stokes.py:86-101: de-interleave into three (nz x ld) planes */
 int plb_x2vp(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_x, double* d_vz,
              double* d_vx, double* d_p);

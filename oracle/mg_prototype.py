@@ -466,3 +466,174 @@ def solve_refine(mg, err_tol=1e-10, inner_rtol=1e-5, max_outer=8, maxit=200, ver
         d, its, rr = bicgstab(Aop, r, Mop, inner_rtol, maxit)
         x = x + d
     return lv.E @ x, calls[0]
+
+
+# ---------------------------------------------------------------------------------------
+# second design iteration: arithmetic coarsening variants, scaled Krylov norm, inner GCR
+# (the CUDA solver in pylamp_b200/csrc/stokes.cu follows MG2 with ms='fw', mn='4x4'|'2x2',
+#  smoother='cheb', nu=3 and solve_scaled(ncyc=1))
+# ---------------------------------------------------------------------------------------
+from pylamp_b200 import setups  # noqa: E402
+
+def coarsen(etas, etan, ms, mn):
+    nz, nxx = etas.shape
+    nzc, nxc = (nz-1)//2+1, (nxx-1)//2+1
+    # nodes
+    Lp = np.pad(etas, 1, mode='edge')
+    def win(a,b): return Lp[a:a+nz:2, b:b+nxx:2][:nzc,:nxc]
+    if ms=='inj': es = etas[::2,::2].copy()
+    elif ms=='fw':
+        w = np.array([[1,2,1],[2,4,2],[1,2,1]])/16.
+        es = sum(w[a,b]*win(a,b) for a in range(3) for b in range(3))
+    elif ms=='max':
+        es = np.max([win(a,b) for a in range(3) for b in range(3)],axis=0)
+    elif ms=='geom':
+        w = np.array([[1,2,1],[2,4,2],[1,2,1]])/16.
+        es = np.exp(sum(w[a,b]*np.log(win(a,b)) for a in range(3) for b in range(3)))
+    # centres: real cells [0:nz-1, 0:nxx-1]
+    c = etan[:nz-1,:nxx-1]
+    ncz, ncx = nzc-1, nxc-1
+    if mn=='2x2':
+        ec = 0.25*(c[0::2,0::2]+c[1::2,0::2]+c[0::2,1::2]+c[1::2,1::2])
+    elif mn=='geom':
+        ec = np.exp(0.25*(np.log(c[0::2,0::2])+np.log(c[1::2,0::2])+np.log(c[0::2,1::2])+np.log(c[1::2,1::2])))
+    else:
+        cp = np.pad(c, 1, mode='edge')   # cp[k] = c[k-1]
+        def w4(a,b): return cp[a:a+2*ncz:2, b:b+2*ncx:2]  # rows 2I-1+a
+        if mn=='4x4':
+            w1 = np.array([1,3,3,1])/8.
+            ec = sum(w1[a]*w1[b]*w4(a,b) for a in range(4) for b in range(4))
+        elif mn=='max':
+            ec = np.max([w4(a,b) for a in range(4) for b in range(4)],axis=0)
+    en = np.ones((nzc,nxc))*ec.mean(); en[:ncz,:ncx]=ec
+    return es, en
+
+class MG2(MG):
+    def __init__(self, nz, nxx, gz, gx, etas, etan, rho, bc, ms='fw', mn='4x4', smoother='cheb', nu=3, min_cells=4, minres=False, cheb_ratio=8.0):
+        self.levels=[]; self.P=[]; self.smoother=smoother; self.nu=nu; self.minres=minres; self.cheb_ratio=cheb_ratio
+        first=True
+        while True:
+            self.levels.append(Level(nz,nxx,gz,gx,etas,etan,rho,bc) if first else ProperLevel(nz,nxx,gz,gx,etas,etan))
+            first=False
+            if (nz-1)%2 or (nxx-1)%2 or min(nz-1,nxx-1)//2 < min_cells: break
+            etas, etan = coarsen(etas, etan, ms, mn)
+            rho = rho[::2,::2]; gz, gx = gz[::2], gx[::2]
+            nz, nxx = (nz-1)//2+1, (nxx-1)//2+1
+        for a,b in zip(self.levels[:-1], self.levels[1:]): self.P.append(transfer(a,b))
+        self.lu = spla.splu(self.levels[-1].K.tocsc())
+        self.lmax=[]
+        for lv in self.levels:
+            x=np.random.default_rng(0).normal(size=lv.nv)
+            for _ in range(20):
+                x=(lv.K@x)/lv.Kdiag; lam=np.linalg.norm(x); x/=lam
+            self.lmax.append(lam*1.1)
+        if smoother=='cgs':
+            self.colors=[]
+            for lv in self.levels:
+                I=lv.I; node=I//3; eq=I%3; i=node//lv.nxx; j=node%lv.nxx
+                col = eq*2 + (i+j)%2
+                self.colors.append([ (np.where(col==c)[0], lv.K[np.where(col==c)[0]]) for c in range(4)])
+    def smooth(self,l,x,b,nu,post=False):
+        lv=self.levels[l]
+        if self.smoother=='cgs':
+            order = range(4) if not post else range(3,-1,-1)
+            for _ in range(nu):
+                for c in order:
+                    idx,Kc = self.colors[l][c]
+                    x[idx] += (b[idx]-Kc@x)/lv.Kdiag[idx]
+            return x
+        if self.smoother=='cheb':
+            lmax=self.lmax[l]; lmin=lmax/self.cheb_ratio
+            theta,delta=0.5*(lmax+lmin),0.5*(lmax-lmin); sigma=theta/delta; rho_=1/sigma
+            r=(b-lv.K@x)/lv.Kdiag; d=r/theta
+            for k in range(nu):
+                x=x+d
+                if k==nu-1: break
+                r=(b-lv.K@x)/lv.Kdiag
+                rho_new=1/(2*sigma-rho_); d=rho_new*rho_*d+2*rho_new/delta*r; rho_=rho_new
+            return x
+        return MG.smooth(self,l,x,b,nu,post)
+    def vcycle(self,l,b):
+        lv=self.levels[l]
+        if l==len(self.levels)-1: return self.lu.solve(b)
+        x=self.smooth(l,np.zeros_like(b),b,self.nu)
+        r=b-lv.K@x
+        ec=self.vcycle(l+1, 0.25*(self.P[l].T@r))
+        e=self.P[l]@ec
+        if self.minres:
+            Ke=lv.K@e; a=(r@Ke)/(Ke@Ke); e=a*e
+        x=x+e
+        return self.smooth(l,x,b,self.nu,post=True)
+
+def fields(case,n):
+    nx, L, grid, gridmp, etas, etan, rho = setups.solcx_fields(n)
+    zs, xs = np.meshgrid(grid[0], grid[1], indexing="ij")
+    zc, xc = np.meshgrid(gridmp[0], gridmp[1], indexing="ij")
+    if case=='const': etas[:]=1; etan[:]=1
+    if case=='incl':
+        f=lambda z,x: np.where((z-0.3)**2+(x-0.5)**2<0.1**2,1e6,1.0)
+        etas=f(zs,xs); etan=f(zc,xc); rho=np.where((zs-0.3)**2+(xs-0.5)**2<0.1**2,1.1,1.0)
+    if case=='sinkers':
+        rng=np.random.default_rng(3); cz=rng.uniform(0.1,0.9,8); cx=rng.uniform(0.1,0.9,8)
+        def f(z,x):
+            m=np.zeros_like(z,bool)
+            for a,b in zip(cz,cx): m|=((z-a)**2+(x-b)**2<0.05**2)
+            return m
+        etas=np.where(f(zs,xs),1e4,1.0); etan=np.where(f(zc,xc),1e4,1.0); rho=np.where(f(zs,xs),1.2,1.0)
+    if case=='arrh':
+        T=lambda z,x: 273+1350*z+0.05*1350*np.sin(np.pi*z)*np.cos(np.pi*x)
+        e=lambda T: np.clip(1e20*np.exp(120e3/(8.314*T)-120e3/(8.314*1623)),1e17,1e23)
+        etas=e(T(zs,xs)); etan=e(T(zc,xc)); rho=3300/(3.5e-5*(T(zs,xs)-1623)+1)
+    if case=='smallincl':
+        f=lambda z,x: np.where((z-0.3)**2+(x-0.5)**2<(2.2/(n-1))**2,1e10,1.0)
+        etas=f(zs,xs); etan=f(zc,xc); rho=np.where((zs-0.3)**2+(xs-0.5)**2<(2.2/(n-1))**2,1.1,1.0)
+    return nx,L,grid,gridmp,etas,etan,rho
+
+def solve_scaled(mg, tol=1e-12, m=50, maxit=150, ncyc=1, scaled=True, inner_gmres=0):
+    lv=mg.levels[0]; nv=lv.nv
+    sd = lv.Kc**2/lv.eta_p
+    if scaled:
+        W=np.concatenate([1/np.sqrt(np.abs(lv.Kdiag)), 1/np.sqrt(sd)])
+    else:
+        W=np.ones(lv.Ar.shape[0])
+    def Aop(y): return W*(lv.Ar@(W*y))
+    def Ksolve(rv):
+        dv=mg.vcycle(0,rv)
+        for _ in range(ncyc-1): dv=dv+mg.vcycle(0,rv-lv.K@dv)
+        return dv
+    def M(r):
+        dp=r[nv:]/sd; dv=Ksolve(r[:nv]-lv.G@dp); return np.concatenate([dv,dp])
+    def Mop(rh): return M(rh/W)/W
+    xh,its,hist=fgmres(Aop, W*lv.b, Mop, m=m, tol=tol, maxit=maxit)
+    return lv.E@(W*xh), its, hist
+
+def gcr(Aop, b, Mop, k, rtol=0.0):
+    """k steps of GCR (flexible), x0=0"""
+    x=np.zeros_like(b); r=b.copy(); Zs=[]; Cs=[]; r0=np.linalg.norm(b)
+    for i in range(k):
+        z=Mop(r); c=Aop(z)
+        for zj,cj in zip(Zs,Cs):
+            a=cj@c; c=c-a*cj; z=z-a*zj
+        nc=np.linalg.norm(c); c/=nc; z/=nc
+        a=c@r; x+=a*z; r-=a*c; Zs.append(z); Cs.append(c)
+        if np.linalg.norm(r)<rtol*r0: break
+    return x, i+1
+
+def solve_inner(mg, tol=1e-12, m=50, maxit=150, kin=4, rtol_in=0.0, mode='upper'):
+    lv=mg.levels[0]; nv=lv.nv
+    sd = lv.Kc**2/lv.eta_p
+    W=np.concatenate([1/np.sqrt(np.abs(lv.Kdiag)), 1/np.sqrt(sd)])
+    Wv=W[:nv]
+    nV=[0]
+    def Aop(y): return W*(lv.Ar@(W*y))
+    def Vc(r): nV[0]+=1; return mg.vcycle(0,r)
+    def Ksolve(rv):
+        if kin<=1: return Vc(rv)
+        # scaled inner GCR: minimise ||Wv (rv - K dv)||
+        dv,_=gcr(lambda y: Wv*(lv.K@(Wv*y)), Wv*rv, lambda r: Vc(r/Wv)/Wv, kin, rtol_in)
+        return Wv*dv
+    def M(r):
+        dp=r[nv:]/sd; dv=Ksolve(r[:nv]-lv.G@dp); return np.concatenate([dv,dp])
+    def Mop(rh): return M(rh/W)/W
+    xh,its,hist=fgmres(Aop, W*lv.b, Mop, m=m, tol=tol, maxit=maxit)
+    return lv.E@(W*xh), its, hist, nV[0]

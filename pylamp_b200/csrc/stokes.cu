@@ -1,0 +1,1079 @@
+// stokes.cu -- the reference's Stokes system (pylamp_stokes.makeStokesMatrix, pylamp_stokes.py:
+// 104-563) as matrix-free sm_100a kernels, and the solver that replaces
+// scipy.sparse.linalg.spsolve at pylamp2.py:360: flexible GCR on the BC-eliminated saddle-point
+// system with a block-triangular preconditioner (viscosity-scaled pressure mass + one geometric
+// multigrid V-cycle with Chebyshev-Jacobi smoothing on the velocity block).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "blas1.cuh"
+#include "fgmres.cuh"
+#include "stencil.cuh"
+
+namespace {
+
+constexpr int BX = 32, BY = 8;
+inline dim3 grid2d(int nz, int nxx) { return dim3((nxx + BX - 1) / BX, (nz + BY - 1) / BY); }
+inline dim3 block2d() { return dim3(BX, BY); }
+
+struct Level {
+    int nz = 0, nxx = 0, ld = 0;
+    size_t plane = 0;
+    std::vector<double> gz, gx;
+    double *idz = nullptr, *idzc = nullptr, *idx = nullptr, *idxc = nullptr;
+    const double *etas = nullptr, *etan = nullptr;
+    double *etas_own = nullptr, *etan_own = nullptr;
+    int proper = 0;
+    int vz_i0, vz_i1, vz_j0, vz_j1, vx_i0, vx_i1, vx_j0, vx_j1;
+    double sl_z0 = 1, sl_z1 = 1;
+    int ns_z0 = 0, ns_z1 = 0;
+    double *X = nullptr, *T = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;   // 2 planes each
+    double lmax = 0;
+    LevelDev dev() const {
+        LevelDev L;
+        L.nz = nz, L.nxx = nxx, L.ld = ld;
+        L.idz = idz, L.idzc = idzc, L.idx = idx, L.idxc = idxc;
+        L.etas = etas, L.etan = etan, L.proper = proper;
+        L.vz_i0 = vz_i0, L.vz_i1 = vz_i1, L.vz_j0 = vz_j0, L.vz_j1 = vz_j1;
+        L.vx_i0 = vx_i0, L.vx_i1 = vx_i1, L.vx_j0 = vx_j0, L.vx_j1 = vx_j1;
+        L.sl_z0 = sl_z0, L.sl_z1 = sl_z1;
+        L.ns_z0 = ns_z0, L.ns_z1 = ns_z1;
+        return L;
+    }
+};
+
+}  // namespace
+
+struct plb_stokes {
+    plb_ctx* ctx = nullptr;
+    int nz = 0, nxx = 0, ld = 0;
+    int bc[4] = {1, 1, 1, 1};
+    std::vector<Level> lv;
+    const double* rho = nullptr;
+    double g_z = 9.81, g_x = 0;
+    double Kc = 0, Kb = 0;
+    bool coeffs = false, hierarchy = false;
+    plb_reduce_ws rws{};
+    double* d_scal = nullptr;     // 128 device scalars
+    // dense coarse solve
+    int nc = 0;
+    double* cinv = nullptr;       // nc x nc inverse (row-major)
+    double* cwork = nullptr;
+    // Krylov storage (3 planes per vector)
+    plb_fgmres_ws kry;
+    double *xs = nullptr, *r3 = nullptr, *b3 = nullptr, *t3 = nullptr, *gz_d = nullptr, *gx_d = nullptr;
+    // parameters
+    int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
+    double cheb_ratio = 8.0;
+    double rtol_accept = 0;       // a stalled solve is still accepted below this true residual
+    // statistics of the last solve
+    int last_iters = 0, last_vcycles = 0;
+    double last_relres = 0;
+};
+
+namespace {
+
+// -------------------------------------------------------------------------------------------
+// scaling constants: mineta reduction (pylamp_stokes.py:116-122)
+// -------------------------------------------------------------------------------------------
+__global__ void k_set1(double* p, double v) { *p = v; }
+
+__global__ void __launch_bounds__(256)
+k_min2(long long n, const double* __restrict__ a, const double* __restrict__ b, double* out) {
+    double m = INFINITY;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x)
+        m = fmin(m, fmin(a[t], b[t]));
+    m = warp_min(m);
+    __shared__ double s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) m = fmin(m, s[i]);
+        atomic_min_double(out, m);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// full-row operator in the reference's layout (parity path): y = A x for ALL rows, planar in/out
+// -------------------------------------------------------------------------------------------
+struct FullArgs {
+    const double *gz, *gx;
+    int bz0, bz1;          // z-wall types (NOSLIP / FREESLIP); x-walls are FREESLIP
+    double Kc, Kb;
+};
+
+__global__ void __launch_bounds__(BX* BY)
+k_stokes_full(LevelDev L, FullArgs a, const double* __restrict__ vz, const double* __restrict__ vx,
+              const double* __restrict__ p, double* __restrict__ yz, double* __restrict__ yx,
+              double* __restrict__ yp) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const int nz = L.nz, nxx = L.nxx, ld = L.ld;
+    const long long o = (long long)i * ld + j;
+    const double Kc = a.Kc;
+    // ---- vz row
+    double r;
+    if (j == nxx - 1 || i == 0 || i == nz - 1) {
+        r = Kc * vz[o];                                              // ghost / wall-normal rows
+    } else if (j == 0) {
+        r = Kc * (vz[o] - vz[o + 1]);                                // free slip, x=0
+    } else if (j == nxx - 2) {
+        r = Kc * (vz[o] - vz[o - 1]);                                // free slip, x=L
+    } else {
+        VzCoef c = vz_coef(L, i, j);
+        r = kvz_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idzc[i] * (p[o] - p[o - ld]);
+    }
+    yz[o] = r;
+    // ---- vx row
+    if (i == nz - 1 || j == 0 || j == nxx - 1) {
+        r = Kc * vx[o];
+    } else if (i == 0) {
+        if (a.bz0 == PLB_BC_FREESLIP) {
+            r = Kc * (vx[o] - vx[o + ld]);
+        } else {                                                     // no slip, :163-168
+            double d2 = a.gz[2] - a.gz[0], d1 = a.gz[1] - a.gz[0];
+            r = Kc * (-1 / d2 + (-1) / d1) * vx[o] + Kc * (1 / d2) * vx[o + ld];
+        }
+    } else if (i == nz - 2) {
+        if (a.bz1 == PLB_BC_FREESLIP) {
+            r = Kc * (vx[o] - vx[o - ld]);
+        } else {                                                     // :202-207
+            double d2 = a.gz[nz - 3] - a.gz[nz - 1], d1 = a.gz[nz - 2] - a.gz[nz - 1];
+            r = Kc * (-1 / d2 + (-1) / d1) * vx[o] + Kc * (1 / d2) * vx[o - ld];
+        }
+    } else {
+        VxCoef c = vx_coef(L, i, j);
+        r = kvx_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idxc[j] * (p[o] - p[o - 1]);
+    }
+    yx[o] = r;
+    // ---- pressure row
+    if (i == nz - 1 || j == nxx - 1) {
+        r = Kc * p[o];
+    } else if ((i == 0 || i == nz - 2) && (j == 0 || j == nxx - 2)) {
+        r = (j == 0) ? a.Kb * (p[o + 1] - p[o]) : a.Kb * (p[o - 1] - p[o]);      // :358-369
+    } else if (i == 3 && j == 2) {
+        r = Kc * p[o];                                               // anchor, :525-551
+    } else {
+        r = Kc * (L.idx[j] * (vx[o + 1] - vx[o]) + L.idz[i] * (vz[o + ld] - vz[o]));
+    }
+    yp[o] = r;
+}
+
+// rhs planes (pylamp_stokes.py:429, :490); zero on every non-momentum row
+__global__ void __launch_bounds__(BX* BY)
+k_stokes_rhs(LevelDev L, const double* __restrict__ rho, double g_z, double g_x,
+             double* __restrict__ bz, double* __restrict__ bx, double* __restrict__ bp) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const long long o = (long long)i * L.ld + j;
+    bz[o] = is_vz_row(L, i, j) ? -0.5 * (rho[o] + rho[o + 1]) * g_z : 0.0;
+    bx[o] = is_vx_row(L, i, j) ? -0.5 * (rho[o] + rho[o + L.ld]) * g_x : 0.0;
+    bp[o] = 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+k_interleave(long long n, const double* __restrict__ a, const double* __restrict__ b,
+             const double* __restrict__ c, double* __restrict__ x) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        x[3 * t] = a[t], x[3 * t + 1] = b[t], x[3 * t + 2] = c[t];
+    }
+}
+__global__ void __launch_bounds__(256)
+k_deinterleave(long long n, const double* __restrict__ x, double* __restrict__ a,
+               double* __restrict__ b, double* __restrict__ c) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        a[t] = x[3 * t], b[t] = x[3 * t + 1], c[t] = x[3 * t + 2];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// reduced (BC-eliminated) saddle-point operator with the weighted-norm row scaling
+//   RESID: out = W (b - A x)   else   out = W (A x);   W_v = 1/sqrt|diag K|, W_p = sqrt(eta_n)/Kc
+// x must satisfy the homogeneous BC rows (slaves filled); out is zero on non-rows.
+// -------------------------------------------------------------------------------------------
+template <bool RESID>
+__global__ void __launch_bounds__(BX* BY)
+k_stokes_op(LevelDev L, double Kc, const double* __restrict__ vz, const double* __restrict__ vx,
+            const double* __restrict__ p, const double* __restrict__ bz, const double* __restrict__ bx,
+            const double* __restrict__ bp, double* __restrict__ oz, double* __restrict__ ox,
+            double* __restrict__ op) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const int ld = L.ld;
+    const long long o = (long long)i * ld + j;
+    double r = 0;
+    if (is_vz_row(L, i, j)) {
+        VzCoef c = vz_coef(L, i, j);
+        double a = kvz_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idzc[i] * (p[o] - p[o - ld]);
+        r = (RESID ? bz[o] - a : a) * rsqrt(-c.diag);
+    }
+    oz[o] = r;
+    r = 0;
+    if (is_vx_row(L, i, j)) {
+        VxCoef c = vx_coef(L, i, j);
+        double a = kvx_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idxc[j] * (p[o] - p[o - 1]);
+        r = (RESID ? bx[o] - a : a) * rsqrt(-c.diag);
+    }
+    ox[o] = r;
+    r = 0;
+    if (is_p_row(L, i, j)) {
+        double a = Kc * (L.idx[j] * (vx[o + 1] - vx[o]) + L.idz[i] * (vz[o + ld] - vz[o]));
+        r = (RESID ? bp[o] - a : a) * (sqrt(L.etan[o]) / Kc);
+    }
+    op[o] = r;
+}
+
+// preconditioner, stage 1: dp = S^-1 r_p with S = Kc^2/eta_n (diagonal), and the right-hand side
+// of the velocity-block solve  bv = r_v - G dp   (r = W^-1 r^ un-scaled on the fly)
+__device__ __forceinline__ double dp_at(const LevelDev& L, double Kc, const double* __restrict__ rp, long long o) {
+    return rp[o] * sqrt(L.etan[o]) / Kc;        // (rp/W_p) / (Kc^2/eta) = rp * sqrt(eta)/Kc
+}
+
+__global__ void __launch_bounds__(BX* BY)
+k_precond_rhs(LevelDev L, double Kc, const double* __restrict__ rz, const double* __restrict__ rx,
+              const double* __restrict__ rp, double* __restrict__ zp, double* __restrict__ bvz,
+              double* __restrict__ bvx) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const int ld = L.ld, nz = L.nz, nxx = L.nxx;
+    const long long o = (long long)i * ld + j;
+    double dp = 0;
+    if (i <= nz - 2 && j <= nxx - 2) {
+        bool corner = (i == 0 || i == nz - 2) && (j == 0 || j == nxx - 2);
+        // corner pressures are slaves of their x-neighbour (pylamp_stokes.py:358-369)
+        dp = corner ? dp_at(L, Kc, rp, j == 0 ? o + 1 : o - 1) : dp_at(L, Kc, rp, o);
+    }
+    zp[o] = dp;
+    double b = 0;
+    if (is_vz_row(L, i, j)) {
+        VzCoef c = vz_coef(L, i, j);
+        b = rz[o] * sqrt(-c.diag) + 2 * Kc * L.idzc[i] * (dp_at(L, Kc, rp, o) - dp_at(L, Kc, rp, o - ld));
+    }
+    bvz[o] = b;
+    b = 0;
+    if (is_vx_row(L, i, j)) {
+        VxCoef c = vx_coef(L, i, j);
+        b = rx[o] * sqrt(-c.diag) + 2 * Kc * L.idxc[j] * (dp_at(L, Kc, rp, o) - dp_at(L, Kc, rp, o - 1));
+    }
+    bvx[o] = b;
+}
+
+// -------------------------------------------------------------------------------------------
+// multigrid on the velocity block K
+// -------------------------------------------------------------------------------------------
+// one Chebyshev-Jacobi step:  r = D^-1 (b - K x);  d = cd*d + cr*r;  xout = x + d
+// FIRST (x == 0): d = cr * D^-1 b; xout = d
+template <bool FIRST>
+__global__ void __launch_bounds__(BX* BY)
+k_cheb(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
+       const double* __restrict__ bz, const double* __restrict__ bx, double* __restrict__ dz,
+       double* __restrict__ dx, double* __restrict__ oz, double* __restrict__ ox, double cd, double cr) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const long long o = (long long)i * L.ld + j;
+    if (is_vz_row(L, i, j)) {
+        VzCoef c = vz_coef(L, i, j);
+        double d;
+        if (FIRST) {
+            d = cr * bz[o] / c.diag;
+            dz[o] = d;
+            store_vz(L, oz, i, j, d);
+        } else {
+            double r = (bz[o] - kvz_apply(L, c, xz, xx, i, j)) / c.diag;
+            d = cd * dz[o] + cr * r;
+            dz[o] = d;
+            store_vz(L, oz, i, j, xz[o] + d);
+        }
+    }
+    if (is_vx_row(L, i, j)) {
+        VxCoef c = vx_coef(L, i, j);
+        double d;
+        if (FIRST) {
+            d = cr * bx[o] / c.diag;
+            dx[o] = d;
+            store_vx(L, ox, i, j, d);
+        } else {
+            double r = (bx[o] - kvx_apply(L, c, xz, xx, i, j)) / c.diag;
+            d = cd * dx[o] + cr * r;
+            dx[o] = d;
+            store_vx(L, ox, i, j, xx[o] + d);
+        }
+    }
+}
+
+// MODE 0: r = b - K x;  MODE 1: r = D^-1 K x (power iteration);  zero on non-rows
+template <int MODE>
+__global__ void __launch_bounds__(BX* BY)
+k_vel_op(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
+         const double* __restrict__ bz, const double* __restrict__ bx, double* __restrict__ rz,
+         double* __restrict__ rx) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const long long o = (long long)i * L.ld + j;
+    double r = 0;
+    if (is_vz_row(L, i, j)) {
+        VzCoef c = vz_coef(L, i, j);
+        double a = kvz_apply(L, c, xz, xx, i, j);
+        r = MODE == 0 ? bz[o] - a : a / c.diag;
+    }
+    if (MODE == 1) { if (is_vz_row(L, i, j)) store_vz(L, rz, i, j, r); }
+    else rz[o] = r;
+    r = 0;
+    if (is_vx_row(L, i, j)) {
+        VxCoef c = vx_coef(L, i, j);
+        double a = kvx_apply(L, c, xz, xx, i, j);
+        r = MODE == 0 ? bx[o] - a : a / c.diag;
+    }
+    if (MODE == 1) { if (is_vx_row(L, i, j)) store_vx(L, rx, i, j, r); }
+    else rx[o] = r;
+}
+
+// deterministic pseudo-random start vector for the power iteration (rows + slaves)
+__global__ void __launch_bounds__(BX* BY)
+k_fill_random(LevelDev L, double* __restrict__ xz, double* __restrict__ xx) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    unsigned long long h = ((unsigned long long)i * 2654435761ull) ^ ((unsigned long long)j * 40503ull + 12345ull);
+    h ^= h >> 13, h *= 0x9E3779B97F4A7C15ull, h ^= h >> 29;
+    double u = (double)(h & 0xFFFFFF) / 16777216.0 - 0.5;
+    if (is_vz_row(L, i, j)) store_vz(L, xz, i, j, u);
+    if (is_vx_row(L, i, j)) store_vx(L, xx, i, j, 0.7 * u + 0.1);
+}
+
+// restriction of the fine residual (zero on non-rows) to the coarse right-hand side:
+// b_c = 1/4 P^T r  with bilinear P (nodal direction: 1/2,1,1/2; staggered direction: 1/4,3/4,3/4,1/4
+// with constant extrapolation at the ends)
+__global__ void __launch_bounds__(BX* BY)
+k_restrict(LevelDev F, LevelDev Cc, const double* __restrict__ rz, const double* __restrict__ rx,
+           double* __restrict__ bz, double* __restrict__ bx) {
+    const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
+    if (I >= Cc.nz || J >= Cc.nxx) return;
+    const long long oc = (long long)I * Cc.ld + J;
+    const int ldf = F.ld;
+    double s = 0;
+    if (is_vz_row(Cc, I, J)) {
+        const double wn[3] = {0.5, 1.0, 0.5};
+        double wm[4] = {0.25, 0.75, 0.75, 0.25};
+        if (J == 0) wm[1] = 1.0;                       // fine j=0 interpolates from coarse 0 only
+        if (J == Cc.nxx - 2) wm[2] = 1.0;              // fine j=nxx_f-2 from the last coarse mid only
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            int i = 2 * I - 1 + a;
+            if (i < 0 || i >= F.nz) continue;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int j = 2 * J - 1 + b;
+                if (j < 0 || j >= F.nxx) continue;
+                s += wn[a] * wm[b] * rz[(long long)i * ldf + j];
+            }
+        }
+        s *= 0.25;
+    }
+    bz[oc] = s;
+    s = 0;
+    if (is_vx_row(Cc, I, J)) {
+        const double wn[3] = {0.5, 1.0, 0.5};
+        double wm[4] = {0.25, 0.75, 0.75, 0.25};
+        if (I == 0) wm[1] = 1.0;
+        if (I == Cc.nz - 2) wm[2] = 1.0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            int i = 2 * I - 1 + a;
+            if (i < 0 || i >= F.nz) continue;
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                int j = 2 * J - 1 + b;
+                if (j < 0 || j >= F.nxx) continue;
+                s += wm[a] * wn[b] * rx[(long long)i * ldf + j];
+            }
+        }
+        s *= 0.25;
+    }
+    bx[oc] = s;
+}
+
+// xout = xin + P e_c on the fine rows (+ slaves)
+__device__ __forceinline__ void mid_parents(int j, int ncm, int& a, int& b, double& wa, double& wb) {
+    int Jp = j >> 1;
+    if ((j & 1) == 0) a = Jp - 1, b = Jp, wa = 0.25, wb = 0.75;
+    else a = Jp, b = Jp + 1, wa = 0.75, wb = 0.25;
+    a = a < 0 ? 0 : (a > ncm ? ncm : a);
+    b = b < 0 ? 0 : (b > ncm ? ncm : b);
+}
+
+__global__ void __launch_bounds__(BX* BY)
+k_prolong_add(LevelDev F, LevelDev Cc, const double* __restrict__ ez, const double* __restrict__ ex,
+              const double* __restrict__ xz, const double* __restrict__ xx, double* __restrict__ oz,
+              double* __restrict__ ox) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= F.nz || j >= F.nxx) return;
+    const long long o = (long long)i * F.ld + j;
+    const int ldc = Cc.ld;
+    if (is_vz_row(F, i, j)) {
+        int a, b;
+        double wa, wb;
+        mid_parents(j, Cc.nxx - 2, a, b, wa, wb);
+        int I = i >> 1;
+        double v;
+        if ((i & 1) == 0) v = wa * ez[(long long)I * ldc + a] + wb * ez[(long long)I * ldc + b];
+        else v = 0.5 * (wa * ez[(long long)I * ldc + a] + wb * ez[(long long)I * ldc + b] +
+                        wa * ez[(long long)(I + 1) * ldc + a] + wb * ez[(long long)(I + 1) * ldc + b]);
+        store_vz(F, oz, i, j, xz[o] + v);
+    }
+    if (is_vx_row(F, i, j)) {
+        int a, b;
+        double wa, wb;
+        mid_parents(i, Cc.nz - 2, a, b, wa, wb);
+        int J = j >> 1;
+        double v;
+        if ((j & 1) == 0) v = wa * ex[(long long)a * ldc + J] + wb * ex[(long long)b * ldc + J];
+        else v = 0.5 * (wa * ex[(long long)a * ldc + J] + wb * ex[(long long)b * ldc + J] +
+                        wa * ex[(long long)a * ldc + J + 1] + wb * ex[(long long)b * ldc + J + 1]);
+        store_vx(F, ox, i, j, xx[o] + v);
+    }
+}
+
+// viscosity coarsening (arithmetic): nodes = 9-point full weighting with edge clamping; centres =
+// (1,3,3,1)/8 x (1,3,3,1)/8 over the 4x4 block of fine cells around the coarse cell (wide, stable
+// with sharp contrasts) or the plain mean of its 2x2 fine cells (narrow)
+__global__ void __launch_bounds__(BX* BY)
+k_coarsen_eta(int nzf, int nxf, int ldf, const double* __restrict__ es, const double* __restrict__ en,
+              int nzc, int nxc, int ldc, double* __restrict__ cs, double* __restrict__ cn, int wide) {
+    const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
+    if (I >= nzc || J >= nxc) return;
+    const double w3[3] = {0.25, 0.5, 0.25};
+    double s = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int i = min(max(2 * I - 1 + a, 0), nzf - 1);
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            int j = min(max(2 * J - 1 + b, 0), nxf - 1);
+            s += w3[a] * w3[b] * es[(long long)i * ldf + j];
+        }
+    }
+    cs[(long long)I * ldc + J] = s;
+    // centres: real fine cells are [0,nzf-2] x [0,nxf-2]; ghost coarse cells copy the edge
+    int Ic = min(I, nzc - 2), Jc = min(J, nxc - 2);
+    s = 0;
+    if (wide) {
+        const double w4[4] = {0.125, 0.375, 0.375, 0.125};
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            int i = min(max(2 * Ic - 1 + a, 0), nzf - 2);
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int j = min(max(2 * Jc - 1 + b, 0), nxf - 2);
+                s += w4[a] * w4[b] * en[(long long)i * ldf + j];
+            }
+        }
+    } else {
+        long long o = (long long)(2 * Ic) * ldf + 2 * Jc;
+        s = 0.25 * (en[o] + en[o + 1] + en[o + ldf] + en[o + ldf + 1]);
+    }
+    cn[(long long)I * ldc + J] = s;
+}
+
+// ---- dense coarse-level solve ----------------------------------------------------------------
+__device__ __forceinline__ int unk_vz(const LevelDev& L, int i, int j) {
+    return (i - L.vz_i0) * (L.vz_j1 - L.vz_j0 + 1) + (j - L.vz_j0);
+}
+__device__ __forceinline__ int n_vz(const LevelDev& L) {
+    return (L.vz_i1 - L.vz_i0 + 1) * (L.vz_j1 - L.vz_j0 + 1);
+}
+__device__ __forceinline__ int unk_vx(const LevelDev& L, int i, int j) {
+    return n_vz(L) + (i - L.vx_i0) * (L.vx_j1 - L.vx_j0 + 1) + (j - L.vx_j0);
+}
+
+// probe k = unit vector of unknown k (with its slaves) in its own pair of planes
+__global__ void k_probe_set(LevelDev L, int n, size_t plane, double* __restrict__ probes) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    if (is_vz_row(L, i, j)) store_vz(L, probes + (size_t)unk_vz(L, i, j) * 2 * plane, i, j, 1.0);
+    if (is_vx_row(L, i, j)) store_vx(L, probes + (size_t)unk_vx(L, i, j) * 2 * plane + plane, i, j, 1.0);
+}
+
+// A[row][k] = (K e_k)[row], augmented with the identity: M = [A | I], n x 2n row-major
+__global__ void k_probe_apply(LevelDev L, int n, size_t plane, const double* __restrict__ probes,
+                              double* __restrict__ M) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    if (i >= L.nz || j >= L.nxx) return;
+    const double* xz = probes + (size_t)k * 2 * plane;
+    const double* xx = xz + plane;
+    if (is_vz_row(L, i, j)) {
+        VzCoef c = vz_coef(L, i, j);
+        int row = unk_vz(L, i, j);
+        M[(size_t)row * 2 * n + k] = kvz_apply(L, c, xz, xx, i, j);
+        M[(size_t)row * 2 * n + n + k] = (row == k) ? 1.0 : 0.0;
+    }
+    if (is_vx_row(L, i, j)) {
+        VxCoef c = vx_coef(L, i, j);
+        int row = unk_vx(L, i, j);
+        M[(size_t)row * 2 * n + k] = kvx_apply(L, c, xz, xx, i, j);
+        M[(size_t)row * 2 * n + n + k] = (row == k) ? 1.0 : 0.0;
+    }
+}
+
+// Gauss-Jordan with partial pivoting on [A | I] in one CTA; the right half becomes A^-1
+__global__ void __launch_bounds__(1024) k_gauss_jordan(int n, double* __restrict__ M, int* __restrict__ fail) {
+    extern __shared__ double sh[];
+    double* col = sh;                       // n entries: column k before elimination
+    __shared__ double pv[32];
+    __shared__ int pi[32];
+    __shared__ int prow;
+    const int tid = threadIdx.x, nt = blockDim.x, w2 = 2 * n;
+    for (int k = 0; k < n; k++) {
+        double best = -1;
+        int bi = k;
+        for (int r = k + tid; r < n; r += nt) {
+            double v = fabs(M[(size_t)r * w2 + k]);
+            if (v > best) best = v, bi = r;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_down_sync(0xffffffffu, best, o);
+            int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ob > best) best = ob, bi = oi;
+        }
+        if ((tid & 31) == 0) pv[tid >> 5] = best, pi[tid >> 5] = bi;
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 1; q < (nt + 31) / 32; q++)
+                if (pv[q] > pv[0]) pv[0] = pv[q], pi[0] = pi[q];
+            prow = pi[0];
+            if (!(pv[0] > 0)) *fail = 1;
+        }
+        __syncthreads();
+        const int p = prow;
+        if (p != k) {
+            for (int c = tid; c < w2; c += nt) {
+                double t = M[(size_t)k * w2 + c];
+                M[(size_t)k * w2 + c] = M[(size_t)p * w2 + c];
+                M[(size_t)p * w2 + c] = t;
+            }
+        }
+        __syncthreads();
+        const double inv = 1.0 / M[(size_t)k * w2 + k];
+        __syncthreads();
+        for (int c = tid; c < w2; c += nt) M[(size_t)k * w2 + c] *= inv;
+        for (int r = tid; r < n; r += nt) col[r] = M[(size_t)r * w2 + k];
+        __syncthreads();
+        // eliminate: only columns > k of the left half and all touched columns of the right half
+        for (long long e = tid; e < (long long)n * w2; e += nt) {
+            int r = (int)(e / w2), c = (int)(e % w2);
+            if (r == k) continue;
+            double f = col[r];
+            if (f != 0.0) M[(size_t)r * w2 + c] -= f * M[(size_t)k * w2 + c];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_extract_inverse(int n, const double* __restrict__ M, double* __restrict__ inv) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)n * n) return;
+    int r = (int)(t / n), c = (int)(t % n);
+    inv[t] = M[(size_t)r * 2 * n + n + c];
+}
+
+// x = inv * b on the coarsest level (b, x in plane layout): one warp per unknown
+__global__ void __launch_bounds__(256)
+k_dense_solve(LevelDev L, int n, const double* __restrict__ inv, const double* __restrict__ bz,
+              const double* __restrict__ bx, double* __restrict__ xz, double* __restrict__ xx) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const int nvz = n_vz(L), wz = L.vz_j1 - L.vz_j0 + 1, wx = L.vx_j1 - L.vx_j0 + 1;
+    double s = 0;
+    for (int k = lane; k < n; k += 32) {
+        double bv;
+        if (k < nvz) bv = bz[(long long)(L.vz_i0 + k / wz) * L.ld + L.vz_j0 + k % wz];
+        else bv = bx[(long long)(L.vx_i0 + (k - nvz) / wx) * L.ld + L.vx_j0 + (k - nvz) % wx];
+        s += inv[(size_t)warp * n + k] * bv;
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        if (warp < nvz) store_vz(L, xz, L.vz_i0 + warp / wz, L.vz_j0 + warp % wz, s);
+        else store_vx(L, xx, L.vx_i0 + (warp - nvz) / wx, L.vx_j0 + (warp - nvz) % wx, s);
+    }
+}
+
+// final solution: planar -> interleaved with the slaved corner pressures filled in
+__global__ void __launch_bounds__(BX* BY)
+k_solution_out(LevelDev L, const double* __restrict__ vz, const double* __restrict__ vx,
+               const double* __restrict__ p, double* __restrict__ x) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const long long o = (long long)i * L.ld + j, t = (long long)i * L.nxx + j;
+    double pv = p[o];
+    if ((i == 0 || i == L.nz - 2) && (j == 0 || j == L.nxx - 2)) pv = (j == 0) ? p[o + 1] : p[o - 1];
+    if (i == L.nz - 1 || j == L.nxx - 1) pv = 0;
+    x[3 * t] = vz[o], x[3 * t + 1] = vx[o], x[3 * t + 2] = pv;
+}
+
+// -------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------
+int upload(plb_ctx* ctx, const std::vector<double>& h, double** d) {
+    PLB_CUDA(ctx, cudaMalloc(d, sizeof(double) * h.size()));
+    PLB_CUDA(ctx, cudaMemcpyAsync(*d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int zalloc(plb_ctx* ctx, double** d, size_t n) {
+    PLB_CUDA(ctx, cudaMalloc(d, sizeof(double) * n));
+    PLB_CUDA(ctx, cudaMemsetAsync(*d, 0, sizeof(double) * n, ctx->stream));
+    return 0;
+}
+
+int level_metrics(plb_ctx* ctx, Level& L) {
+    const int nz = L.nz, nxx = L.nxx;
+    std::vector<double> idz(nz, 0.0), idzc(nz, 0.0), idx(nxx, 0.0), idxc(nxx, 0.0);
+    for (int i = 0; i + 1 < nz; i++) idz[i] = 1.0 / (L.gz[i + 1] - L.gz[i]);
+    for (int i = 1; i + 1 < nz; i++) idzc[i] = 1.0 / (L.gz[i + 1] - L.gz[i - 1]);
+    for (int j = 0; j + 1 < nxx; j++) idx[j] = 1.0 / (L.gx[j + 1] - L.gx[j]);
+    for (int j = 1; j + 1 < nxx; j++) idxc[j] = 1.0 / (L.gx[j + 1] - L.gx[j - 1]);
+    if (upload(ctx, idz, &L.idz) || upload(ctx, idzc, &L.idzc) || upload(ctx, idx, &L.idx) ||
+        upload(ctx, idxc, &L.idxc))
+        return 2;
+    return 0;
+}
+
+void free_level(Level& L) {
+    double* ptrs[] = {L.idz, L.idzc, L.idx, L.idxc, L.etas_own, L.etan_own, L.X, L.T, L.b, L.r, L.d};
+    for (double* p : ptrs)
+        if (p) cudaFree(p);
+}
+
+int build_levels(plb_stokes* op, const double* h_gz, const double* h_gx) {
+    plb_ctx* ctx = op->ctx;
+    int nz = op->nz, nxx = op->nxx;
+    std::vector<double> gz(h_gz, h_gz + nz), gx(h_gx, h_gx + nxx);
+    for (int l = 0;; l++) {
+        Level L;
+        L.nz = nz, L.nxx = nxx, L.ld = nxx, L.plane = (size_t)nz * nxx;
+        L.gz = gz, L.gx = gx;
+        L.proper = l > 0;
+        if (l == 0) {
+            L.vz_i0 = 1, L.vz_i1 = nz - 2, L.vz_j0 = 1, L.vz_j1 = nxx - 3;
+            L.vx_i0 = 1, L.vx_i1 = nz - 3, L.vx_j0 = 1, L.vx_j1 = nxx - 2;
+            // slave factors of the tangential wall rows (pylamp_stokes.py:163-175, :202-214)
+            if (op->bc[0] == PLB_BC_NOSLIP) {
+                double d2 = gz[2] - gz[0], d1 = gz[1] - gz[0];
+                L.sl_z0 = (1 / d2) / (1 / d2 + 1 / d1);
+            }
+            if (op->bc[2] == PLB_BC_NOSLIP) {
+                double d2 = gz[nz - 3] - gz[nz - 1], d1 = gz[nz - 2] - gz[nz - 1];
+                L.sl_z1 = (1 / d2) / (1 / d2 + 1 / d1);
+            }
+        } else {
+            L.vz_i0 = 1, L.vz_i1 = nz - 2, L.vz_j0 = 0, L.vz_j1 = nxx - 2;
+            L.vx_i0 = 0, L.vx_i1 = nz - 2, L.vx_j0 = 1, L.vx_j1 = nxx - 2;
+            L.ns_z0 = op->bc[0] == PLB_BC_NOSLIP, L.ns_z1 = op->bc[2] == PLB_BC_NOSLIP;
+        }
+        if (level_metrics(ctx, L)) return 2;
+        if (l > 0) {
+            if (zalloc(ctx, &L.etas_own, L.plane) || zalloc(ctx, &L.etan_own, L.plane)) return 2;
+            L.etas = L.etas_own, L.etan = L.etan_own;
+        }
+        if (zalloc(ctx, &L.X, 2 * L.plane) || zalloc(ctx, &L.T, 2 * L.plane) || zalloc(ctx, &L.b, 2 * L.plane) ||
+            zalloc(ctx, &L.r, 2 * L.plane) || zalloc(ctx, &L.d, 2 * L.plane))
+            return 2;
+        op->lv.push_back(L);
+        int cz = nz - 1, cx = nxx - 1;
+        if ((cz % 2) || (cx % 2) || std::min(cz, cx) / 2 < 4) break;
+        std::vector<double> ngz, ngx;
+        for (int i = 0; i < nz; i += 2) ngz.push_back(gz[i]);
+        for (int j = 0; j < nxx; j += 2) ngx.push_back(gx[j]);
+        gz.swap(ngz), gx.swap(ngx);
+        nz = cz / 2 + 1, nxx = cx / 2 + 1;
+    }
+    return 0;
+}
+
+int n_unknowns(const Level& L) {
+    return (L.vz_i1 - L.vz_i0 + 1) * (L.vz_j1 - L.vz_j0 + 1) + (L.vx_i1 - L.vx_i0 + 1) * (L.vx_j1 - L.vx_j0 + 1);
+}
+
+// nu Chebyshev steps on level l.  `from_zero`: the iterate is zero on entry.  Writes alternate
+// between the two buffers; returns the buffer holding the result.
+double* smooth(plb_stokes* op, int l, const double* b, double* cur, double* other, bool from_zero, int nu) {
+    Level& L = op->lv[l];
+    plb_ctx* ctx = op->ctx;
+    const LevelDev D = L.dev();
+    const size_t P = L.plane;
+    const double lmax = L.lmax, lmin = lmax / op->cheb_ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    for (int k = 0; k < nu; k++) {
+        double cd, cr;
+        if (k == 0) cd = 0, cr = 1.0 / theta;
+        else {
+            double rn = 1.0 / (2 * sigma - rho);
+            cd = rn * rho, cr = 2 * rn / delta, rho = rn;
+        }
+        if (k == 0 && from_zero) {
+            // result goes to `cur` (no input needed)
+            k_cheb<true><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(
+                D, nullptr, nullptr, b, b + P, L.d, L.d + P, cur, cur + P, cd, cr);
+        } else {
+            k_cheb<false><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(
+                D, cur, cur + P, b, b + P, L.d, L.d + P, other, other + P, cd, cr);
+            std::swap(cur, other);
+        }
+        ctx->launches++;
+    }
+    return cur;
+}
+
+// one V-cycle for K x = b on level l; the result lands in `xout` (2 planes).  Buffers alternate
+// so that the (2 nu + 1)-th write hits xout.
+int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
+    Level& L = op->lv[l];
+    plb_ctx* ctx = op->ctx;
+    const LevelDev D = L.dev();
+    const size_t P = L.plane;
+    const int nlev = (int)op->lv.size();
+    if (l == nlev - 1) {
+        if (op->cinv) {
+            k_dense_solve<<<(op->nc * 32 + 255) / 256, 256, 0, ctx->stream>>>(D, op->nc, op->cinv, b, b + P,
+                                                                             xout, xout + P);
+            PLB_LAUNCHED(ctx);
+        } else {
+            // large coarsest level (odd cell counts): many smoothing steps instead of a direct solve
+            int nu = op->nu_coarse | 1;          // odd: lands in xout
+            double* res = smooth(op, l, b, xout, L.T, true, nu);
+            if (res != xout) PLB_FAIL(ctx, "internal: coarse smoother parity");
+            PLB_CUDA(ctx, cudaGetLastError());
+        }
+        return 0;
+    }
+    double* other = L.T;
+    // write 1 -> xout, 2 -> T, 3 -> xout ...: after nu writes the iterate is in (nu odd ? xout : T)
+    double* cur = smooth(op, l, b, xout, other, true, op->nu);
+    double* oth = (cur == xout) ? other : xout;
+    k_vel_op<0><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, cur, cur + P, b, b + P, L.r, L.r + P);
+    PLB_LAUNCHED(ctx);
+    Level& Cl = op->lv[l + 1];
+    const LevelDev DC = Cl.dev();
+    k_restrict<<<grid2d(Cl.nz, Cl.nxx), block2d(), 0, ctx->stream>>>(D, DC, L.r, L.r + P, Cl.b, Cl.b + Cl.plane);
+    PLB_LAUNCHED(ctx);
+    if (vcycle(op, l + 1, Cl.b, Cl.X)) return 2;
+    k_prolong_add<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, DC, Cl.X, Cl.X + Cl.plane, cur, cur + P,
+                                                                   oth, oth + P);
+    PLB_LAUNCHED(ctx);
+    std::swap(cur, oth);
+    cur = smooth(op, l, b, cur, oth, false, op->nu);
+    PLB_CUDA(ctx, cudaGetLastError());
+    if (cur != xout) PLB_FAIL(ctx, "internal: V-cycle buffer parity");
+    return 0;
+}
+
+int setup_hierarchy(plb_stokes* op) {
+    plb_ctx* ctx = op->ctx;
+    const int nlev = (int)op->lv.size();
+    // coarse viscosities
+    for (int l = 1; l < nlev; l++) {
+        Level &F = op->lv[l - 1], &Cc = op->lv[l];
+        k_coarsen_eta<<<grid2d(Cc.nz, Cc.nxx), block2d(), 0, ctx->stream>>>(
+            F.nz, F.nxx, F.ld, F.etas, F.etan, Cc.nz, Cc.nxx, Cc.ld, Cc.etas_own, Cc.etan_own, op->coarsen_wide);
+        PLB_LAUNCHED(ctx);
+    }
+    // largest eigenvalue of D^-1 K per level by power iteration
+    const int npow = 12;
+    for (int l = 0; l < nlev; l++) {
+        Level& L = op->lv[l];
+        const LevelDev D = L.dev();
+        const size_t P = L.plane;
+        double *x = L.X, *y = L.T;
+        PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 2 * P, ctx->stream));
+        PLB_CUDA(ctx, cudaMemsetAsync(y, 0, sizeof(double) * 2 * P, ctx->stream));
+        k_fill_random<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, x, x + P);
+        PLB_LAUNCHED(ctx);
+        double* s = op->d_scal + 900;
+        for (int it = 0; it < npow; it++) {
+            k_vel_op<1><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, x, x + P, nullptr, nullptr, y, y + P);
+            PLB_LAUNCHED(ctx);
+            if (plb_dot(ctx, &op->rws, 2 * P, y, y, s)) return 2;
+            if (plb_scale_rsqrt2(ctx, 2 * P, s, y, nullptr)) return 2;
+            std::swap(x, y);
+        }
+        // Rayleigh-type estimate: || D^-1 K x || with ||x|| = 1 (over rows + slaves)
+        k_vel_op<1><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, x, x + P, nullptr, nullptr, y, y + P);
+        PLB_LAUNCHED(ctx);
+        if (plb_dot(ctx, &op->rws, 2 * P, y, y, s)) return 2;
+        if (plb_dot(ctx, &op->rws, 2 * P, x, x, s + 1)) return 2;
+        double h[2];
+        if (plb_read_scalars(ctx, s, 2, h)) return 2;
+        L.lmax = 1.1 * sqrt(h[0] / h[1]);
+        if (!(L.lmax > 0) || !(L.lmax < 1e6)) PLB_FAIL(ctx, "Stokes MG: bad eigenvalue estimate %g on level %d", L.lmax, l);
+        PLB_CUDA(ctx, cudaMemsetAsync(L.X, 0, sizeof(double) * 2 * P, ctx->stream));
+        PLB_CUDA(ctx, cudaMemsetAsync(L.T, 0, sizeof(double) * 2 * P, ctx->stream));
+    }
+    // dense inverse on the coarsest level
+    Level& Lc = op->lv[nlev - 1];
+    const int n = n_unknowns(Lc);
+    if (op->cinv) cudaFree(op->cinv), op->cinv = nullptr;
+    op->nc = 0;
+    if (n <= op->dense_max) {
+        const LevelDev D = Lc.dev();
+        const size_t P = Lc.plane;
+        double *probes = nullptr, *M = nullptr;
+        int* fail = nullptr;
+        if (zalloc(ctx, &probes, (size_t)n * 2 * P) || zalloc(ctx, &M, (size_t)n * 2 * n)) return 2;
+        PLB_CUDA(ctx, cudaMalloc(&fail, sizeof(int)));
+        PLB_CUDA(ctx, cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
+        PLB_CUDA(ctx, cudaMalloc(&op->cinv, sizeof(double) * (size_t)n * n));
+        k_probe_set<<<grid2d(Lc.nz, Lc.nxx), block2d(), 0, ctx->stream>>>(D, n, P, probes);
+        PLB_LAUNCHED(ctx);
+        dim3 g = grid2d(Lc.nz, Lc.nxx);
+        g.z = n;
+        k_probe_apply<<<g, block2d(), 0, ctx->stream>>>(D, n, P, probes, M);
+        PLB_LAUNCHED(ctx);
+        k_gauss_jordan<<<1, 1024, sizeof(double) * n, ctx->stream>>>(n, M, fail);
+        PLB_LAUNCHED(ctx);
+        k_extract_inverse<<<(int)(((size_t)n * n + 255) / 256), 256, 0, ctx->stream>>>(n, M, op->cinv);
+        PLB_LAUNCHED(ctx);
+        int hfail = 0;
+        PLB_CUDA(ctx, cudaMemcpyAsync(&hfail, fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(probes), cudaFree(M), cudaFree(fail);
+        if (hfail) PLB_FAIL(ctx, "Stokes MG: singular coarse-level operator");
+        op->nc = n;
+    }
+    op->hierarchy = true;
+    return 0;
+}
+
+int ensure_krylov(plb_stokes* op) {
+    plb_ctx* ctx = op->ctx;
+    const size_t n3 = 3 * op->lv[0].plane;
+    if (!op->xs) {
+        if (zalloc(ctx, &op->xs, n3) || zalloc(ctx, &op->r3, n3) || zalloc(ctx, &op->b3, n3) ||
+            zalloc(ctx, &op->t3, n3))
+            return 2;
+    }
+    if (op->kry.m != op->gcr_m && plb_fgmres_alloc(ctx, &op->kry, op->gcr_m, (long long)n3, op->d_scal)) return 2;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plb_stokes_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_z,
+                      const double* h_grid_x, const int* h_bc, plb_stokes** out) {
+    if (!ctx || !out) return 1;
+    *out = nullptr;
+    if (nz < 6 || nxx < 6) PLB_FAIL(ctx, "plb_stokes_create: grid %dx%d too small (anchor cell (3,2) must exist)", nz, nxx);
+    if (ld != nxx) PLB_FAIL(ctx, "plb_stokes_create: only ld == nxx is supported");
+    for (int w = 0; w < 4; w++) {
+        int b = h_bc[w];
+        bool zwall = (w % 2) == 0;
+        if (zwall && b != PLB_BC_NOSLIP && b != PLB_BC_FREESLIP)
+            PLB_FAIL(ctx, "plb_stokes_create: z-wall BC %d not supported (NOSLIP|FREESLIP; CYCLIC is SURVEY 8f-4)", b);
+        if (!zwall && b != PLB_BC_FREESLIP)
+            PLB_FAIL(ctx, "plb_stokes_create: x-wall BC %d not supported (the reference's matrix is singular "
+                          "for NOSLIP x-walls, pylamp_stokes.py:242; CYCLIC/FLOWTHRU are SURVEY 8f-4)", b);
+    }
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    plb_stokes* op = new plb_stokes();
+    op->ctx = ctx, op->nz = nz, op->nxx = nxx, op->ld = ld;
+    for (int w = 0; w < 4; w++) op->bc[w] = h_bc[w];
+    if (plb_reduce_ws_init(ctx, &op->rws)) { delete op; return 2; }
+    if (zalloc(ctx, &op->d_scal, 1024)) { delete op; return 2; }
+    if (build_levels(op, h_grid_z, h_grid_x)) { plb_stokes_destroy(op); return 2; }
+    std::vector<double> gz(h_grid_z, h_grid_z + nz), gx(h_grid_x, h_grid_x + nxx);
+    if (upload(ctx, gz, &op->gz_d) || upload(ctx, gx, &op->gx_d)) { plb_stokes_destroy(op); return 2; }
+    *out = op;
+    return 0;
+}
+
+void plb_stokes_destroy(plb_stokes* op) {
+    if (!op) return;
+    cudaSetDevice(op->ctx->device);
+    cudaStreamSynchronize(op->ctx->stream);
+    for (Level& L : op->lv) free_level(L);
+    plb_fgmres_free(&op->kry);
+    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d};
+    for (double* p : ptrs) if (p) cudaFree(p);
+    plb_reduce_ws_free(&op->rws);
+    delete op;
+}
+
+int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
+    if (!op || !name) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!strcmp(name, "nu")) op->nu = (int)value;
+    else if (!strcmp(name, "gcr_m")) {
+        if (value < 2 || value > 800) PLB_FAIL(ctx, "plb_stokes_set_param: gcr_m out of range 2..800");
+        op->gcr_m = (int)value;
+    }
+    else if (!strcmp(name, "coarsen_wide")) op->coarsen_wide = (int)value, op->hierarchy = false;
+    else if (!strcmp(name, "cheb_ratio")) op->cheb_ratio = value;
+    else if (!strcmp(name, "dense_max")) op->dense_max = (int)value, op->hierarchy = false;
+    else if (!strcmp(name, "nu_coarse")) op->nu_coarse = (int)value;
+    else if (!strcmp(name, "reorth")) op->reorth = (int)value;
+    else if (!strcmp(name, "rtol_accept")) op->rtol_accept = value;
+    else PLB_FAIL(ctx, "plb_stokes_set_param: unknown parameter '%s'", name);
+    return 0;
+}
+
+int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_etan,
+                          const double* d_rho, double gz, double gx) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    Level& L = op->lv[0];
+    L.etas = d_etas, L.etan = d_etan;
+    op->rho = d_rho, op->g_z = gz, op->g_x = gx;
+    // mineta over both fields INCLUDING the ghost row/column of etan, like np.min (:116)
+    double* d = op->d_scal + 920;
+    k_set1<<<1, 1, 0, ctx->stream>>>(d, INFINITY);
+    PLB_LAUNCHED(ctx);
+    k_min2<<<plb_grid_for(ctx, (long long)L.plane, 256, 8), 256, 0, ctx->stream>>>((long long)L.plane, d_etas, d_etan, d);
+    PLB_LAUNCHED(ctx);
+    double mineta;
+    if (plb_read_scalars(ctx, d, 1, &mineta)) return 2;
+    // avgd = L/n with n = number of NODES (sic), pylamp_stokes.py:119-120
+    double avgdx = (L.gx[op->nxx - 1] - L.gx[0]) / op->nxx;
+    double avgdz = (L.gz[op->nz - 1] - L.gz[0]) / op->nz;
+    op->Kc = 2 * mineta / (avgdx + avgdz);
+    op->Kb = 4 * mineta / ((avgdx + avgdz) * (avgdx + avgdz));
+    op->coeffs = true, op->hierarchy = false;
+    return 0;
+}
+
+int plb_stokes_scaling(plb_stokes* op, double* h_out) {
+    if (!op || !op->coeffs) return 1;
+    h_out[0] = op->Kc, h_out[1] = op->Kb;
+    return 0;
+}
+
+int plb_stokes_rhs(plb_stokes* op, double* d_rhs) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_rhs: coefficients not set");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ensure_krylov(op)) return 2;
+    Level& L = op->lv[0];
+    const size_t P = L.plane;
+    k_stokes_rhs<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(L.dev(), op->rho, op->g_z, op->g_x,
+                                                                   op->t3, op->t3 + P, op->t3 + 2 * P);
+    PLB_LAUNCHED(ctx);
+    k_interleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, op->t3, op->t3 + P,
+                                                                                op->t3 + 2 * P, d_rhs);
+    PLB_LAUNCHED(ctx);
+    return 0;
+}
+
+int plb_stokes_apply(plb_stokes* op, const double* d_x, double* d_y) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_apply: coefficients not set");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ensure_krylov(op)) return 2;
+    Level& L = op->lv[0];
+    const size_t P = L.plane;
+    double *in = op->t3, *outp = op->r3;
+    k_deinterleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, d_x, in, in + P, in + 2 * P);
+    PLB_LAUNCHED(ctx);
+    FullArgs a = {op->gz_d, op->gx_d, op->bc[0], op->bc[2], op->Kc, op->Kb};
+    k_stokes_full<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(L.dev(), a, in, in + P, in + 2 * P, outp,
+                                                                    outp + P, outp + 2 * P);
+    PLB_LAUNCHED(ctx);
+    k_interleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, outp, outp + P,
+                                                                                outp + 2 * P, d_y);
+    PLB_LAUNCHED(ctx);
+    return 0;
+}
+
+// one multigrid V-cycle on the velocity block of level 0 (planar 2-plane vectors): test hook
+int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_vcycle: coefficients not set");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!op->hierarchy && setup_hierarchy(op)) return 2;
+    PLB_CUDA(ctx, cudaMemsetAsync(d_x2, 0, sizeof(double) * 2 * op->lv[0].plane, ctx->stream));
+    return vcycle(op, 0, d_b2, d_x2);
+}
+
+int plb_stokes_last_stats(plb_stokes* op, double* h_out) {
+    if (!op) return 1;
+    h_out[0] = op->last_iters, h_out[1] = op->last_vcycles, h_out[2] = op->last_relres;
+    return 0;
+}
+
+int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit, double* d_x,
+                     int* h_iters, double* h_relres) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_solve: coefficients not set");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ensure_krylov(op)) return 2;
+    if (!op->hierarchy && setup_hierarchy(op)) return 2;
+    Level& L = op->lv[0];
+    const LevelDev D = L.dev();
+    const size_t P = L.plane;
+    const double Kc = op->Kc;
+    double *x = op->xs, *r = op->r3, *b = op->b3;
+    const dim3 g = grid2d(L.nz, L.nxx), blk = block2d();
+    if (d_rhs) {
+        // caller's right-hand side in the reference layout; entries on wall/ghost/corner/anchor rows
+        // are homogeneous in the reference (pylamp_stokes.py never writes them) and are ignored
+        k_deinterleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, d_rhs, b, b + P,
+                                                                                      b + 2 * P);
+    } else {
+        k_stokes_rhs<<<g, blk, 0, ctx->stream>>>(D, op->rho, op->g_z, op->g_x, b, b + P, b + 2 * P);
+    }
+    PLB_LAUNCHED(ctx);
+    PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
+    auto residual = [&](double* out) -> int {
+        k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, x, x + P, x + 2 * P, b, b + P, b + 2 * P, out, out + P,
+                                                      out + 2 * P);
+        PLB_LAUNCHED(ctx);
+        return 0;
+    };
+    if (residual(r)) return 2;
+    double bn2;
+    if (plb_dot(ctx, &op->rws, 3 * P, r, r, op->d_scal + 910)) return 2;
+    if (plb_read_scalars(ctx, op->d_scal + 910, 1, &bn2)) return 2;
+    const double bnorm = sqrt(bn2);
+    int vcycles = 0;
+    auto apply = [&](const double* z, double* c) -> int {
+        k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, z, z + P, z + 2 * P, nullptr, nullptr, nullptr, c,
+                                                       c + P, c + 2 * P);
+        PLB_LAUNCHED(ctx);
+        return 0;
+    };
+    auto precond = [&](const double* rr, double* z) -> int {
+        k_precond_rhs<<<g, blk, 0, ctx->stream>>>(D, Kc, rr, rr + P, rr + 2 * P, z + 2 * P, L.b, L.b + P);
+        PLB_LAUNCHED(ctx);
+        PLB_CUDA(ctx, cudaMemsetAsync(z, 0, sizeof(double) * 2 * P, ctx->stream));
+        vcycles++;
+        return vcycle(op, 0, L.b, z);
+    };
+    plb_fgmres_result res;
+    if (bnorm > 0) {
+        if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol, maxit, &res)) return 2;
+    } else {
+        res.converged = true;
+    }
+    const int total = res.iters;
+    op->last_iters = total, op->last_vcycles = vcycles, op->last_relres = res.relres;
+    if (h_iters) *h_iters = total;
+    if (h_relres) *h_relres = res.relres;
+    k_solution_out<<<g, blk, 0, ctx->stream>>>(D, x, x + P, x + 2 * P, d_x);
+    PLB_LAUNCHED(ctx);
+    if (!res.converged && res.relres > op->rtol_accept)
+        PLB_FAIL(ctx, "plb_stokes_solve: not converged after %d iterations (relres %.3e > rtol %.3e, "
+                      "accept %.1e)", total, res.relres, rtol, op->rtol_accept);
+    return 0;
+}
+
+}  // extern "C"
