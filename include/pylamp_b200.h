@@ -169,9 +169,10 @@ int plb_diff_set_coeffs(plb_diff* op, const double* d_T, const double* d_kz, con
 /* rhs / apply / solve on (nz x nxx) vectors stored with the leading dimension ld */
 int plb_diff_rhs(plb_diff* op, double* d_rhs);
 int plb_diff_apply(plb_diff* op, const double* d_x, double* d_y);
-/* replaces spsolve at pylamp2.py:419 */
-int plb_diff_solve(plb_diff* op, double rtol, int maxit, double* d_x, int* h_iters,
-                   double* h_relres);
+/* replaces spsolve at pylamp2.py:419: restarted GMRES on the row-scaled system, started from the
+ * current temperature field.  d_rhs NULL = the system's own right-hand side. */
+int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, double* d_x,
+                   int* h_iters, double* h_relres);
 
 #ifdef __cplusplus
 }

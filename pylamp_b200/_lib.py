@@ -55,7 +55,7 @@ _PROTOS = {
     "plb_diff_set_coeffs": (I, [VP, VP, VP, VP, VP, VP, VP, D]),
     "plb_diff_rhs": (I, [VP, VP]),
     "plb_diff_apply": (I, [VP, VP, VP]),
-    "plb_diff_solve": (I, [VP, D, I, VP, IP, DP]),
+    "plb_diff_solve": (I, [VP, VP, D, I, VP, IP, DP]),
 }
 
 _lib = None

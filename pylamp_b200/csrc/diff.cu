@@ -1,0 +1,257 @@
+// diff.cu -- the reference's implicit-Euler heat-conduction system (pylamp_diff.makeDiffusionMatrix,
+// pylamp_diff.py:85-183) as a matrix-free sm_100a operator, and the solver that replaces
+// scipy.sparse.linalg.spsolve at pylamp2.py:419.
+//
+// Row r = i*nxx + j.  Interior rows (pylamp_diff.py:157-179), walls FIXTEMP / FIXFLOW (:99-152; the
+// z-walls own the corners).  Because the driver's dt never exceeds 0.67*dx^2/max(2*kappa)
+// (pylamp2.py:339-343), the row-scaled operator D^-1 A is I + (a perturbation of norm < 1): plain
+// restarted GMRES on the row-scaled system converges in a few tens of iterations independent of
+// the grid size, so no multigrid is needed here.
+#include <math.h>
+
+#include <vector>
+
+#include "blas1.cuh"
+#include "fgmres.cuh"
+
+namespace {
+
+constexpr int BX = 32, BY = 8;
+inline dim3 grid2d(int nz, int nxx) { return dim3((nxx + BX - 1) / BX, (nz + BY - 1) / BY); }
+inline dim3 block2d() { return dim3(BX, BY); }
+
+struct DiffDev {
+    int nz, nxx, ld;
+    const double *idz, *idx;      // 1/(g[k+1]-g[k])
+    const double *idzm, *idxm;    // 1/(gmp[k]-gmp[k-1]), k >= 1
+    const double *T, *kz, *kx, *cp, *rho, *H;
+    double dt;
+    int bc[4];                    // [z=0, x=0, z=L, x=L]
+    double bcval[4];
+};
+
+// coefficients of row (i,j): value = cC*T[i,j] + cE*T[i,j+1] + cW*T[i,j-1] + cS*T[i+1,j] + cN*T[i-1,j]
+struct Row {
+    double cC, cE, cW, cS, cN, rhs;
+};
+
+__device__ __forceinline__ Row diff_row(const DiffDev& D, int i, int j) {
+    Row r = {0, 0, 0, 0, 0, 0};
+    const int nz = D.nz, nxx = D.nxx;
+    const long long o = (long long)i * D.ld + j;
+    if (i == 0 || i == nz - 1) {                                  // z-walls, :99-124
+        const int w = (i == 0) ? 0 : 2;
+        r.rhs = D.bcval[w];
+        if (D.bc[w] == PLB_BC_FIXTEMP) {
+            r.cC = 1.0;
+        } else if (i == 0) {
+            double c = D.kz[o] * D.idz[0];
+            r.cS = c, r.cC = -c;
+        } else {
+            double c = D.kz[o - D.ld] * D.idz[nz - 2];
+            r.cC = c, r.cN = -c;
+        }
+    } else if (j == 0 || j == nxx - 1) {                          // x-walls, :126-152
+        const int w = (j == 0) ? 1 : 3;
+        r.rhs = D.bcval[w];
+        if (D.bc[w] == PLB_BC_FIXTEMP) {
+            r.cC = 1.0;
+        } else if (j == 0) {
+            double c = D.kx[o] * D.idx[0];
+            r.cE = c, r.cC = -c;
+        } else {
+            double c = D.kx[o - 1] * D.idx[nxx - 2];
+            r.cC = c, r.cW = -c;
+        }
+    } else {                                                       // interior, :157-179
+        const double rc = D.rho[o] * D.cp[o];
+        const double pre = D.dt / rc;
+        r.cE = pre * D.kx[o] * D.idx[j] * D.idxm[j];
+        r.cW = pre * D.kx[o - 1] * D.idx[j - 1] * D.idxm[j];
+        r.cS = pre * D.kz[o] * D.idz[i] * D.idzm[i];
+        r.cN = pre * D.kz[o - D.ld] * D.idz[i - 1] * D.idzm[i];
+        r.cC = -(r.cE + r.cW + r.cS + r.cN) - 1.0;
+        r.rhs = -D.T[o] - D.dt * D.H[o] / rc;
+    }
+    return r;
+}
+
+__device__ __forceinline__ double row_apply(const DiffDev& D, const Row& r, const double* __restrict__ x,
+                                            int i, int j) {
+    const long long o = (long long)i * D.ld + j;
+    double v = r.cC * x[o];
+    if (r.cE != 0) v += r.cE * x[o + 1];
+    if (r.cW != 0) v += r.cW * x[o - 1];
+    if (r.cS != 0) v += r.cS * x[o + D.ld];
+    if (r.cN != 0) v += r.cN * x[o - D.ld];
+    return v;
+}
+
+// MODE 0: y = A x (reference rows, unscaled)   MODE 1: y = rhs   MODE 2: y = D^-1 (b - A x)
+// MODE 3: y = D^-1 A x        (b == nullptr in MODE 2 means the system's own rhs)
+template <int MODE>
+__global__ void __launch_bounds__(BX* BY)
+k_diff(DiffDev D, const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= D.nz || j >= D.nxx) return;
+    const long long o = (long long)i * D.ld + j;
+    Row r = diff_row(D, i, j);
+    if (MODE == 1) {
+        y[o] = r.rhs;
+        return;
+    }
+    double a = row_apply(D, r, x, i, j);
+    if (MODE == 0) y[o] = a;
+    else if (MODE == 2) y[o] = ((b ? b[o] : r.rhs) - a) / r.cC;
+    else y[o] = a / r.cC;
+}
+
+}  // namespace
+
+struct plb_diff {
+    plb_ctx* ctx = nullptr;
+    int nz = 0, nxx = 0, ld = 0;
+    double *idz = nullptr, *idx = nullptr, *idzm = nullptr, *idxm = nullptr;
+    DiffDev dev{};
+    bool coeffs = false;
+    plb_reduce_ws rws{};
+    double* d_scal = nullptr;
+    plb_fgmres_ws kry;
+    double* xs = nullptr;
+    int m = 40;
+    int last_iters = 0;
+    double last_relres = 0;
+};
+
+namespace {
+int upload(plb_ctx* ctx, const std::vector<double>& h, double** d) {
+    PLB_CUDA(ctx, cudaMalloc(d, sizeof(double) * h.size()));
+    PLB_CUDA(ctx, cudaMemcpyAsync(*d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_z,
+                    const double* h_grid_x, const double* h_gridmp_z, const double* h_gridmp_x,
+                    const int* h_bc, const double* h_bcvalue, plb_diff** out) {
+    if (!ctx || !out) return 1;
+    *out = nullptr;
+    if (nz < 3 || nxx < 3) PLB_FAIL(ctx, "plb_diff_create: grid too small");
+    if (ld != nxx) PLB_FAIL(ctx, "plb_diff_create: only ld == nxx is supported");
+    for (int w = 0; w < 4; w++)
+        if (h_bc[w] != PLB_BC_FIXTEMP && h_bc[w] != PLB_BC_FIXFLOW)
+            PLB_FAIL(ctx, "plb_diff_create: unknown heat BC %d on wall %d", h_bc[w], w);
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    plb_diff* op = new plb_diff();
+    op->ctx = ctx, op->nz = nz, op->nxx = nxx, op->ld = ld;
+    std::vector<double> idz(nz, 0.0), idx(nxx, 0.0), idzm(nz, 0.0), idxm(nxx, 0.0);
+    for (int i = 0; i + 1 < nz; i++) idz[i] = 1.0 / (h_grid_z[i + 1] - h_grid_z[i]);
+    for (int j = 0; j + 1 < nxx; j++) idx[j] = 1.0 / (h_grid_x[j + 1] - h_grid_x[j]);
+    for (int i = 1; i < nz; i++) idzm[i] = 1.0 / (h_gridmp_z[i] - h_gridmp_z[i - 1]);
+    for (int j = 1; j < nxx; j++) idxm[j] = 1.0 / (h_gridmp_x[j] - h_gridmp_x[j - 1]);
+    if (upload(ctx, idz, &op->idz) || upload(ctx, idx, &op->idx) || upload(ctx, idzm, &op->idzm) ||
+        upload(ctx, idxm, &op->idxm) || plb_reduce_ws_init(ctx, &op->rws)) {
+        plb_diff_destroy(op);
+        return 2;
+    }
+    PLB_CUDA(ctx, cudaMalloc(&op->d_scal, sizeof(double) * 1024));
+    PLB_CUDA(ctx, cudaMalloc(&op->xs, sizeof(double) * (size_t)nz * ld));
+    DiffDev& D = op->dev;
+    D.nz = nz, D.nxx = nxx, D.ld = ld;
+    D.idz = op->idz, D.idx = op->idx, D.idzm = op->idzm, D.idxm = op->idxm;
+    for (int w = 0; w < 4; w++) D.bc[w] = h_bc[w], D.bcval[w] = h_bcvalue[w];
+    *out = op;
+    return 0;
+}
+
+void plb_diff_destroy(plb_diff* op) {
+    if (!op) return;
+    cudaSetDevice(op->ctx->device);
+    cudaStreamSynchronize(op->ctx->stream);
+    double* ptrs[] = {op->idz, op->idx, op->idzm, op->idxm, op->d_scal, op->xs};
+    for (double* p : ptrs) if (p) cudaFree(p);
+    plb_fgmres_free(&op->kry);
+    plb_reduce_ws_free(&op->rws);
+    delete op;
+}
+
+int plb_diff_set_coeffs(plb_diff* op, const double* d_T, const double* d_kz, const double* d_kx,
+                        const double* d_cp, const double* d_rho, const double* d_H, double tstep) {
+    if (!op) return 1;
+    DiffDev& D = op->dev;
+    D.T = d_T, D.kz = d_kz, D.kx = d_kx, D.cp = d_cp, D.rho = d_rho, D.H = d_H, D.dt = tstep;
+    op->coeffs = true;
+    return 0;
+}
+
+int plb_diff_rhs(plb_diff* op, double* d_rhs) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_diff_rhs: coefficients not set");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_diff<1><<<grid2d(op->nz, op->nxx), block2d(), 0, ctx->stream>>>(op->dev, nullptr, nullptr, d_rhs);
+    PLB_LAUNCHED(ctx);
+    return 0;
+}
+
+int plb_diff_apply(plb_diff* op, const double* d_x, double* d_y) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_diff_apply: coefficients not set");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_diff<0><<<grid2d(op->nz, op->nxx), block2d(), 0, ctx->stream>>>(op->dev, d_x, nullptr, d_y);
+    PLB_LAUNCHED(ctx);
+    return 0;
+}
+
+int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, double* d_x,
+                   int* h_iters, double* h_relres) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_diff_solve: coefficients not set");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const long long n = (long long)op->nz * op->ld;
+    if (op->kry.m != op->m && plb_fgmres_alloc(ctx, &op->kry, op->m, n, op->d_scal)) return 2;
+    const DiffDev D = op->dev;
+    const dim3 g = grid2d(op->nz, op->nxx), blk = block2d();
+    double* x = d_x;
+    // bnorm = || D^-1 b ||: residual of x = 0
+    PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+    auto residual = [&](double* out) -> int {
+        k_diff<2><<<g, blk, 0, ctx->stream>>>(D, x, d_rhs, out);
+        PLB_LAUNCHED(ctx);
+        return 0;
+    };
+    if (residual(op->xs)) return 2;
+    double bn2;
+    if (plb_dot(ctx, &op->rws, n, op->xs, op->xs, op->d_scal + 900)) return 2;
+    if (plb_read_scalars(ctx, op->d_scal + 900, 1, &bn2)) return 2;
+    const double bnorm = sqrt(bn2);
+    // initial guess: the current temperature field (the rhs is -T_old - dt*H/(rho*cp))
+    PLB_CUDA(ctx, cudaMemcpyAsync(x, D.T, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    auto apply = [&](const double* z, double* w) -> int {
+        k_diff<3><<<g, blk, 0, ctx->stream>>>(D, z, nullptr, w);
+        PLB_LAUNCHED(ctx);
+        return 0;
+    };
+    auto precond = [&](const double* v, double* z) -> int { return plb_copy(ctx, n, v, z); };
+    plb_fgmres_result res;
+    if (bnorm > 0) {
+        if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol, maxit, &res)) return 2;
+    } else {
+        PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+        res.converged = true;
+    }
+    op->last_iters = res.iters, op->last_relres = res.relres;
+    if (h_iters) *h_iters = res.iters;
+    if (h_relres) *h_relres = res.relres;
+    if (!res.converged && res.relres > 1e3 * rtol)
+        PLB_FAIL(ctx, "plb_diff_solve: not converged after %d iterations (relres %.3e > rtol %.3e)", res.iters,
+                 res.relres, rtol);
+    return 0;
+}
+
+}  // extern "C"

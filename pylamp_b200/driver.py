@@ -1,0 +1,202 @@
+"""Device-resident thin driver: one pass of the reference's loop body (pylamp2.py:273-594) built
+from the same module-level functions pylamp2.py calls, with all state kept in HBM.
+
+The unmodified reference driver can also be run against the drop-in modules, but
+its inline NumPy steps then bounce every marker through host memory each call; this driver keeps
+markers (SoA columns) and grid fields on the GPU and is what `bench.py` times.
+
+Mirrors oracle/pylamp_oracle.py's State/Options/timestep so that the parity tests read the same on
+both sides.  No injection / output here (SURVEY.md §8f "next" rows); NPROC = 1 per slab.
+"""
+import numpy as np
+import torch
+
+from . import _lib, markers, pylamp_diff, pylamp_stokes, pylamp_trac
+from .pylamp_const import *  # noqa: F401,F403
+from .pylamp_const import (DIM, EPS, IX, IZ, NFTRAC, SECINYR, TR_ACE, TR_ALP, TR_ET0, TR_ETA, TR_HCD,
+                           TR_HCP, TR_IHT, TR_MAT, TR_RH0, TR_RHO, TR_TMP)
+from .pylamp_trac import (INTERP_AVG_ARITHW, INTERP_AVG_GEOMETRIC, INTERP_AVG_GEOMW,
+                          INTERP_METHOD_LINEAR)
+from .setups import make_grids
+
+
+class Options:
+    """The configurable locals of pylamp2.py:37-77 (defaults as shipped)."""
+
+    def __init__(self, **kw):
+        self.do_stokes = True
+        self.do_advect = True
+        self.do_heatdiff = True
+        self.do_subgrid_heatdiff = True
+        self.tstep_adv_max = 50e9 * SECINYR
+        self.tstep_adv_min = 50e-9 * SECINYR
+        self.tstep_dif_max = 50e9 * SECINYR
+        self.tstep_dif_min = 50e-9 * SECINYR
+        self.tstep_modifier = 0.67
+        self.tdep_rho = True
+        self.tdep_eta = True
+        self.etamin = 1e17
+        self.etamax = 1e23
+        self.Tref = 1623
+        self.tracs_fence_enabled = True
+        self.bcstokes = [pylamp_stokes.BC_TYPE_FREESLIP] * 4
+        self.bcheat = [pylamp_diff.BC_TYPE_FIXTEMP, pylamp_diff.BC_TYPE_FIXFLOW,
+                       pylamp_diff.BC_TYPE_FIXTEMP, pylamp_diff.BC_TYPE_FIXFLOW]
+        self.bcheatvals = [273, 0, 1623, 0]
+        # solver controls (not in the reference: it calls a direct solver)
+        self.stokes_rtol = 1e-12
+        self.stokes_maxit = 600
+        self.stokes_params = {}
+        self.heat_rtol = 1e-13
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+
+def _clamp(v, lo, hi):
+    return max(min(v, hi), lo)
+
+
+class State:
+    """All arrays the reference driver keeps as locals (pylamp2.py:100-127), in HBM.
+
+    ``tr_x`` is (M,2) [z,x] like the reference; marker properties are 13 separate columns
+    (``cols[TR_*]``, SoA) instead of the reference's (M,13) ``tr_f``."""
+
+    def __init__(self, nx, L, tr_x, tr_f, device=None):
+        self.ctx = _lib.default_context(device)
+        dev = self.ctx.torch_device
+        self.nx, self.L = [int(n) for n in nx], [float(v) for v in L]
+        self.dx = [self.L[i] / (self.nx[i] - 1) for i in range(DIM)]
+        self.grid, self.gridmp = make_grids(self.nx, self.L)
+        self.tr_x = _to_dev(tr_x, dev)
+        if isinstance(tr_f, (list, tuple)):
+            self.cols = [_to_dev(c, dev) for c in tr_f]
+        else:
+            tf = np.asarray(tr_f)
+            self.cols = [_to_dev(np.ascontiguousarray(tf[:, k]), dev) for k in range(NFTRAC)]
+        z = lambda: torch.zeros(tuple(self.nx), dtype=torch.float64, device=dev)
+        self.f_etas, self.f_T, self.f_rho, self.f_Cp, self.f_etan = z(), z(), z(), z(), z()
+        self.f_k = [z(), z()]
+        self.f_H, self.f_mat, self.f_sgc = z(), z(), z()
+        self.it, self.totaltime = 0, 0.0
+        self.newvel, self.newpres, self.newtemp = None, None, None
+        self.trac_vel, self.tstep, self.limiter = None, None, ""
+        self.kelem, self.count = None, None
+        self.stokes_op, self.diff_op = None, None
+        self.stats = {}
+
+    @property
+    def ntrac(self):
+        return self.tr_x.shape[0]
+
+    def tr_f_host(self):
+        """(M,13) NumPy array in the reference's tr_f layout."""
+        return np.stack([c.cpu().numpy() for c in self.cols], axis=1)
+
+
+def _to_dev(a, dev):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+
+def timestep(s, o, want_kelem=True):
+    """One pass of the loop body pylamp2.py:273-594 on device-resident state."""
+    ctx = s.ctx
+    s.it += 1
+    nx, grid, gridmp = s.nx, s.grid, s.gridmp
+    cols, tr_x = s.cols, s.tr_x
+    # marker property update, pylamp2.py:291-303
+    markers.update_properties(cols[TR_TMP], cols[TR_RH0], cols[TR_ALP], cols[TR_ACE], cols[TR_ET0],
+                              o.tdep_rho, o.tdep_eta, o.Tref, o.etamin, o.etamax,
+                              rho_out=cols[TR_RHO], eta_out=cols[TR_ETA])
+    # markers -> grids, pylamp2.py:307-319
+    mm = pylamp_trac.marker_minmax(tr_x, ctx)
+    t2g = pylamp_trac.trac2grid_device
+    if o.do_advect and o.do_heatdiff:
+        t2g(ctx, tr_x, [cols[k] for k in (TR_RHO, TR_ETA, TR_HCP, TR_TMP, TR_IHT, TR_MAT)],
+            [INTERP_AVG_ARITHW, INTERP_AVG_GEOMW] + [INTERP_AVG_ARITHW] * 4, grid,
+            [s.f_rho, s.f_etas, s.f_Cp, s.f_T, s.f_H, s.f_mat], mm)
+        t2g(ctx, tr_x, [cols[TR_ETA]], [INTERP_AVG_GEOMW], gridmp, [s.f_etan], mm)
+        t2g(ctx, tr_x, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [gridmp[IZ], grid[IX]], [s.f_k[IZ]], mm)
+        t2g(ctx, tr_x, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [grid[IZ], gridmp[IX]], [s.f_k[IX]], mm)
+    elif o.do_advect:
+        t2g(ctx, tr_x, [cols[TR_RHO], cols[TR_ETA]], [INTERP_AVG_ARITHW, INTERP_AVG_GEOMW], grid,
+            [s.f_rho, s.f_etas], mm)
+        t2g(ctx, tr_x, [cols[TR_ETA]], [INTERP_AVG_GEOMETRIC], gridmp, [s.f_etan], mm)
+    else:
+        raise NotImplementedError("heat-only mode (pylamp2.py:321-331) is outside the hot path")
+    if o.do_heatdiff and s.it > 1:                                                  # :333-337
+        s.f_T[:, 0], s.f_T[:, -1] = s.newtemp[:, 0], s.newtemp[:, -1]
+        s.f_T[0, :], s.f_T[-1, :] = s.newtemp[0, :], s.newtemp[-1, :]
+    if o.do_heatdiff:                                                               # :339-343
+        diffusivity = markers.max_diffusivity2(s.f_k[IZ], s.f_rho, s.f_Cp)
+        tstep_temp = _clamp(o.tstep_modifier * min(s.dx) ** 2 / diffusivity, o.tstep_dif_min,
+                            o.tstep_dif_max)
+    # Stokes system + solve, pylamp2.py:353-362
+    if s.stokes_op is None:
+        s.stokes_op = pylamp_stokes.StokesOperator(nx, grid, s.f_etas, s.f_etan, s.f_rho, o.bcstokes,
+                                                   ctx=ctx)
+        for k, v in o.stokes_params.items():
+            s.stokes_op.set_param(k, v)
+    else:
+        s.stokes_op.set_coeffs(s.f_etas, s.f_etan, s.f_rho)
+    x = s.stokes_op.solve(None, rtol=o.stokes_rtol, maxit=o.stokes_maxit)
+    s.stats["stokes_iters"] = s.stokes_op.iterations
+    s.stats["stokes_relres"] = s.stokes_op.relres
+    s.newvel, s.newpres = pylamp_stokes.x2vp(x, nx)
+    vmax = max(markers.field_max(s.newvel[IZ]), markers.field_max(s.newvel[IX]))   # :364 (signed)
+    tstep_stokes = _clamp(o.tstep_modifier * min(s.dx) / vmax, o.tstep_adv_min, o.tstep_adv_max)
+    if o.do_heatdiff:                                                               # :374-385
+        s.limiter = "H" if tstep_temp < tstep_stokes else "S"
+        tstep = min(tstep_temp, tstep_stokes)
+    else:
+        tstep, s.limiter = tstep_stokes, "S"
+    s.tstep = tstep
+    s.totaltime += tstep
+    if o.do_heatdiff:                                                               # :415-480
+        args = (s.f_T, s.f_k, s.f_Cp, s.f_rho, s.f_H, tstep)
+        if s.diff_op is None:
+            s.diff_op = pylamp_diff.DiffusionOperator(nx, grid, gridmp, *args[:5], o.bcheat,
+                                                      o.bcheatvals, tstep, ctx=ctx)
+        else:
+            s.diff_op.set_coeffs(*args)
+        newtemp = pylamp_diff.x2t(s.diff_op.solve(None, rtol=o.heat_rtol), nx)
+        s.stats["heat_iters"] = s.diff_op.iterations
+        T = cols[TR_TMP]
+        g2t = pylamp_trac.grid2trac_device
+        interp = torch.empty_like(T)
+        if s.it == 1:                                                               # :441-447
+            nbad = g2t(ctx, tr_x, grid, [newtemp], nx, INTERP_METHOD_LINEAR, float("nan"), [interp])
+            if nbad:
+                raise Exception("stopOnError in grid2trac")
+            T.copy_(interp)
+        else:                                                                       # :448-480
+            old_T = T.clone() if o.do_subgrid_heatdiff else None
+            dT_grid = newtemp - s.f_T
+            nbad = g2t(ctx, tr_x, grid, [dT_grid], nx, INTERP_METHOD_LINEAR, float("nan"), [interp])
+            if nbad:
+                raise Exception("stopOnError in grid2trac")
+            T.add_(interp)
+            if o.do_subgrid_heatdiff:                                               # :471-480
+                Tsg, dT = markers.subgrid_stage1(tstep, s.dx[IZ], s.dx[IX], old_T, T, cols[TR_HCP],
+                                                 cols[TR_RHO], cols[TR_HCD])
+                t2g(ctx, tr_x, [dT], [INTERP_AVG_ARITHW], grid, [s.f_sgc], mm)
+                nbad = g2t(ctx, tr_x, grid, [s.f_sgc], nx, INTERP_METHOD_LINEAR, float("nan"), [interp])
+                if nbad:
+                    raise Exception("stopOnError in grid2trac")
+                markers.subgrid_stage2(Tsg, interp, T)
+        s.newtemp = newtemp
+    # velocities to cell centres + BC ring, RK4, pylamp2.py:491-550
+    vzc, vxc = markers.centre_velocities(s.newvel[IZ], s.newvel[IX], o.bcstokes)
+    pre = [gridmp[d][0] - (gridmp[d][1] - gridmp[d][0]) for d in range(DIM)]
+    newgrid = [np.insert(gridmp[IZ], 0, pre[IZ]), np.insert(gridmp[IX], 0, pre[IX])]
+    s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep)
+    # fence + per-cell count, pylamp2.py:558-593
+    if not o.tracs_fence_enabled:
+        raise NotImplementedError("marker deletion (fence disabled / FLOWTHRU): SURVEY.md §8f-1")
+    markers.fence(s.tr_x, s.L, EPS)
+    s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=want_kelem)
+    return s

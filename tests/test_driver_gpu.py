@@ -1,0 +1,94 @@
+"""GPU parity of the whole timestep (pylamp2.py:273-594): the device-resident driver versus the
+oracle's restated loop body (itself pinned to the reference's own np.savez output, see
+test_oracle_golden.py) and versus the committed golden dumps of the unmodified reference.
+
+Tolerances.  Thermo-mechanical variant (smooth Arrhenius viscosity): velocity, pressure and
+temperature 1e-8 relative L2 at every step, marker positions 1e-10 relative (north_star).
+C1 as shipped (eta contrast 1e10): the reference's own direct solve is reproducible only to
+~1e-5 (oracle raw-vs-refined distance, printed), so fields are held to 3x that floor.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pylamp_oracle as O
+from pylamp_b200 import setups
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(np.asarray(b).ravel()), 1e-300)
+
+
+def _run_both(setup, nsteps, tol_fields, tol_first=None, **okw):
+    from pylamp_b200 import driver
+    nx, L, tr_x, tr_f, opts = setup
+    so = O.State(nx, L, tr_x.copy(), tr_f.copy())
+    oo = O.Options(solve=O.solve_refined, **opts)
+    sg = driver.State(nx, L, tr_x, tr_f)
+    og = driver.Options(**opts, **okw)
+    out = []
+    for it in range(nsteps):
+        O.timestep(so, oo)
+        driver.timestep(sg, og)
+        e = {"vz": _rel(sg.newvel[0], so.newvel[0]), "vx": _rel(sg.newvel[1], so.newvel[1]),
+             "P": _rel(sg.newpres, so.newpres), "rho": _rel(sg.f_rho, so.f_rho),
+             "x": _rel(sg.tr_x, so.tr_x), "dt": abs(sg.tstep - so.tstep) / so.tstep}
+        if oo.do_heatdiff:
+            e["T"] = _rel(sg.newtemp, so.newtemp)
+            e["Tm"] = _rel(sg.cols[O.TR_TMP], so.tr_f[:, O.TR_TMP])
+        print("step", it + 1, "iters", sg.stats, {k: "%.1e" % v for k, v in e.items()}, sg.limiter, so.limiter)
+        tol = tol_first if (it == 0 and tol_first) else tol_fields
+        for k in ("vz", "vx", "P", "T"):
+            if k in e:
+                assert e[k] <= tol, (it, k, e[k])
+        assert e["rho"] <= 1e-12
+        assert sg.limiter == so.limiter
+        # cell indices are bit-exact for identical positions; after a GPU-solved step positions
+        # differ by ~1e-12 relative, so compare counts through the markers that agree
+        kg, cg = sg.kelem.cpu().numpy(), sg.count.cpu().numpy()
+        assert cg.sum() == so.count.sum() == sg.ntrac
+        assert np.mean(kg == so.kelem) > 0.9999
+        out.append(e)
+    return sg, so, out
+
+
+def test_thermo_variant_vs_oracle_and_golden():
+    gold = np.load(os.path.join(GOLDEN, "thermo_variant.npz"))
+    setup = setups.thermo_variant(int(gold["seed"]))
+    sg, so, errs = _run_both(setup, int(gold["nsteps"]), tol_fields=1e-8)
+    for e in errs:
+        assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
+    # golden dump of the unmodified reference (raw spsolve), last step
+    it = int(gold["nsteps"]) - 1
+    stride = int(gold["stride"])
+    for k, v in (("velz", sg.newvel[0]), ("velx", sg.newvel[1]), ("pres", sg.newpres), ("temp", sg.newtemp)):
+        assert _rel(v, gold["s%d_%s" % (it, k)]) < 1e-7, k
+    assert np.allclose(sg.tr_x.cpu().numpy()[::stride], gold["s%d_tr_x" % it], rtol=1e-9, atol=0)
+
+
+def test_c1_shipped_noinject_vs_oracle():
+    gold = np.load(os.path.join(GOLDEN, "c1_noinject.npz"))
+    setup = setups.c1_shipped(int(gold["seed"]))
+    # oracle noise floor of this system (raw spsolve vs refined): ~5e-6 velocity, 3e-3 pressure
+    sg, so, errs = _run_both(setup, 2, tol_fields=3e-5)
+    for e in errs:
+        assert e["x"] <= 1e-8
+    assert sg.ntrac == int(gold["s1_ntrac"])
+
+
+def test_rayleigh_taylor_small():
+    sg, so, errs = _run_both(setups.rayleigh_taylor(ncell=64), 3, tol_fields=1e-8)
+    for e in errs:
+        assert e["x"] <= 1e-10
+
+
+def test_convection_small():
+    sg, so, errs = _run_both(setups.convection(ncell=64), 3, tol_fields=1e-8)
+    for e in errs:
+        assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
