@@ -65,9 +65,10 @@ struct plb_stokes {
     plb_fgmres_ws kry;
     double *xs = nullptr, *r3 = nullptr, *b3 = nullptr, *t3 = nullptr, *gz_d = nullptr, *gx_d = nullptr;
     // parameters
+    int hydrostatic = 1;
     int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
     double cheb_ratio = 8.0;
-    double rtol_accept = 0;       // a stalled solve is still accepted below this true residual
+    double rtol_accept = 1e-8;    // a solve stalled at its fp64 floor is accepted below this true residual
     // statistics of the last solve
     int last_iters = 0, last_vcycles = 0;
     double last_relres = 0;
@@ -601,15 +602,53 @@ k_dense_solve(LevelDev L, int n, const double* __restrict__ inv, const double* _
     }
 }
 
+// ---- hydrostatic splitting --------------------------------------------------------------------
+// The z-momentum right-hand side is dominated by the horizontally uniform (lithostatic) load, which
+// is balanced exactly by a pressure P_h(z): A [0,0,P_h] has entries only on the vz rows and they
+// do not depend on j.  Solving for the deviation from P_h makes the residual norm relative to the
+// flow-driving part of the load, so that near-hydrostatic states are resolved to the same
+// relative accuracy as a direct solve.  m[i] = mean_j b_vz(i,j) over the vz rows of grid row i.
+__global__ void __launch_bounds__(256) k_row_mean(LevelDev L, const double* __restrict__ bz, double* __restrict__ m) {
+    const int i = blockIdx.x;
+    double s = 0;
+    if (i >= L.vz_i0 && i <= L.vz_i1)
+        for (int j = L.vz_j0 + threadIdx.x; j <= L.vz_j1; j += blockDim.x) s += bz[(long long)i * L.ld + j];
+    s = warp_sum(s);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; q++) s += sm[q];
+        m[i] = (i >= L.vz_i0 && i <= L.vz_i1) ? s / (L.vz_j1 - L.vz_j0 + 1) : 0.0;
+    }
+}
+// P_h per cell row with P_h(row 3) = 0 (the anchor row): -2 Kc idzc[i] (P_h[i] - P_h[i-1]) = m[i]
+__global__ void k_scan_ph(LevelDev L, double Kc, const double* __restrict__ m, double* __restrict__ ph) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nz = L.nz;
+    ph[0] = 0;
+    for (int i = 1; i <= nz - 2; i++) ph[i] = ph[i - 1] - m[i] / (2 * Kc * L.idzc[i]);
+    ph[nz - 1] = 0;
+    const double p3 = ph[3];
+    for (int i = 0; i <= nz - 2; i++) ph[i] -= p3;
+}
+__global__ void __launch_bounds__(BX* BY)
+k_sub_row_mean(LevelDev L, const double* __restrict__ m, double* __restrict__ bz) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    if (is_vz_row(L, i, j)) bz[(long long)i * L.ld + j] -= m[i];
+}
+
 // final solution: planar -> interleaved with the slaved corner pressures filled in
 __global__ void __launch_bounds__(BX* BY)
 k_solution_out(LevelDev L, const double* __restrict__ vz, const double* __restrict__ vx,
-               const double* __restrict__ p, double* __restrict__ x) {
+               const double* __restrict__ p, const double* __restrict__ ph, double* __restrict__ x) {
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     if (i >= L.nz || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j, t = (long long)i * L.nxx + j;
     double pv = p[o];
     if ((i == 0 || i == L.nz - 2) && (j == 0 || j == L.nxx - 2)) pv = (j == 0) ? p[o + 1] : p[o - 1];
+    if (ph) pv += ph[i];
     if (i == L.nz - 1 || j == L.nxx - 1) pv = 0;
     x[3 * t] = vz[o], x[3 * t + 1] = vx[o], x[3 * t + 2] = pv;
 }
@@ -885,7 +924,7 @@ int plb_stokes_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_gri
     op->ctx = ctx, op->nz = nz, op->nxx = nxx, op->ld = ld;
     for (int w = 0; w < 4; w++) op->bc[w] = h_bc[w];
     if (plb_reduce_ws_init(ctx, &op->rws)) { delete op; return 2; }
-    if (zalloc(ctx, &op->d_scal, 1024)) { delete op; return 2; }
+    if (zalloc(ctx, &op->d_scal, 1024 + 2 * (size_t)nz)) { delete op; return 2; }
     if (build_levels(op, h_grid_z, h_grid_x)) { plb_stokes_destroy(op); return 2; }
     std::vector<double> gz(h_grid_z, h_grid_z + nz), gx(h_grid_x, h_grid_x + nxx);
     if (upload(ctx, gz, &op->gz_d) || upload(ctx, gx, &op->gx_d)) { plb_stokes_destroy(op); return 2; }
@@ -919,6 +958,7 @@ int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     else if (!strcmp(name, "nu_coarse")) op->nu_coarse = (int)value;
     else if (!strcmp(name, "reorth")) op->reorth = (int)value;
     else if (!strcmp(name, "rtol_accept")) op->rtol_accept = value;
+    else if (!strcmp(name, "hydrostatic")) op->hydrostatic = (int)value;
     else PLB_FAIL(ctx, "plb_stokes_set_param: unknown parameter '%s'", name);
     return 0;
 }
@@ -1032,6 +1072,17 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         k_stokes_rhs<<<g, blk, 0, ctx->stream>>>(D, op->rho, op->g_z, op->g_x, b, b + P, b + 2 * P);
     }
     PLB_LAUNCHED(ctx);
+    double* ph = nullptr;
+    if (op->hydrostatic) {
+        double* m = op->d_scal + 1024;        // [nz] row means, then [nz] P_h
+        ph = m + L.nz;
+        k_row_mean<<<L.nz, 256, 0, ctx->stream>>>(D, b, m);
+        PLB_LAUNCHED(ctx);
+        k_scan_ph<<<1, 1, 0, ctx->stream>>>(D, Kc, m, ph);
+        PLB_LAUNCHED(ctx);
+        k_sub_row_mean<<<g, blk, 0, ctx->stream>>>(D, m, b);
+        PLB_LAUNCHED(ctx);
+    }
     PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
     auto residual = [&](double* out) -> int {
         k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, x, x + P, x + 2 * P, b, b + P, b + 2 * P, out, out + P,
@@ -1068,7 +1119,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     op->last_iters = total, op->last_vcycles = vcycles, op->last_relres = res.relres;
     if (h_iters) *h_iters = total;
     if (h_relres) *h_relres = res.relres;
-    k_solution_out<<<g, blk, 0, ctx->stream>>>(D, x, x + P, x + 2 * P, d_x);
+    k_solution_out<<<g, blk, 0, ctx->stream>>>(D, x, x + P, x + 2 * P, ph, d_x);
     PLB_LAUNCHED(ctx);
     if (!res.converged && res.relres > op->rtol_accept)
         PLB_FAIL(ctx, "plb_stokes_solve: not converged after %d iterations (relres %.3e > rtol %.3e, "
