@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- PyLamp hot-path benchmark on B200 (one timestep = one pass of the loop body
+pylamp2.py:273-594: marker->grid, Stokes solve, energy solve, grid->marker, RK4 advection, fence,
+per-cell count).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): 2-D thermal convection,
+Ra=1e6, Arrhenius viscosity clipped to [1e17,1e23], 4096^2 cells (4097^2 nodes), 16 markers/cell
+(2.7e8 markers), coupled Stokes + energy + marker advection, synthetic fields generated in HBM.
+Prints ONE JSON line (contract in the task statement).  `value` times the device-resident driver;
+`e2e` times the same step through host buffers (pinned host -> device marker/field upload and
+device -> host result download inside the timed region).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLASS_NAMES = {0: "k_cheb (Chebyshev-Jacobi smoother sweep, finest level)",
+               1: "k_stokes_op (coupled Stokes residual/apply)", 2: "k_multi_dot", 3: "k_multi_axpy2",
+               4: "k_t2g_scatter (trac2grid)", 5: "k_rk4", 6: "k_grid2trac",
+               7: "coarse part of the V-cycle (levels >= 1, many launches)",
+               8: "finest-level residual+restrict+prolong", 9: "k_precond_rhs", 10: "k_diff", 11: "marker misc"}
+SINGLE_KERNEL_CLASSES = (0, 1, 2, 3, 4, 5, 6, 9)
+
+
+def peaks():
+    """HBM peak: MEASURED_PEAKS.json (driver-written) else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool's B200)"
+        except Exception:
+            pass
+    return 7700.0, "fallback: B200_PROFILING.md nominal HBM3e 7.7 TB/s"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.05):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period, self._stop_evt = period, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_steps(ncell, nsteps, warmup):
+    """The reference algorithm (oracle restatement of pylamp2.py's loop body with scipy spsolve)
+    on the host CPU: returns (seconds per step list, nx, markers, per-phase timers)."""
+    from oracle import pylamp_oracle as O
+    from pylamp_b200 import setups
+    nx, L, tr_x, tr_f, opts = setups.convection(ncell=ncell)
+    s, o = O.State(nx, L, tr_x, tr_f), O.Options(**opts)
+    times, timers = [], {}
+    for it in range(warmup + nsteps):
+        t = time.perf_counter()
+        O.timestep(s, o, timers if it >= warmup else None)
+        if it >= warmup:
+            times.append(time.perf_counter() - t)
+    return times, nx, tr_x.shape[0], timers
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncell = args.ref_ncell
+    times, nx, M, timers = cpu_reference_steps(ncell, args.steps, args.warmup)
+    sec = float(np.mean(times))
+    cores = 1
+    sample = ("same C4 convection setup at %d^2 cells (%d markers) instead of 4096^2: scipy SuperLU needs "
+              "days and > host RAM at 4096^2 (BASELINE.md); NumPy/SuperLU path is single-threaded" % (ncell, M))
+    line = {"impl": "reference", "metric": "timesteps_per_s", "value": 1.0 / sec, "unit": "timesteps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C4 thermal convection Ra=1e6 (Stokes+energy+MIC), CPU sample at %d^2 cells, "
+                                   "16 markers/cell" % ncell, "grid_nodes": nx, "markers": M},
+            "stokes_dof_per_s": 3.0 * nx[0] * nx[1] / sec,
+            "cpu_baseline": {"value": 1.0 / sec, "unit": "timesteps/s", "cores": cores, "kind": "port",
+                             "sample": sample, "phases_s": {k: v / args.steps for k, v in timers.items()}},
+            "e2e": {"value": 1.0 / sec, "unit": "timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pylamp_b200 import _lib, driver, setups
+    ctx = _lib.default_context(local)
+    ncell = args.ncell
+    nx, L, tr_x, cols, opts = setups.convection_device(ncell=ncell, per_side=args.per_side, device="cuda:%d" % local)
+    s = driver.State(nx, L, tr_x, cols, device=local)
+    o = driver.Options(**opts)
+    M = s.ntrac
+    N = nx[0] * nx[1]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        driver.timestep(s, o, want_kelem=False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.profile(True)
+    l0 = ctx.launches
+    prof = {}
+    iters = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        driver.timestep(s, o, want_kelem=False)
+        iters.append(dict(s.stats))
+        for k, (c, ms, by) in ctx.profile_read().items():
+            a = prof.setdefault(k, [0, 0.0, 0.0])
+            a[0] += c
+            a[1] += ms
+            a[2] += by
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    ctx.profile(False)
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # ---- e2e: the same step through host buffers (rank-local) ----
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e = run_e2e(torch, driver, s, o, args.e2e_steps)
+        if world > 1:
+            t = torch.tensor([e2e["ms"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e["ms"] = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    single = {k: v for k, v in prof.items() if k in SINGLE_KERNEL_CLASSES}
+    dom = max(single, key=lambda k: single[k][1]) if single else None
+    roofline = None
+    if dom is not None:
+        c, ms, by = prof[dom]
+        ach = by / (ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": CLASS_NAMES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "launches_timed": c, "avg_launch_ms": ms / c,
+                    "algorithmic_bytes_per_launch": by / c, "peak_source": peak_src,
+                    "share_of_step": ms / (ms_step * args.steps)}
+    breakdown = {CLASS_NAMES[k]: {"launch_groups": v[0], "ms_per_step": v[1] / args.steps,
+                                  "GBps": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 and v[2] > 0 else None}
+                 for k, v in sorted(prof.items())}
+    value = world / (ms_step * 1e-3)          # independent replicas per rank until slabs land
+    line = {"metric": "timesteps_per_s", "value": value, "unit": "timesteps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 thermal convection Ra=1e6, Arrhenius viscosity clipped [1e17,1e23], "
+                                   "%d^2 cells, %d markers/cell, Stokes+energy+MIC advection" % (ncell, args.per_side ** 2),
+                       "grid_nodes": nx, "markers": M, "stokes_dof": 3 * N,
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one per GPU)" % world,
+                       "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
+                       "stokes_rtol": o.stokes_rtol},
+            "stokes_dof_per_s": world * 3.0 * N * np.mean([1.0]) / (ms_step * 1e-3),
+            "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": roofline, "kernel_breakdown": breakdown}
+    if e2e is not None:
+        line["e2e"] = {"value": world / (e2e["ms"] * 1e-3), "unit": "timesteps/s",
+                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": args.e2e_steps}
+    if world == 1 and args.cpu_ncell > 0:
+        times, cnx, cM, timers = cpu_reference_steps(args.cpu_ncell, 2, 0)
+        sec = float(np.mean(times))
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "timesteps/s", "cores": 1, "kind": "port",
+                                "sample": "2 steps of the same C4 setup at %d^2 cells (%d markers); the reference "
+                                          "cannot run 4096^2 (SuperLU: days, > host RAM)" % (args.cpu_ncell, cM),
+                                "stokes_dof_per_s": 3.0 * cnx[0] * cnx[1] / sec,
+                                "phases_s": {k: v / 2 for k, v in timers.items()}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, driver, s, o, nsteps):
+    """Same timestep with HOST state: per step, marker coordinates + the 9 live property columns are
+    copied from pinned host memory to the device, the step runs, and new coordinates, marker
+    temperature, marker velocities and the velocity/pressure/temperature grids are copied back."""
+    from pylamp_b200.pylamp_const import (TR_ACE, TR_ALP, TR_ET0, TR_HCD, TR_HCP, TR_IHT, TR_MAT, TR_RH0, TR_TMP)
+    live = [TR_TMP, TR_RH0, TR_ALP, TR_ACE, TR_ET0, TR_HCD, TR_HCP, TR_IHT, TR_MAT]
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+    h_x = pin(s.tr_x)
+    h_cols = {k: pin(s.cols[k]) for k in live}
+    h_v = torch.empty(s.tr_x.shape, dtype=torch.float64, pin_memory=True)
+    h_grids = [torch.empty(tuple(s.nx), dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    h2d = h_x.numel() * 8 + sum(c.numel() * 8 for c in h_cols.values())
+    d2h = h_x.numel() * 8 * 2 + h_cols[TR_TMP].numel() * 8 + 4 * h_grids[0].numel() * 8
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(nsteps):
+        s.tr_x.copy_(h_x, non_blocking=True)
+        for k in live:
+            s.cols[k].copy_(h_cols[k], non_blocking=True)
+        driver.timestep(s, o, want_kelem=False)
+        h_x.copy_(s.tr_x, non_blocking=True)
+        h_cols[TR_TMP].copy_(s.cols[TR_TMP], non_blocking=True)
+        h_v.copy_(s.trac_vel, non_blocking=True)
+        for h, d in zip(h_grids, (s.newvel[0], s.newvel[1], s.newpres, s.newtemp)):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+    ev1.record()
+    torch.cuda.synchronize()
+    return {"ms": ev0.elapsed_time(ev1) / nsteps, "h2d": int(h2d), "d2h": int(d2h)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncell", type=int, default=4096, help="cells per side of the GPU workload")
+    ap.add_argument("--per-side", type=int, default=4, help="markers per cell side (16/cell)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
+    ap.add_argument("--ref-ncell", type=int, default=192, help="--impl reference sample size")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

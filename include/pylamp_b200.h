@@ -54,6 +54,14 @@ const char* plb_last_error(plb_ctx* ctx);
 /* number of CUDA kernels this library has launched on the context so far */
 long long plb_launch_count(plb_ctx* ctx);
 const char* plb_version(void);
+/* per-kernel-class timing with CUDA event pairs recorded around the launches on the context's
+ * stream (classes: 0 smoother sweep on the finest level, 1 coupled Stokes operator, 2 multi-dot,
+ * 3 multi-axpy, 4 trac2grid scatter, 5 RK4, 6 grid2trac, 7 coarse part of a V-cycle, 8 finest-level
+ * residual/restriction/prolongation, 9 preconditioner rhs, 10 heat operator, 11 other marker
+ * kernels).  plb_profile_read fills h_count[16], h_ms[16], h_bytes[16] (algorithmic bytes of the
+ * recorded launches) and resets. */
+int plb_profile_enable(plb_ctx* ctx, int on);
+int plb_profile_read(plb_ctx* ctx, long long* h_count, double* h_ms, double* h_bytes);
 
 /* ---- markers -> grid: pylamp_trac.trac2grid, pylamp_trac.py:161-318 -------------------- */
 /* h_out[4] = min z, max z, min x, max x over the markers (the ghost-node extension test of

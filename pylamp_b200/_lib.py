@@ -26,6 +26,8 @@ _PROTOS = {
     "plb_ctx_sync": (I, [VP]),
     "plb_last_error": (C.c_char_p, [VP]),
     "plb_launch_count": (LL, [VP]),
+    "plb_profile_enable": (I, [VP, I]),
+    "plb_profile_read": (I, [VP, C.POINTER(LL), DP, DP]),
     "plb_marker_minmax": (I, [VP, LL, VP, DP]),
     "plb_trac2grid": (I, [VP, LL, VP, I, PP, IP, VP, I, VP, I, D, D, D, D, I, I, I, I, I, PP]),
     "plb_grid2trac": (I, [VP, LL, VP, I, I, PP, VP, I, VP, I, I, D, D, D, D, D, PP,
@@ -125,6 +127,15 @@ class Context:
 
     def sync(self):
         self.check(self.lib.plb_ctx_sync(self.h))
+
+    def profile(self, on=True):
+        self.call("plb_profile_enable", 1 if on else 0)
+
+    def profile_read(self):
+        """{class index: (launch count, total ms, algorithmic bytes)} since the last read."""
+        cnt, ms, by = (LL * 16)(), (D * 16)(), (D * 16)()
+        self.call("plb_profile_read", cnt, ms, by)
+        return {i: (int(cnt[i]), float(ms[i]), float(by[i])) for i in range(16) if cnt[i]}
 
     @property
     def launches(self):

@@ -138,6 +138,8 @@ int plb_multi_dot(plb_ctx* ctx, plb_reduce_ws* ws, long long n, int k, const dou
                   const double* w, double* d_out) {
     int grid = vec_grid(ctx, n);
     if (grid > ws->max_blocks) grid = ws->max_blocks;
+    // k vectors read once, w once per chunk of 8
+    plb_prof_scope prof_(ctx, PLB_K_MDOT, 8.0 * (double)n * (k + (k + PLB_DOT_CHUNK - 1) / PLB_DOT_CHUNK));
     for (int j0 = 0; j0 < k; j0 += PLB_DOT_CHUNK) {
         int J = k - j0 < PLB_DOT_CHUNK ? k - j0 : PLB_DOT_CHUNK;
         VecList V;
@@ -158,6 +160,8 @@ int plb_dot(plb_ctx* ctx, plb_reduce_ws* ws, long long n, const double* a, const
 int plb_multi_axpy2(plb_ctx* ctx, long long n, int k, const double* d_h, const double* const* h_V,
                     double* w, const double* const* h_U, double* u) {
     int grid = vec_grid(ctx, n);
+    // k (2k) vectors read once, w (and u) read+written once per chunk of 8
+    plb_prof_scope prof_(ctx, PLB_K_MAXPY, 8.0 * (double)n * (h_U ? 2 : 1) * (k + 2 * ((k + PLB_DOT_CHUNK - 1) / PLB_DOT_CHUNK)));
     for (int j0 = 0; j0 < k; j0 += PLB_DOT_CHUNK) {
         int J = k - j0 < PLB_DOT_CHUNK ? k - j0 : PLB_DOT_CHUNK;
         VecList2 L;

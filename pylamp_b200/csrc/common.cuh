@@ -18,6 +18,41 @@ struct plb_ctx {
     size_t ws_bytes;
     double* h_pinned;      // small pinned staging buffer for scalar read-backs
     int num_sms;
+    // optional per-kernel-class timing with CUDA event pairs on the launching stream
+    bool prof_on;
+    cudaEvent_t* prof_ev;  // 2 * prof_cap events
+    int* prof_cls;
+    int prof_cap, prof_used;
+    long long prof_skipped[16];
+    double* prof_bytes;    // algorithmic bytes per recorded pair
+};
+
+// kernel classes for plb_profile_* (bench.py's roofline block)
+enum {
+    PLB_K_CHEB0 = 0,     // Chebyshev-Jacobi smoother sweep, finest level
+    PLB_K_STOKES_OP = 1, // coupled Stokes residual / apply, finest level
+    PLB_K_MDOT = 2,      // fused multi-dot (Gram-Schmidt)
+    PLB_K_MAXPY = 3,     // fused multi-axpy
+    PLB_K_T2G = 4,       // marker -> grid scatter
+    PLB_K_RK4 = 5,       // RK4 advection
+    PLB_K_G2T = 6,       // grid -> marker interpolation
+    PLB_K_MGCOARSE = 7,  // everything below the finest MG level (whole coarse part of a V-cycle)
+    PLB_K_MGXFER0 = 8,   // finest-level residual + restriction + prolongation
+    PLB_K_PRECRHS = 9,   // preconditioner right-hand side
+    PLB_K_DIFF = 10,     // heat operator
+    PLB_K_MARKER_MISC = 11,
+    PLB_K_NCLASS = 16
+};
+
+void plb_prof_begin(plb_ctx* ctx, int cls, double bytes);
+void plb_prof_end(plb_ctx* ctx);
+struct plb_prof_scope {   // cls < 0: no-op (scopes must not nest)
+    plb_ctx* c;
+    bool live;
+    plb_prof_scope(plb_ctx* ctx, int cls, double bytes = 0) : c(ctx), live(ctx->prof_on && cls >= 0) {
+        if (live) plb_prof_begin(c, cls, bytes);
+    }
+    ~plb_prof_scope() { if (live) plb_prof_end(c); }
 };
 
 #define PLB_FAIL(ctx, ...)                                     \

@@ -37,6 +37,12 @@ void plb_ctx_destroy(plb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < 2 * ctx->prof_cap; i++) cudaEventDestroy(ctx->prof_ev[i]);
+        delete[] ctx->prof_ev;
+        delete[] ctx->prof_cls;
+        delete[] ctx->prof_bytes;
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -63,7 +69,55 @@ const char* plb_last_error(plb_ctx* ctx) { return ctx ? ctx->err : "null context
 
 long long plb_launch_count(plb_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+int plb_profile_enable(plb_ctx* ctx, int on) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on && !ctx->prof_ev) {
+        ctx->prof_cap = 16384;
+        ctx->prof_ev = new cudaEvent_t[2 * ctx->prof_cap];
+        ctx->prof_cls = new int[ctx->prof_cap];
+        ctx->prof_bytes = new double[ctx->prof_cap];
+        for (int i = 0; i < 2 * ctx->prof_cap; i++) PLB_CUDA(ctx, cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    ctx->prof_used = 0;
+    for (int i = 0; i < 16; i++) ctx->prof_skipped[i] = 0;
+    ctx->prof_on = on != 0;
+    return 0;
+}
+
+int plb_profile_read(plb_ctx* ctx, long long* h_count, double* h_ms, double* h_bytes) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < PLB_K_NCLASS; i++) h_count[i] = 0, h_ms[i] = 0, h_bytes[i] = 0;
+    for (int i = 0; i < ctx->prof_used; i++) {
+        float ms = 0;
+        PLB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        h_count[ctx->prof_cls[i]]++;
+        h_ms[ctx->prof_cls[i]] += ms;
+        h_bytes[ctx->prof_cls[i]] += ctx->prof_bytes[i];
+    }
+    ctx->prof_used = 0;
+    return 0;
+}
+
 }  // extern "C"
+
+void plb_prof_begin(plb_ctx* ctx, int cls, double bytes) {
+    if (ctx->prof_used >= ctx->prof_cap) {
+        ctx->prof_skipped[cls]++;
+        return;
+    }
+    ctx->prof_cls[ctx->prof_used] = cls;
+    ctx->prof_bytes[ctx->prof_used] = bytes;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], ctx->stream);
+}
+
+void plb_prof_end(plb_ctx* ctx) {
+    if (ctx->prof_used >= ctx->prof_cap) return;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], ctx->stream);
+    ctx->prof_used++;
+}
 
 int plb_ws_reserve(plb_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return 0;

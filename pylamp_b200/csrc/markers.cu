@@ -461,6 +461,7 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
     a.z0 = z0, a.zlen = zlen, a.x0 = x0, a.xlen = xlen, a.k = k;
     PLB_CUDA(ctx, cudaMemsetAsync(w, 0, nplanes * plane * sizeof(double), ctx->stream));
     if (M > 0) {
+        plb_prof_scope prof_(ctx, PLB_K_T2G, (16.0 + 8.0 * k) * (double)M);
         const double2* x = (const double2*)d_tr_x;
         switch (k) {
             case 1: launch_scatter<1>(ctx, M, x, a); break;
@@ -500,6 +501,7 @@ int plb_grid2trac(plb_ctx* ctx, long long M, const double* d_tr_x, int method, i
     a.k = k;
     for (int f = 0; f < k; f++) a.f[f] = h_fields[f], a.out[f] = h_out[f];
     if (M > 0) {
+        plb_prof_scope prof_(ctx, PLB_K_G2T, (16.0 + 8.0 * k) * (double)M);
         k_grid2trac<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
             M, (const double2*)d_tr_x, method, g, a, defval, d_bad);
         PLB_LAUNCHED(ctx);
@@ -522,6 +524,7 @@ int plb_rk4(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_vz_
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     G2TGrid g = {d_gc_z, d_gc_x, nzc, nxc, ld, z0, zlen, x0, xlen};
     if (M > 0) {
+        plb_prof_scope prof_(ctx, PLB_K_RK4, (d_v_out ? 48.0 : 32.0) * (double)M);
         k_rk4<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
             M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, dt, (double2*)d_x_out, (double2*)d_v_out);
         PLB_LAUNCHED(ctx);

@@ -755,6 +755,7 @@ double* smooth(plb_stokes* op, int l, const double* b, double* cur, double* othe
             double rn = 1.0 / (2 * sigma - rho);
             cd = rn * rho, cr = 2 * rn / delta, rho = rn;
         }
+        plb_prof_scope prof_(ctx, l == 0 ? PLB_K_CHEB0 : -1, ((k == 0 && from_zero) ? 64.0 : 96.0) * (double)P);
         if (k == 0 && from_zero) {
             // result goes to `cur` (no input needed)
             k_cheb<true><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(
@@ -795,16 +796,25 @@ int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
     // write 1 -> xout, 2 -> T, 3 -> xout ...: after nu writes the iterate is in (nu odd ? xout : T)
     double* cur = smooth(op, l, b, xout, other, true, op->nu);
     double* oth = (cur == xout) ? other : xout;
-    k_vel_op<0><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, cur, cur + P, b, b + P, L.r, L.r + P);
-    PLB_LAUNCHED(ctx);
     Level& Cl = op->lv[l + 1];
     const LevelDev DC = Cl.dev();
-    k_restrict<<<grid2d(Cl.nz, Cl.nxx), block2d(), 0, ctx->stream>>>(D, DC, L.r, L.r + P, Cl.b, Cl.b + Cl.plane);
-    PLB_LAUNCHED(ctx);
-    if (vcycle(op, l + 1, Cl.b, Cl.X)) return 2;
-    k_prolong_add<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, DC, Cl.X, Cl.X + Cl.plane, cur, cur + P,
-                                                                   oth, oth + P);
-    PLB_LAUNCHED(ctx);
+    {
+        plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGXFER0 : -1, 84.0 * (double)P);
+        k_vel_op<0><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, cur, cur + P, b, b + P, L.r, L.r + P);
+        PLB_LAUNCHED(ctx);
+        k_restrict<<<grid2d(Cl.nz, Cl.nxx), block2d(), 0, ctx->stream>>>(D, DC, L.r, L.r + P, Cl.b, Cl.b + Cl.plane);
+        PLB_LAUNCHED(ctx);
+    }
+    {
+        plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGCOARSE : -1);
+        if (vcycle(op, l + 1, Cl.b, Cl.X)) return 2;
+    }
+    {
+        plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGXFER0 : -1, 36.0 * (double)P);
+        k_prolong_add<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, DC, Cl.X, Cl.X + Cl.plane, cur, cur + P,
+                                                                       oth, oth + P);
+        PLB_LAUNCHED(ctx);
+    }
     std::swap(cur, oth);
     cur = smooth(op, l, b, cur, oth, false, op->nu);
     PLB_CUDA(ctx, cudaGetLastError());
@@ -1085,6 +1095,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     }
     PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
     auto residual = [&](double* out) -> int {
+        plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 88.0 * (double)P);
         k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, x, x + P, x + 2 * P, b, b + P, b + 2 * P, out, out + P,
                                                       out + 2 * P);
         PLB_LAUNCHED(ctx);
@@ -1097,15 +1108,19 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     const double bnorm = sqrt(bn2);
     int vcycles = 0;
     auto apply = [&](const double* z, double* c) -> int {
+        plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 64.0 * (double)P);
         k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, z, z + P, z + 2 * P, nullptr, nullptr, nullptr, c,
                                                        c + P, c + 2 * P);
         PLB_LAUNCHED(ctx);
         return 0;
     };
     auto precond = [&](const double* rr, double* z) -> int {
-        k_precond_rhs<<<g, blk, 0, ctx->stream>>>(D, Kc, rr, rr + P, rr + 2 * P, z + 2 * P, L.b, L.b + P);
-        PLB_LAUNCHED(ctx);
-        PLB_CUDA(ctx, cudaMemsetAsync(z, 0, sizeof(double) * 2 * P, ctx->stream));
+        {
+            plb_prof_scope prof_(ctx, PLB_K_PRECRHS, 80.0 * (double)P);
+            k_precond_rhs<<<g, blk, 0, ctx->stream>>>(D, Kc, rr, rr + P, rr + 2 * P, z + 2 * P, L.b, L.b + P);
+            PLB_LAUNCHED(ctx);
+            PLB_CUDA(ctx, cudaMemsetAsync(z, 0, sizeof(double) * 2 * P, ctx->stream));
+        }
         vcycles++;
         return vcycle(op, 0, L.b, z);
     };

@@ -142,3 +142,42 @@ def solcx_fields(n, eta_right=1e6):
     etan = np.where(xc < 0.5, 1.0, eta_right)
     rho = -np.sin(np.pi * zs) * np.cos(np.pi * xs) / G[IZ]
     return nx, L, grid, gridmp, etas, etan, rho
+
+
+def convection_device(ncell=4096, per_side=4, seed=11, Ra=1e6, Lbox=1e6, device="cuda"):
+    """`convection` generated directly in HBM with torch (the 4096^2 case has 2.7e8 markers: ~32 GB
+    of host arrays otherwise).  Same lattice/ordering/physics; the jitter comes from torch's RNG,
+    so positions differ from the NumPy generator's (benchmarks only -- parity tests use `convection`).
+    Returns (nx, L, tr_x (M,2) cuda, cols list of 13 (M,) cuda tensors, opts)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    nx, L = [ncell + 1, ncell + 1], [Lbox, Lbox]
+    ns = ncell * per_side
+    dev = torch.device(device)
+    ci = torch.arange(ncell, device=dev, dtype=torch.float64)
+    si = torch.arange(per_side, device=dev, dtype=torch.float64)
+    # cell-major ordering (cell i, cell j, sub i, sub j)
+    z = ((ci.view(-1, 1, 1, 1) * per_side + si.view(1, 1, -1, 1) + 0.5) / ns).expand(ncell, ncell, per_side, per_side)
+    x = ((ci.view(1, -1, 1, 1) * per_side + si.view(1, 1, 1, -1) + 0.5) / ns).expand(ncell, ncell, per_side, per_side)
+    M = ncell * ncell * per_side * per_side
+    tr_x = torch.empty((M, 2), dtype=torch.float64, device=dev)
+    tr_x[:, 0] = z.reshape(-1)
+    tr_x[:, 1] = x.reshape(-1)
+    tr_x += (torch.rand((M, 2), generator=g, dtype=torch.float64, device=dev) - 0.5) * (0.5 / ns)
+    rho0, alpha, k, cp, Ea = 3300.0, 3.5e-5, 4.0, 1250.0, 120e3
+    dT = 1623.0 - 273.0
+    eta0 = rho0 * G[IZ] * alpha * dT * Lbox ** 3 / ((k / (rho0 * cp)) * Ra)
+    zn, xn = tr_x[:, 0], tr_x[:, 1]
+    T = 273.0 + dT * zn + 0.01 * dT * torch.sin(np.pi * zn) * torch.cos(np.pi * xn)
+    tr_x *= Lbox
+    const = lambda v: torch.full((M,), float(v), dtype=torch.float64, device=dev)
+    cols = [None] * NFTRAC
+    cols[TR_TMP] = T
+    cols[TR_RH0], cols[TR_ALP], cols[TR_HCD], cols[TR_HCP] = const(rho0), const(alpha), const(k), const(cp)
+    cols[TR_ACE], cols[TR_ET0], cols[TR_MAT], cols[TR_IHT] = const(Ea), const(eta0), const(1), const(0)
+    cols[TR_RHO], cols[TR_ETA] = torch.empty_like(T), torch.empty_like(T)
+    # TR_MRK / TR__ID are never read on the hot path: share one zero column
+    cols[TR_MRK] = cols[TR__ID] = cols[TR_IHT]
+    opts = dict(do_heatdiff=True, tdep_rho=True, tdep_eta=True, bcstokes=[BC_FREESLIP] * 4)
+    return nx, L, tr_x, cols, opts
