@@ -143,6 +143,7 @@ def run_b200(args):
     nx, L, tr_x, cols, opts = setups.convection_device(ncell=ncell, per_side=args.per_side, device="cuda:%d" % local)
     s = driver.State(nx, L, tr_x, cols, device=local)
     o = driver.Options(**opts)
+    o.stokes_params = {"warm_start": 1, "gcr_m": args.gmres_m}
     M = s.ntrac
     N = nx[0] * nx[1]
 
@@ -218,7 +219,7 @@ def run_b200(args):
                        "grid_nodes": nx, "markers": M, "stokes_dof": 3 * N,
                        "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one per GPU)" % world,
                        "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
-                       "stokes_rtol": o.stokes_rtol},
+                       "stokes_rtol": o.stokes_rtol, "stokes_solver": "FGMRES(%d) + GMG V(3,3) Chebyshev-Jacobi, warm start" % args.gmres_m},
             "stokes_dof_per_s": world * 3.0 * N * np.mean([1.0]) / (ms_step * 1e-3),
             "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "kernel_breakdown": breakdown}
@@ -279,6 +280,7 @@ def main():
     ap.add_argument("--ncell", type=int, default=4096, help="cells per side of the GPU workload")
     ap.add_argument("--per-side", type=int, default=4, help="markers per cell side (16/cell)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--gmres-m", type=int, default=30, help="FGMRES restart length of the Stokes solve")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
     ap.add_argument("--ref-ncell", type=int, default=192, help="--impl reference sample size")
     args = ap.parse_args()

@@ -156,12 +156,15 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
 /* solver tuning: "nu" (Chebyshev steps per smoothing, default 3), "gcr_m" (truncation window, 30),
  * "coarsen_wide" (1: 4x4-cell viscosity averaging, stable with sharp contrasts; 0: 2x2),
  * "cheb_ratio" (8), "dense_max" (largest coarse level solved by a dense inverse, 640),
- * "nu_coarse" (60), "reorth" (0/1 second Gram-Schmidt pass) */
+ * "nu_coarse" (60), "rtol_accept" (1e-8: a solve stalled at its fp64 floor is accepted below
+ * this), "hydrostatic" (1: solve for the deviation from the lithostatic pressure), "warm_start"
+ * (0/1: start from the previous solve's iterate), "reorth_thresh" (1e-4) */
 int plb_stokes_set_param(plb_stokes* op, const char* name, double value);
 /* test hook: one multigrid V-cycle x = V(b) on the velocity block; b, x are two planes
  * [vz | vx] of nz*nxx doubles each */
 int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2);
-/* h_out[3] = {Krylov iterations, V-cycles, final scaled relative residual} of the last solve */
+/* h_out[4] = {Krylov iterations, V-cycles, final scaled relative residual of the last solve,
+ * residual floor learnt so far (0 = none met)} */
 int plb_stokes_last_stats(plb_stokes* op, double* h_out);
 /* x2vp, pylamp_stokes.py:86-101: de-interleave into three (nz x ld) planes */
 int plb_x2vp(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_x, double* d_vz,

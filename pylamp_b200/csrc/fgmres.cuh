@@ -7,7 +7,7 @@
 // least-squares problem is updated on the host with Givens rotations (two scalar read-backs per
 // iteration: the Gram-Schmidt coefficients, then the norm of the new basis vector).
 // Orthogonalisation: classical Gram-Schmidt with one fused multi-dot, and a second pass whenever
-// the first one cancelled more than half of the vector (selective re-orthogonalisation).
+// the first one cancelled the vector by more than two digits (selective re-orthogonalisation).
 // Restarting rather than a sliding window matters here: the preconditioned saddle-point operator
 // has many outlying eigenvalues and truncated recurrences stagnate (oracle/mg_prototype.py).
 // Basis vectors are allocated on first use.
@@ -24,12 +24,14 @@ struct plb_fgmres_ws {
     std::vector<double*> V, Z; // m+1 basis vectors, m directions (device, lazily allocated)
     double* d_scal = nullptr;  // >= m + 8 device scalars
     double* h_coef = nullptr;  // pinned host staging, >= m + 8 doubles
+    double reorth_thresh = 1e-4;   // second Gram-Schmidt pass if |w_after|^2 < thresh * |w_before|^2
 };
 
 struct plb_fgmres_result {
     int iters = 0;
     double relres = 0;         // Arnoldi estimate of || r || / bnorm at exit
     bool converged = false;
+    double floor = 0;          // > 0: the true residual stopped following the Arnoldi estimate here
 };
 
 inline int plb_fgmres_alloc(plb_ctx* ctx, plb_fgmres_ws* ws, int m, long long n, double* d_scal) {
@@ -72,7 +74,8 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
     };
     res->iters = 0, res->converged = false, res->relres = 1;
     int total = 0, stalls = 0;
-    double beta_prev = INFINITY;
+    double beta_prev = INFINITY, est_prev = -1;
+    res->floor = 0;
     while (total < maxit) {
         if (need(ws->V, 0)) return 2;
         if (residual(ws->V[0])) return 2;
@@ -85,9 +88,19 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
             res->converged = true;
             break;
         }
-        // fp64 floor of an ill-conditioned system: restart cycles no longer reduce the TRUE residual
+        // fp64 floor of the residual evaluation (~ eps * n^2 for this operator): the TRUE residual no
+        // longer follows the Arnoldi estimate / restart cycles no longer reduce it
+        // (a mismatch alone can also come from orthogonality loss in a long cycle, which the restart
+        // repairs -- so require that the last cycle also failed to halve the true residual)
+        if (est_prev >= 0 && beta > 5 * est_prev && beta > 0.5 * beta_prev) {
+            res->floor = beta / bnorm;
+            break;
+        }
         stalls = (beta > 0.5 * beta_prev) ? stalls + 1 : 0;
-        if (stalls >= 2) break;
+        if (stalls >= 2) {
+            res->floor = beta / bnorm;
+            break;
+        }
         beta_prev = beta;
         if (plb_scale_rsqrt2(ctx, n, S, ws->V[0], nullptr)) return 2;
         g.assign(m + 1, 0.0);
@@ -111,7 +124,10 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
                 if (plb_fgmres_read(ctx, ws, S, k + 3)) return 2;
                 for (int j = 0; j <= k; j++) hcol[j] += ws->h_coef[j];
                 w2_before = ws->h_coef[k + 1], w2_after = ws->h_coef[k + 2];
-                if (w2_after > 0.25 * w2_before) break;        // little cancellation: done
+                // Re-orthogonalise only after severe cancellation (more than reorth_digits lost).  With a
+                // good preconditioner A^ M is close to the identity, so w always has an O(1) component
+                // along V_k and a "lost half of the norm" test would fire on every step for nothing.
+                if (w2_after > ws->reorth_thresh * w2_before) break;
             }
             double hn = sqrt(w2_after);
             if (!(hn == hn)) PLB_FAIL(ctx, "FGMRES: NaN in Arnoldi step %d", total + 1);
@@ -151,6 +167,7 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
         if (k > 0 && plb_multi_axpy2(ctx, n, k, S, Zp.data(), x, nullptr, nullptr)) return 2;
         PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // h_coef is reused by the next read
         (void)inner_conv;    // the loop head re-evaluates the TRUE residual and decides
+        est_prev = k > 0 ? fabs(g[k]) : beta;
     }
     if (!res->converged) {
         // final true residual for the report

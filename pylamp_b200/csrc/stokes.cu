@@ -65,9 +65,11 @@ struct plb_stokes {
     plb_fgmres_ws kry;
     double *xs = nullptr, *r3 = nullptr, *b3 = nullptr, *t3 = nullptr, *gz_d = nullptr, *gx_d = nullptr;
     // parameters
-    int hydrostatic = 1;
+    int hydrostatic = 1, warm_start = 0;
+    bool have_prev = false;
+    double floor_est = 0;         // attainable scaled residual learnt from a stalled solve
     int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
-    double cheb_ratio = 8.0;
+    double cheb_ratio = 8.0, kry_reorth = 1e-4;
     double rtol_accept = 1e-8;    // a solve stalled at its fp64 floor is accepted below this true residual
     // statistics of the last solve
     int last_iters = 0, last_vcycles = 0;
@@ -969,6 +971,8 @@ int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     else if (!strcmp(name, "reorth")) op->reorth = (int)value;
     else if (!strcmp(name, "rtol_accept")) op->rtol_accept = value;
     else if (!strcmp(name, "hydrostatic")) op->hydrostatic = (int)value;
+    else if (!strcmp(name, "warm_start")) op->warm_start = (int)value;
+    else if (!strcmp(name, "reorth_thresh")) op->kry_reorth = value;
     else PLB_FAIL(ctx, "plb_stokes_set_param: unknown parameter '%s'", name);
     return 0;
 }
@@ -1055,7 +1059,7 @@ int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2) {
 
 int plb_stokes_last_stats(plb_stokes* op, double* h_out) {
     if (!op) return 1;
-    h_out[0] = op->last_iters, h_out[1] = op->last_vcycles, h_out[2] = op->last_relres;
+    h_out[0] = op->last_iters, h_out[1] = op->last_vcycles, h_out[2] = op->last_relres, h_out[3] = op->floor_est;
     return 0;
 }
 
@@ -1093,7 +1097,6 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         k_sub_row_mean<<<g, blk, 0, ctx->stream>>>(D, m, b);
         PLB_LAUNCHED(ctx);
     }
-    PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
     auto residual = [&](double* out) -> int {
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 88.0 * (double)P);
         k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, x, x + P, x + 2 * P, b, b + P, b + 2 * P, out, out + P,
@@ -1101,11 +1104,23 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         PLB_LAUNCHED(ctx);
         return 0;
     };
-    if (residual(r)) return 2;
+    // || W b ||: the scaled norm of the right-hand side (W b is the residual of x = 0 and the
+    // operator is linear, so evaluate it with a zero iterate in the scratch vector)
+    PLB_CUDA(ctx, cudaMemsetAsync(op->t3, 0, sizeof(double) * 3 * P, ctx->stream));
+    {
+        double* z0 = op->t3;
+        k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, z0, z0 + P, z0 + 2 * P, b, b + P, b + 2 * P, r, r + P,
+                                                      r + 2 * P);
+        PLB_LAUNCHED(ctx);
+    }
     double bn2;
     if (plb_dot(ctx, &op->rws, 3 * P, r, r, op->d_scal + 910)) return 2;
     if (plb_read_scalars(ctx, op->d_scal + 910, 1, &bn2)) return 2;
     const double bnorm = sqrt(bn2);
+    // initial guess: the previous solve's iterate (deviation from its hydrostatic pressure) when
+    // warm starts are enabled, otherwise zero
+    if (!(op->warm_start && op->have_prev))
+        PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
     int vcycles = 0;
     auto apply = [&](const double* z, double* c) -> int {
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 64.0 * (double)P);
@@ -1125,13 +1140,18 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         return vcycle(op, 0, L.b, z);
     };
     plb_fgmres_result res;
+    op->kry.reorth_thresh = op->kry_reorth;
+    // the residual floor met by an earlier solve on this grid bounds what any later one can reach
+    const double rtol_eff = std::max(rtol, 2 * op->floor_est);
     if (bnorm > 0) {
-        if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol, maxit, &res)) return 2;
+        if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol_eff, maxit, &res)) return 2;
+        if (res.floor > 0 && res.floor <= op->rtol_accept) op->floor_est = res.floor;
     } else {
         res.converged = true;
     }
     const int total = res.iters;
     op->last_iters = total, op->last_vcycles = vcycles, op->last_relres = res.relres;
+    op->have_prev = res.converged || res.relres <= op->rtol_accept;
     if (h_iters) *h_iters = total;
     if (h_relres) *h_relres = res.relres;
     k_solution_out<<<g, blk, 0, ctx->stream>>>(D, x, x + P, x + 2 * P, ph, d_x);

@@ -46,7 +46,7 @@ class Options:
         # solver controls (not in the reference: it calls a direct solver)
         self.stokes_rtol = 1e-12
         self.stokes_maxit = 600
-        self.stokes_params = {}
+        self.stokes_params = {"warm_start": 1}     # start each solve from the previous step's iterate
         self.heat_rtol = 1e-13
         for k, v in kw.items():
             if not hasattr(self, k):

@@ -130,9 +130,9 @@ class StokesOperator:
 
     @property
     def stats(self):
-        out = (C.c_double * 3)()
+        out = (C.c_double * 4)()
         self.ctx.check(self.ctx.lib.plb_stokes_last_stats(self.h, out))
-        return {"iterations": int(out[0]), "vcycles": int(out[1]), "relres": out[2]}
+        return {"iterations": int(out[0]), "vcycles": int(out[1]), "relres": out[2], "floor": out[3]}
 
     def close(self):
         if getattr(self, "h", None):
