@@ -130,3 +130,61 @@ __device__ __forceinline__ void store_vx(const LevelDev& L, double* __restrict__
         if (i == L.vx_i1) vx[o + L.ld] = L.sl_z1 * v;   // :202-214
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Interior fast path.  For 1 <= i <= nz-2 and 1 <= j <= nxx-2 every neighbour index is in range, so
+// all loads of both momentum rows are issued unconditionally and up front (one round of memory
+// latency per thread instead of one per sub-expression; shared values are loaded once), and only
+// the final stores are predicated on the row ranges.  Same arithmetic as vz_coef/kvz_apply and
+// vx_coef/kvx_apply.
+// ---------------------------------------------------------------------------------------------
+struct Rows2 {
+    double kz, dz;    // (K v)_vz and the vz diagonal
+    double kx, dx;    // (K v)_vx and the vx diagonal
+};
+
+__device__ __forceinline__ bool is_interior(const LevelDev& L, int i, int j) {
+    return i >= 1 && i <= L.nz - 2 && j >= 1 && j <= L.nxx - 2;
+}
+
+template <bool APPLY>
+__device__ __forceinline__ Rows2 rows_interior(const LevelDev& L, const double* __restrict__ vz,
+                                               const double* __restrict__ vx, int i, int j) {
+    const int ld = L.ld;
+    const long long o = (long long)i * ld + j;
+    // coefficients
+    const double enC = L.etan[o], enM0 = L.etan[o - ld], en0M = L.etan[o - 1];
+    const double esC = L.etas[o], es0P = L.etas[o + 1], esP0 = L.etas[o + ld];
+    const double idz_i = L.idz[i], idz_m = L.idz[i - 1], idzc_i = L.idzc[i], idzc_p = L.idzc[i + 1];
+    const double idx_j = L.idx[j], idx_m = L.idx[j - 1], idxc_j = L.idxc[j], idxc_p = L.idxc[j + 1];
+    double z00 = 0, zP0 = 0, zM0 = 0, z0P = 0, z0M = 0, zPM = 0, x00 = 0, x0P = 0, x0M = 0, xP0 = 0, xM0 = 0,
+           xMP = 0;
+    if (APPLY) {
+        z00 = vz[o], zP0 = vz[o + ld], zM0 = vz[o - ld], z0P = vz[o + 1], z0M = vz[o - 1], zPM = vz[o + ld - 1];
+        x00 = vx[o], x0P = vx[o + 1], x0M = vx[o - 1], xP0 = vx[o + ld], xM0 = vx[o - ld], xMP = vx[o - ld + 1];
+    }
+    Rows2 r;
+    {   // z-momentum row
+        double cN = 4 * enC * idz_i * idzc_i, cS = 4 * enM0 * idz_m * idzc_i;
+        double cE = 2 * es0P * idxc_p * idx_j, cW = 2 * esC * idxc_j * idx_j;
+        double xE = 2 * es0P * idzc_i * idx_j, xW = 2 * esC * idzc_i * idx_j;
+        if (L.proper && j + 1 == L.nxx - 1) cE = 0, xE = 0;
+        r.dz = -(cN + cS + cE + cW);
+        r.kz = APPLY ? cN * zP0 + cS * zM0 + cE * z0P + cW * z0M + r.dz * z00 + xE * (x0P - xMP) - xW * (x00 - xM0)
+                     : 0.0;
+    }
+    {   // x-momentum row
+        double cE = 4 * enC * idx_j * idxc_j, cW = 4 * en0M * idx_m * idxc_j;
+        double cS = 2 * esP0 * idzc_p * idz_i, cN = 2 * esC * idzc_i * idz_i;
+        double xS = 2 * esP0 * idxc_j * idz_i, xN = 2 * esC * idxc_j * idz_i;
+        double wall = 0;
+        if (L.proper && i + 1 == L.nz - 1) {
+            if (L.ns_z1) wall = 2 * esP0 * idz_i * idz_i;
+            cS = 0, xS = 0;
+        }
+        r.dx = -(cE + cW + cS + cN + wall);
+        r.kx = APPLY ? cE * x0P + cW * x0M + cS * xP0 + cN * xM0 + r.dx * x00 + xS * (zP0 - zPM) - xN * (z00 - z0M)
+                     : 0.0;
+    }
+    return r;
+}

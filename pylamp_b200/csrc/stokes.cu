@@ -209,6 +209,22 @@ k_stokes_op(LevelDev L, double Kc, const double* __restrict__ vz, const double* 
     if (i >= L.nz || j >= L.nxx) return;
     const int ld = L.ld;
     const long long o = (long long)i * ld + j;
+    if (is_interior(L, i, j)) {
+        // interior fast path: all loads up front (see rows_interior), stores predicated
+        const double p00 = p[o], pM0 = p[o - ld], p0M = p[o - 1];
+        const double en = L.etan[o];
+        double bzv = 0, bxv = 0, bpv = 0;
+        if (RESID) bzv = bz[o], bxv = bx[o], bpv = bp[o];
+        const double vz00 = vz[o], vzP0 = vz[o + ld], vx00 = vx[o], vx0P = vx[o + 1];
+        const Rows2 q = rows_interior<true>(L, vz, vx, i, j);
+        double a = q.kz - 2 * Kc * L.idzc[i] * (p00 - pM0);
+        oz[o] = is_vz_row(L, i, j) ? (RESID ? bzv - a : a) * rsqrt(-q.dz) : 0.0;
+        a = q.kx - 2 * Kc * L.idxc[j] * (p00 - p0M);
+        ox[o] = is_vx_row(L, i, j) ? (RESID ? bxv - a : a) * rsqrt(-q.dx) : 0.0;
+        a = Kc * (L.idx[j] * (vx0P - vx00) + L.idz[i] * (vzP0 - vz00));
+        op[o] = is_p_row(L, i, j) ? (RESID ? bpv - a : a) * (sqrt(en) / Kc) : 0.0;
+        return;
+    }
     double r = 0;
     if (is_vz_row(L, i, j)) {
         VzCoef c = vz_coef(L, i, j);
@@ -279,7 +295,26 @@ k_cheb(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     if (i >= L.nz || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j;
-    if (is_vz_row(L, i, j)) {
+    const bool rz = is_vz_row(L, i, j), rx = is_vx_row(L, i, j);
+    if (is_interior(L, i, j)) {
+        // all loads up front, stores predicated
+        const double bzv = bz[o], bxv = bx[o];
+        double dzv = 0, dxv = 0, xzv = 0, xxv = 0;
+        if (!FIRST) dzv = dz[o], dxv = dx[o], xzv = xz[o], xxv = xx[o];
+        const Rows2 r = rows_interior<!FIRST>(L, xz, xx, i, j);
+        if (rz) {
+            double d = FIRST ? cr * bzv / r.dz : cd * dzv + cr * ((bzv - r.kz) / r.dz);
+            dz[o] = d;
+            store_vz(L, oz, i, j, FIRST ? d : xzv + d);
+        }
+        if (rx) {
+            double d = FIRST ? cr * bxv / r.dx : cd * dxv + cr * ((bxv - r.kx) / r.dx);
+            dx[o] = d;
+            store_vx(L, ox, i, j, FIRST ? d : xxv + d);
+        }
+        return;
+    }
+    if (rz) {
         VzCoef c = vz_coef(L, i, j);
         double d;
         if (FIRST) {
@@ -293,7 +328,7 @@ k_cheb(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
             store_vz(L, oz, i, j, xz[o] + d);
         }
     }
-    if (is_vx_row(L, i, j)) {
+    if (rx) {
         VxCoef c = vx_coef(L, i, j);
         double d;
         if (FIRST) {
@@ -318,6 +353,13 @@ k_vel_op(LevelDev L, const double* __restrict__ xz, const double* __restrict__ x
     const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
     if (i >= L.nz || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j;
+    if (MODE == 0 && is_interior(L, i, j)) {
+        const double bzv = bz[o], bxv = bx[o];
+        const Rows2 q = rows_interior<true>(L, xz, xx, i, j);
+        rz[o] = is_vz_row(L, i, j) ? bzv - q.kz : 0.0;
+        rx[o] = is_vx_row(L, i, j) ? bxv - q.kx : 0.0;
+        return;
+    }
     double r = 0;
     if (is_vz_row(L, i, j)) {
         VzCoef c = vz_coef(L, i, j);
