@@ -70,7 +70,7 @@ struct VecList2 {
 template <int J, bool TWO>
 __global__ void __launch_bounds__(TB)
 k_multi_axpy2(long long n, const double* __restrict__ h, VecList2 L, double* __restrict__ w,
-              double* __restrict__ u) {
+              double* __restrict__ u, double post_scale) {
     double c[J];
 #pragma unroll
     for (int j = 0; j < J; j++) c[j] = h[j];
@@ -78,12 +78,12 @@ k_multi_axpy2(long long n, const double* __restrict__ h, VecList2 L, double* __r
         double a = w[i];
 #pragma unroll
         for (int j = 0; j < J; j++) a -= c[j] * L.v[j][i];
-        w[i] = a;
+        w[i] = a * post_scale;
         if (TWO) {
             double b = u[i];
 #pragma unroll
             for (int j = 0; j < J; j++) b -= c[j] * L.u[j][i];
-            u[i] = b;
+            u[i] = b * post_scale;
         }
     }
 }
@@ -158,21 +158,22 @@ int plb_dot(plb_ctx* ctx, plb_reduce_ws* ws, long long n, const double* a, const
 }
 
 int plb_multi_axpy2(plb_ctx* ctx, long long n, int k, const double* d_h, const double* const* h_V,
-                    double* w, const double* const* h_U, double* u) {
+                    double* w, const double* const* h_U, double* u, double post_scale) {
     int grid = vec_grid(ctx, n);
     // k (2k) vectors read once, w (and u) read+written once per chunk of 8
     plb_prof_scope prof_(ctx, PLB_K_MAXPY, 8.0 * (double)n * (h_U ? 2 : 1) * (k + 2 * ((k + PLB_DOT_CHUNK - 1) / PLB_DOT_CHUNK)));
     for (int j0 = 0; j0 < k; j0 += PLB_DOT_CHUNK) {
         int J = k - j0 < PLB_DOT_CHUNK ? k - j0 : PLB_DOT_CHUNK;
         VecList2 L;
+        const double ps = (j0 + J >= k) ? post_scale : 1.0;      // scale once, in the last chunk
         for (int j = 0; j < PLB_DOT_CHUNK; j++) {
             L.v[j] = h_V[j0 + (j < J ? j : 0)];
             L.u[j] = h_U ? h_U[j0 + (j < J ? j : 0)] : nullptr;
         }
 #define MA(JJ)                                                                                   \
     case JJ:                                                                                     \
-        if (h_U) k_multi_axpy2<JJ, true><<<grid, TB, 0, ctx->stream>>>(n, d_h + j0, L, w, u);     \
-        else k_multi_axpy2<JJ, false><<<grid, TB, 0, ctx->stream>>>(n, d_h + j0, L, w, u);        \
+        if (h_U) k_multi_axpy2<JJ, true><<<grid, TB, 0, ctx->stream>>>(n, d_h + j0, L, w, u, ps);     \
+        else k_multi_axpy2<JJ, false><<<grid, TB, 0, ctx->stream>>>(n, d_h + j0, L, w, u, ps);        \
         break;
         switch (J) { MA(1) MA(2) MA(3) MA(4) MA(5) MA(6) MA(7) MA(8) }
 #undef MA

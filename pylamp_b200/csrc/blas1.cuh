@@ -24,9 +24,9 @@ int plb_dot(plb_ctx* ctx, plb_reduce_ws* ws, long long n, const double* a, const
 // d_out[j] = sum V[j][i]*w[i], j < k (any k; processed in chunks of PLB_DOT_CHUNK)
 int plb_multi_dot(plb_ctx* ctx, plb_reduce_ws* ws, long long n, int k, const double* const* h_V,
                   const double* w, double* d_out);
-// w -= sum_j h[j] V[j]   and (if U) u -= sum_j h[j] U[j]     (h on the device)
+// w = post_scale * (w - sum_j h[j] V[j])   and (if U) the same for u with U     (h on the device)
 int plb_multi_axpy2(plb_ctx* ctx, long long n, int k, const double* d_h, const double* const* h_V,
-                    double* w, const double* const* h_U, double* u);
+                    double* w, const double* const* h_U, double* u, double post_scale = 1.0);
 // y += sign * (*d_a) * x
 int plb_axpy_dev(plb_ctx* ctx, long long n, const double* d_a, double sign, const double* x, double* y);
 // a *= 1/sqrt(*d_n2), b *= 1/sqrt(*d_n2) (b may be NULL)

@@ -116,23 +116,37 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
             for (int j = 0; j <= k; j++) Vp.push_back(ws->V[j]);
             Vp.push_back(w);                                   // last entry: w.w
             for (int j = 0; j <= k + 1; j++) hcol[j] = 0;
-            double w2_before = 0, w2_after = 0;
-            for (int pass = 0; pass < 2; pass++) {
-                if (plb_multi_dot(ctx, rws, n, k + 2, Vp.data(), w, S)) return 2;
+            // Pass 1: h = V^T w and w.w in one fused multi-dot.  By Pythagoras the norm after the
+            // projection is w.w - sum h^2; when that keeps at least two digits (the normal case) it is
+            // used directly and the normalisation is folded into the projection kernel (no separate
+            // dot and scale passes).  After heavy cancellation: explicit norm and a second pass.
+            if (plb_multi_dot(ctx, rws, n, k + 2, Vp.data(), w, S)) return 2;
+            if (plb_fgmres_read(ctx, ws, S, k + 2)) return 2;
+            double w2_before = ws->h_coef[k + 1], sumh2 = 0;
+            for (int j = 0; j <= k; j++) hcol[j] = ws->h_coef[j], sumh2 += hcol[j] * hcol[j];
+            double w2_after = w2_before - sumh2;
+            double hn;
+            if (w2_after > 1e-2 * w2_before) {
+                hn = sqrt(w2_after);
+                if (plb_multi_axpy2(ctx, n, k + 1, S, Vp.data(), w, nullptr, nullptr, 1.0 / hn)) return 2;
+            } else {
                 if (plb_multi_axpy2(ctx, n, k + 1, S, Vp.data(), w, nullptr, nullptr)) return 2;
                 if (plb_dot(ctx, rws, n, w, w, S + k + 2)) return 2;
-                if (plb_fgmres_read(ctx, ws, S, k + 3)) return 2;
-                for (int j = 0; j <= k; j++) hcol[j] += ws->h_coef[j];
-                w2_before = ws->h_coef[k + 1], w2_after = ws->h_coef[k + 2];
-                // Re-orthogonalise only after severe cancellation (more than reorth_digits lost).  With a
-                // good preconditioner A^ M is close to the identity, so w always has an O(1) component
-                // along V_k and a "lost half of the norm" test would fire on every step for nothing.
-                if (w2_after > ws->reorth_thresh * w2_before) break;
+                if (plb_fgmres_read(ctx, ws, S + k + 2, 1)) return 2;
+                w2_after = ws->h_coef[0];
+                if (w2_after < ws->reorth_thresh * w2_before) {       // second Gram-Schmidt pass
+                    if (plb_multi_dot(ctx, rws, n, k + 1, Vp.data(), w, S)) return 2;
+                    if (plb_multi_axpy2(ctx, n, k + 1, S, Vp.data(), w, nullptr, nullptr)) return 2;
+                    if (plb_dot(ctx, rws, n, w, w, S + k + 2)) return 2;
+                    if (plb_fgmres_read(ctx, ws, S, k + 3)) return 2;
+                    for (int j = 0; j <= k; j++) hcol[j] += ws->h_coef[j];
+                    w2_after = ws->h_coef[k + 2];
+                }
+                hn = sqrt(w2_after);
+                if (hn > 0 && plb_scale_rsqrt2(ctx, n, S + k + 2, w, nullptr)) return 2;
             }
-            double hn = sqrt(w2_after);
             if (!(hn == hn)) PLB_FAIL(ctx, "FGMRES: NaN in Arnoldi step %d", total + 1);
             hcol[k + 1] = hn;
-            if (hn > 0 && plb_scale_rsqrt2(ctx, n, S + k + 2, w, nullptr)) return 2;
             // Givens update of column k
             for (int j = 0; j < k; j++) {
                 double t = cs[j] * hcol[j] + sn[j] * hcol[j + 1];

@@ -261,6 +261,18 @@ k_precond_rhs(LevelDev L, double Kc, const double* __restrict__ rz, const double
     if (i >= L.nz || j >= L.nxx) return;
     const int ld = L.ld, nz = L.nz, nxx = L.nxx;
     const long long o = (long long)i * ld + j;
+    if (is_interior(L, i, j) && i <= nz - 3 && j <= nxx - 3) {
+        // interior fast path (no corner cell here): all loads up front
+        const double r0 = rp[o], rM = rp[o - ld], rW = rp[o - 1];
+        const double e0 = L.etan[o], eM = L.etan[o - ld], eW = L.etan[o - 1];
+        const double rzv = rz[o], rxv = rx[o];
+        const Rows2 q = rows_interior<false>(L, nullptr, nullptr, i, j);
+        const double d0 = r0 * sqrt(e0) / Kc, dM = rM * sqrt(eM) / Kc, dW = rW * sqrt(eW) / Kc;
+        zp[o] = d0;
+        bvz[o] = is_vz_row(L, i, j) ? rzv * sqrt(-q.dz) + 2 * Kc * L.idzc[i] * (d0 - dM) : 0.0;
+        bvx[o] = is_vx_row(L, i, j) ? rxv * sqrt(-q.dx) + 2 * Kc * L.idxc[j] * (d0 - dW) : 0.0;
+        return;
+    }
     double dp = 0;
     if (i <= nz - 2 && j <= nxx - 2) {
         bool corner = (i == 0 || i == nz - 2) && (j == 0 || j == nxx - 2);

@@ -100,3 +100,12 @@ def test_convection_small():
     sg, so, errs = _run_both(setups.convection(ncell=64), 3, tol_fields=1e-8)
     for e in errs:
         assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
+
+
+def test_convection_257_warm_started_steps():
+    """Larger grid (256^2 cells, 1.0e6 markers), the bench's solver settings (FGMRES(30), warm start):
+    every step within 1e-8 of the oracle's direct solve."""
+    sg, so, errs = _run_both(setups.convection(ncell=256), 2, tol_fields=1e-8,
+                             stokes_params={"warm_start": 1, "gcr_m": 30})
+    for e in errs:
+        assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
