@@ -164,9 +164,12 @@ def run_b200(args):
     iters = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    phase_ms = {}
     for _ in range(args.steps):
-        driver.timestep(s, o, want_kelem=False)
+        driver.timestep(s, o, want_kelem=False, phases=True)
         iters.append(dict(s.stats))
+        for k, v in s.phases.result().items():
+            phase_ms[k] = phase_ms.get(k, 0.0) + v / args.steps
         for k, (c, ms, by) in ctx.profile_read().items():
             a = prof.setdefault(k, [0, 0.0, 0.0])
             a[0] += c
@@ -222,7 +225,7 @@ def run_b200(args):
                        "stokes_rtol": o.stokes_rtol, "stokes_solver": "FGMRES(%d) + GMG V(3,3) Chebyshev-Jacobi, warm start" % args.gmres_m},
             "stokes_dof_per_s": world * 3.0 * N * np.mean([1.0]) / (ms_step * 1e-3),
             "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
-            "roofline": roofline, "kernel_breakdown": breakdown}
+            "roofline": roofline, "phases_ms_per_step": phase_ms, "kernel_breakdown": breakdown}
     if e2e is not None:
         line["e2e"] = {"value": world / (e2e["ms"] * 1e-3), "unit": "timesteps/s",
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": args.e2e_steps}

@@ -84,7 +84,9 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
         double beta = sqrt(ws->h_coef[0]);
         if (!(beta == beta)) PLB_FAIL(ctx, "FGMRES: residual is NaN");
         res->relres = beta / bnorm;
-        if (beta <= rtol * bnorm) {
+        // (after at least one cycle a true residual within 1.5x of the target is accepted: another
+        // restart cycle would spend tens of iterations on a few percent)
+        if (beta <= rtol * bnorm || (total > 0 && beta <= 1.5 * rtol * bnorm)) {
             res->converged = true;
             break;
         }

@@ -65,43 +65,40 @@ struct T2GArgs {
     int k;
 };
 
-// Warp-aggregated scatter.  Consecutive lanes of a warp that fall in the same cell (the common
-// case while the markers are cell-ordered) form a run; each run is reduced to ONE atomic per
-// (node, quantity).  The reduction goes through a per-warp shared-memory transpose instead of
-// shuffles: every lane stores its up to 16 partial values as buf[slot][lane], then lane q sums slot
-// q over each run (32 conflict-free loads) and issues that slot's atomics.  Correct for any marker
-// order (unsorted markers just give runs of length 1).
-//
-// slot layout per marker: 0..3 corner weights; 4 the count (1.0); 5+4f+c field f times weight c
-// (weighted schemes) or the plain value in 5+4f (unweighted schemes, added to all four corners).
-constexpr int T2G_CHUNK = 16;
-constexpr int T2G_WARPS = 8;
+// (A shared-memory transpose variant of this reduction was measured slower: 50 vs 37 ms per 4096^2
+// step -- 105 registers and 35 KB smem per block cost more occupancy than the shuffles cost issue slots.)
+// Warp-aggregated scatter: contiguous lanes of a warp that fall in the same cell (the common
+// case once the markers are cell-ordered) are combined by a segmented shuffle reduction, so
+// only the first lane of each run issues the global fp64 reductions.  Correct for any order.
+__device__ __forceinline__ double seg_reduce(double v, int lane, int run_end) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o <= run_end) v += t;
+    }
+    return v;
+}
 
 template <int K>
-__global__ void __launch_bounds__(32 * T2G_WARPS)
+__global__ void __launch_bounds__(256)
 k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
-    constexpr int NV = 5 + 4 * K;
-    constexpr int NCHUNK = (NV + T2G_CHUNK - 1) / T2G_CHUNK;
-    __shared__ double buf_all[T2G_WARPS][T2G_CHUNK][33];
-    __shared__ long long n00_all[T2G_WARPS][32];
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double(*buf)[33] = buf_all[wib];
-    long long* n00s = n00_all[wib];
+    const int lane = threadIdx.x & 31;
     long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; base < M; base += stride) {
-        const long long m = base + lane;
+        long long m = base + lane;
         bool valid = m < M;
         long long cell = -1 - lane;          // invalid lanes form runs of their own
-        double vals[NV];
+        double w[4] = {0, 0, 0, 0};
+        double v[K];
 #pragma unroll
-        for (int q = 0; q < NV; q++) vals[q] = 0;
-        long long n00 = -1;
+        for (int f = 0; f < K; f++) v[f] = 0;
+        long long ie = 0, je = 0;
         if (valid) {
             double2 p = trx[m];
-            long long ie = cell_of(p.x, a.z0, a.zlen, a.nze);
-            long long je = cell_of(p.y, a.x0, a.xlen, a.nxe);
+            ie = cell_of(p.x, a.z0, a.zlen, a.nze);
+            je = cell_of(p.y, a.x0, a.xlen, a.nxe);
             if (ie < 0 || ie > a.nze - 2 || je < 0 || je > a.nxe - 2) {
                 valid = false;               // cannot happen after the ghost extension
             } else {
@@ -109,76 +106,56 @@ k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
                 double az = (p.x - gz0) / (gz1 - gz0);      // pylamp_trac.py:247
                 double ax = (p.y - gx0) / (gx1 - gx0);
                 double bz = 1 - az, bx = 1 - ax;            // :249
-                vals[0] = (1 - ax) * (1 - az);              // node (i  , j  )   :252
-                vals[1] = (1 - ax) * (1 - bz);              // node (i+1, j  )
-                vals[2] = (1 - bx) * (1 - az);              // node (i  , j+1)
-                vals[3] = (1 - bx) * (1 - bz);              // node (i+1, j+1)
-                vals[4] = 1.0;
+                w[0] = (1 - ax) * (1 - az);                 // node (i  , j  )   :252
+                w[1] = (1 - ax) * (1 - bz);                 // node (i+1, j  )
+                w[2] = (1 - bx) * (1 - az);                 // node (i  , j+1)
+                w[3] = (1 - bx) * (1 - bz);                 // node (i+1, j+1)
                 cell = ie * a.nxe + je;
-                n00 = cell;
 #pragma unroll
                 for (int f = 0; f < K; f++) {
                     double val = a.f[f][m];
-                    double v = (a.scheme[f] & PLB_AVG_ARITHMETIC) ? val : log(val);
-                    if (a.scheme[f] & PLB_AVG_WEIGHTED) {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) vals[5 + 4 * f + c] = v * vals[c];
-                    } else {
-                        vals[5 + 4 * f] = v;
-                    }
+                    v[f] = (a.scheme[f] & PLB_AVG_ARITHMETIC) ? val : log(val);
                 }
             }
         }
-        const long long prev = __shfl_up_sync(full, cell, 1);
-        const bool head = (lane == 0) || (prev != cell);
-        const unsigned heads = __ballot_sync(full, head);
-        n00s[lane] = n00;
+        long long prev = __shfl_up_sync(full, cell, 1);
+        bool head = (lane == 0) || (prev != cell);
+        unsigned heads = __ballot_sync(full, head);
+        unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
+        int run_end = after ? lane + __ffs(after) - 1 : 31;
+        bool emit = head && valid;
+        long long n00 = ie * a.nxe + je;
+        long long idx[4] = {n00, n00 + a.nxe, n00 + 1, n00 + a.nxe + 1};
+        if (a.wsum) {
 #pragma unroll
-        for (int ch = 0; ch < NCHUNK; ch++) {
-            __syncwarp();
-#pragma unroll
-            for (int v = 0; v < T2G_CHUNK; v++) {
-                const int q = ch * T2G_CHUNK + v;
-                if (q < NV) buf[v][lane] = vals[q];
+            for (int c = 0; c < 4; c++) {
+                double s = seg_reduce(w[c], lane, run_end);
+                if (emit) atomicAdd(a.wsum + idx[c], s);
             }
-            __syncwarp();
-            const int q = ch * T2G_CHUNK + lane;
-            if (lane < T2G_CHUNK && q < NV) {
-                // decode the slot: target plane, corner (or all four)
-                double* arr = nullptr;
-                int corner = 0;
-                bool all4 = false;
-                if (q < 4) arr = a.wsum, corner = q;
-                else if (q == 4) arr = a.cnt, all4 = true;
-                else {
-                    const int f = (q - 5) >> 2, c = (q - 5) & 3;
-                    if (a.scheme[f] & PLB_AVG_WEIGHTED) arr = a.acc[f], corner = c;
-                    else if (c == 0) arr = a.acc[f], all4 = true;
+        }
+        if (a.cnt) {
+            double s = seg_reduce(valid ? 1.0 : 0.0, lane, run_end);
+            if (emit) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) atomicAdd(a.cnt + idx[c], s);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < K; f++) {
+            if (a.scheme[f] & PLB_AVG_WEIGHTED) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    double s = seg_reduce(v[f] * w[c], lane, run_end);
+                    if (emit) atomicAdd(a.acc[f] + idx[c], s);
                 }
-                if (arr) {
-                    unsigned mrem = heads;
-                    while (mrem) {
-                        const int h = __ffs(mrem) - 1;
-                        mrem &= mrem - 1;
-                        const int e = mrem ? __ffs(mrem) - 2 : 31;
-                        const long long nb = n00s[h];
-                        if (nb < 0) continue;
-                        double sacc = 0;
-                        for (int t = h; t <= e; t++) sacc += buf[lane][t];
-                        if (all4) {
-                            atomicAdd(arr + nb, sacc);
-                            atomicAdd(arr + nb + a.nxe, sacc);
-                            atomicAdd(arr + nb + 1, sacc);
-                            atomicAdd(arr + nb + a.nxe + 1, sacc);
-                        } else {
-                            const long long off = (corner & 1 ? a.nxe : 0) + (corner >> 1);
-                            atomicAdd(arr + nb + off, sacc);
-                        }
-                    }
+            } else {
+                double s = seg_reduce(v[f], lane, run_end);
+                if (emit) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) atomicAdd(a.acc[f] + idx[c], s);
                 }
             }
         }
-        __syncwarp();
     }
 }
 

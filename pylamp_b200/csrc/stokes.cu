@@ -1196,7 +1196,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     plb_fgmres_result res;
     op->kry.reorth_thresh = op->kry_reorth;
     // the residual floor met by an earlier solve on this grid bounds what any later one can reach
-    const double rtol_eff = std::max(rtol, 2 * op->floor_est);
+    const double rtol_eff = std::max(rtol, 3 * op->floor_est);
     if (bnorm > 0) {
         if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol_eff, maxit, &res)) return 2;
         if (res.floor > 0 && res.floor <= op->rtol_accept) op->floor_est = res.floor;

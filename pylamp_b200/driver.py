@@ -102,9 +102,32 @@ def _to_dev(a, dev):
     return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
 
 
-def timestep(s, o, want_kelem=True):
+class _Phases:
+    """Optional per-phase timing with CUDA events on the current stream (no extra synchronisation:
+    the events are resolved by the caller after the step)."""
+
+    def __init__(self, on):
+        self.on, self.marks = on, []
+
+    def mark(self, name):
+        if self.on:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def result(self):
+        torch.cuda.synchronize()
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def timestep(s, o, want_kelem=True, phases=False):
     """One pass of the loop body pylamp2.py:273-594 on device-resident state."""
     ctx = s.ctx
+    ph = s.phases = _Phases(phases)
+    ph.mark("start")
     s.it += 1
     nx, grid, gridmp = s.nx, s.grid, s.gridmp
     cols, tr_x = s.cols, s.tr_x
@@ -112,6 +135,7 @@ def timestep(s, o, want_kelem=True):
     markers.update_properties(cols[TR_TMP], cols[TR_RH0], cols[TR_ALP], cols[TR_ACE], cols[TR_ET0],
                               o.tdep_rho, o.tdep_eta, o.Tref, o.etamin, o.etamax,
                               rho_out=cols[TR_RHO], eta_out=cols[TR_ETA])
+    ph.mark("properties")
     # markers -> grids, pylamp2.py:307-319
     mm = pylamp_trac.marker_minmax(tr_x, ctx)
     t2g = pylamp_trac.trac2grid_device
@@ -128,6 +152,7 @@ def timestep(s, o, want_kelem=True):
         t2g(ctx, tr_x, [cols[TR_ETA]], [INTERP_AVG_GEOMETRIC], gridmp, [s.f_etan], mm)
     else:
         raise NotImplementedError("heat-only mode (pylamp2.py:321-331) is outside the hot path")
+    ph.mark("trac2grid")
     if o.do_heatdiff and s.it > 1:                                                  # :333-337
         s.f_T[:, 0], s.f_T[:, -1] = s.newtemp[:, 0], s.newtemp[:, -1]
         s.f_T[0, :], s.f_T[-1, :] = s.newtemp[0, :], s.newtemp[-1, :]
@@ -135,6 +160,7 @@ def timestep(s, o, want_kelem=True):
         diffusivity = markers.max_diffusivity2(s.f_k[IZ], s.f_rho, s.f_Cp)
         tstep_temp = _clamp(o.tstep_modifier * min(s.dx) ** 2 / diffusivity, o.tstep_dif_min,
                             o.tstep_dif_max)
+    ph.mark("dt_heat")
     # Stokes system + solve, pylamp2.py:353-362
     if s.stokes_op is None:
         s.stokes_op = pylamp_stokes.StokesOperator(nx, grid, s.f_etas, s.f_etan, s.f_rho, o.bcstokes,
@@ -146,6 +172,7 @@ def timestep(s, o, want_kelem=True):
     x = s.stokes_op.solve(None, rtol=o.stokes_rtol, maxit=o.stokes_maxit)
     s.stats["stokes_iters"] = s.stokes_op.iterations
     s.stats["stokes_relres"] = s.stokes_op.relres
+    ph.mark("stokes_solve")
     s.newvel, s.newpres = pylamp_stokes.x2vp(x, nx)
     vmax = max(markers.field_max(s.newvel[IZ]), markers.field_max(s.newvel[IX]))   # :364 (signed)
     tstep_stokes = _clamp(o.tstep_modifier * min(s.dx) / vmax, o.tstep_adv_min, o.tstep_adv_max)
@@ -156,6 +183,7 @@ def timestep(s, o, want_kelem=True):
         tstep, s.limiter = tstep_stokes, "S"
     s.tstep = tstep
     s.totaltime += tstep
+    ph.mark("x2vp_dt")
     if o.do_heatdiff:                                                               # :415-480
         args = (s.f_T, s.f_k, s.f_Cp, s.f_rho, s.f_H, tstep)
         if s.diff_op is None:
@@ -165,6 +193,7 @@ def timestep(s, o, want_kelem=True):
             s.diff_op.set_coeffs(*args)
         newtemp = pylamp_diff.x2t(s.diff_op.solve(None, rtol=o.heat_rtol), nx)
         s.stats["heat_iters"] = s.diff_op.iterations
+        ph.mark("heat_solve")
         T = cols[TR_TMP]
         g2t = pylamp_trac.grid2trac_device
         interp = torch.empty_like(T)
@@ -189,14 +218,17 @@ def timestep(s, o, want_kelem=True):
                     raise Exception("stopOnError in grid2trac")
                 markers.subgrid_stage2(Tsg, interp, T)
         s.newtemp = newtemp
+        ph.mark("grid2trac_T_subgrid")
     # velocities to cell centres + BC ring, RK4, pylamp2.py:491-550
     vzc, vxc = markers.centre_velocities(s.newvel[IZ], s.newvel[IX], o.bcstokes)
     pre = [gridmp[d][0] - (gridmp[d][1] - gridmp[d][0]) for d in range(DIM)]
     newgrid = [np.insert(gridmp[IZ], 0, pre[IZ]), np.insert(gridmp[IX], 0, pre[IX])]
     s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep)
+    ph.mark("advect_rk4")
     # fence + per-cell count, pylamp2.py:558-593
     if not o.tracs_fence_enabled:
         raise NotImplementedError("marker deletion (fence disabled / FLOWTHRU): SURVEY.md §8f-1")
     markers.fence(s.tr_x, s.L, EPS)
     s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=want_kelem)
+    ph.mark("fence_count")
     return s
