@@ -63,6 +63,19 @@ const char* plb_version(void);
 int plb_profile_enable(plb_ctx* ctx, int on);
 int plb_profile_read(plb_ctx* ctx, long long* h_count, double* h_ms, double* h_bytes);
 
+/* ---- multi-GPU: one process per GPU, z-slab decomposition ------------------------
+ * Rank 0 creates a 128-byte NCCL unique id, the host side distributes it (e.g. torch.distributed
+ * broadcast) and every rank calls plb_comm_init.  Afterwards Stokes operators created on the
+ * context are slab-distributed: halo rows travel with grouped ncclSend/ncclRecv, dot products and
+ * other small reductions with ncclAllReduce, all on the context's stream.  The reference's own
+ * scheme (replicated data + MPI Allreduce of marker-sized arrays, pylamp2.py:446-555) is not reused. */
+int plb_comm_unique_id(plb_ctx* ctx, char* h_id128);
+int plb_comm_init(plb_ctx* ctx, int rank, int size, const char* h_id128);
+int plb_comm_info(plb_ctx* ctx, int* h_rank, int* h_size);
+/* in-place all-reduce of a device buffer of doubles; op: 0 sum, 1 max, 2 min */
+int plb_allreduce(plb_ctx* ctx, double* d_buf, long long count, int op);
+void plb_comm_destroy(plb_ctx* ctx);
+
 /* ---- markers -> grid: pylamp_trac.trac2grid, pylamp_trac.py:161-318 -------------------- */
 /* h_out[4] = min z, max z, min x, max x over the markers (the ghost-node extension test of
  * pylamp_trac.py:207-217 is a global min/max).  Synchronises. */

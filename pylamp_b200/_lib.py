@@ -28,6 +28,11 @@ _PROTOS = {
     "plb_launch_count": (LL, [VP]),
     "plb_profile_enable": (I, [VP, I]),
     "plb_profile_read": (I, [VP, C.POINTER(LL), DP, DP]),
+    "plb_comm_unique_id": (I, [VP, C.c_char_p]),
+    "plb_comm_init": (I, [VP, I, I, C.c_char_p]),
+    "plb_comm_info": (I, [VP, IP, IP]),
+    "plb_allreduce": (I, [VP, VP, LL, I]),
+    "plb_comm_destroy": (None, [VP]),
     "plb_marker_minmax": (I, [VP, LL, VP, DP]),
     "plb_trac2grid": (I, [VP, LL, VP, I, PP, IP, VP, I, VP, I, D, D, D, D, I, I, I, I, I, PP]),
     "plb_grid2trac": (I, [VP, LL, VP, I, I, PP, VP, I, VP, I, I, D, D, D, D, D, PP,
@@ -127,6 +132,35 @@ class Context:
 
     def sync(self):
         self.check(self.lib.plb_ctx_sync(self.h))
+
+    def init_comm(self, group=None):
+        """Create this context's NCCL communicator for the z-slab solver: rank 0 makes the unique id,
+        torch.distributed (any backend) broadcasts it, every rank joins.  One process per GPU."""
+        import torch
+        import torch.distributed as dist
+        rank, size = dist.get_rank(group), dist.get_world_size(group)
+        if size == 1:
+            return 0, 1
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            self.call("plb_comm_unique_id", buf)
+        dev = self.torch_device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(dev)
+        dist.broadcast(t, src=0, group=group)
+        ident = bytes(t.cpu().numpy().tobytes())
+        self.call("plb_comm_init", rank, size, C.create_string_buffer(ident, 128))
+        self.rank, self.size = rank, size
+        return rank, size
+
+    def comm_info(self):
+        r, s = C.c_int(0), C.c_int(1)
+        self.call("plb_comm_info", C.byref(r), C.byref(s))
+        return r.value, s.value
+
+    def allreduce(self, tensor, op="sum"):
+        """In-place all-reduce of a float64 CUDA tensor over the slab communicator (no-op for 1 rank)."""
+        self.call("plb_allreduce", tensor.data_ptr(), tensor.numel(), {"sum": 0, "max": 1, "min": 2}[op])
+        return tensor
 
     def profile(self, on=True):
         self.call("plb_profile_enable", 1 if on else 0)

@@ -59,7 +59,7 @@ def build_library(force=False, verbose=False):
             print(out.decode())
     target = lib_path()
     if force or procs or _stale(target, objs):
-        cmd = ["nvcc"] + ARCH + ["-shared", "-o", target] + objs + ["-lcudart"]
+        cmd = ["nvcc"] + ARCH + ["-shared", "-o", target] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s" % r.stdout.decode())

@@ -1,5 +1,6 @@
 // blas1.cu -- see blas1.cuh
 #include "blas1.cuh"
+#include "comm.cuh"
 
 namespace {
 
@@ -21,7 +22,7 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[J], double* par
         double s = 0;
 #pragma unroll
         for (int q = 0; q < TB / 32; q++) s += sm[threadIdx.x][q];
-        partials[(size_t)threadIdx.x * nblocks + blockIdx.x] = s;
+        partials[(size_t)threadIdx.x * nblocks + (blockIdx.y * gridDim.x + blockIdx.x)] = s;
     }
     __threadfence();
     __syncthreads();
@@ -47,19 +48,22 @@ struct VecList {
     const double* v[PLB_DOT_CHUNK];
 };
 
+// blockIdx.y selects the plane; each plane contributes its segment [base, base + n)
 template <int J>
 __global__ void __launch_bounds__(TB)
-k_multi_dot(long long n, VecList V, const double* __restrict__ w, double* partials,
-            unsigned int* ticket, double* out) {
+k_multi_dot(long long n, long long pstride, long long seg_off, VecList V, const double* __restrict__ w,
+            double* partials, unsigned int* ticket, double* out) {
     double acc[J];
 #pragma unroll
     for (int j = 0; j < J; j++) acc[j] = 0;
-    for (long long i = blockIdx.x * (long long)TB + threadIdx.x; i < n; i += (long long)gridDim.x * TB) {
+    const long long base = blockIdx.y * pstride + seg_off;
+    for (long long t = blockIdx.x * (long long)TB + threadIdx.x; t < n; t += (long long)gridDim.x * TB) {
+        const long long i = base + t;
         double wi = w[i];
 #pragma unroll
         for (int j = 0; j < J; j++) acc[j] += V.v[j][i] * wi;
     }
-    block_reduce_store<J>(acc, partials, gridDim.x, ticket, out);
+    block_reduce_store<J>(acc, partials, gridDim.x * gridDim.y, ticket, out);
 }
 
 struct VecList2 {
@@ -121,6 +125,7 @@ int vec_grid(const plb_ctx* ctx, long long n) { return plb_grid_for(ctx, n, TB, 
 
 int plb_reduce_ws_init(plb_ctx* ctx, plb_reduce_ws* ws) {
     ws->max_blocks = ctx->num_sms * 6;
+    ws->nplanes = 0, ws->pstride = 0, ws->seg_off = 0, ws->seg_len = 0, ws->allreduce = false;
     PLB_CUDA(ctx, cudaMalloc(&ws->partials, sizeof(double) * PLB_DOT_CHUNK * ws->max_blocks));
     PLB_CUDA(ctx, cudaMalloc(&ws->ticket, sizeof(unsigned int)));
     PLB_CUDA(ctx, cudaMemsetAsync(ws->ticket, 0, sizeof(unsigned int), ctx->stream));
@@ -136,19 +141,26 @@ void plb_reduce_ws_free(plb_reduce_ws* ws) {
 
 int plb_multi_dot(plb_ctx* ctx, plb_reduce_ws* ws, long long n, int k, const double* const* h_V,
                   const double* w, double* d_out) {
-    int grid = vec_grid(ctx, n);
-    if (grid > ws->max_blocks) grid = ws->max_blocks;
+    const int np = ws->nplanes > 0 ? ws->nplanes : 1;
+    const long long seg = ws->nplanes > 0 ? ws->seg_len : n;
+    const long long pstride = ws->nplanes > 0 ? ws->pstride : 0, seg_off = ws->nplanes > 0 ? ws->seg_off : 0;
+    int gx = vec_grid(ctx, seg * np) / np;
+    if (gx < 1) gx = 1;
+    if (gx * np > ws->max_blocks) gx = ws->max_blocks / np;
+    const dim3 grid(gx, np);
+    n = seg;
     // k vectors read once, w once per chunk of 8
-    plb_prof_scope prof_(ctx, PLB_K_MDOT, 8.0 * (double)n * (k + (k + PLB_DOT_CHUNK - 1) / PLB_DOT_CHUNK));
+    plb_prof_scope prof_(ctx, PLB_K_MDOT, 8.0 * (double)seg * np * (k + (k + PLB_DOT_CHUNK - 1) / PLB_DOT_CHUNK));
     for (int j0 = 0; j0 < k; j0 += PLB_DOT_CHUNK) {
         int J = k - j0 < PLB_DOT_CHUNK ? k - j0 : PLB_DOT_CHUNK;
         VecList V;
         for (int j = 0; j < PLB_DOT_CHUNK; j++) V.v[j] = h_V[j0 + (j < J ? j : 0)];
-#define MD(JJ) case JJ: k_multi_dot<JJ><<<grid, TB, 0, ctx->stream>>>(n, V, w, ws->partials, ws->ticket, d_out + j0); break;
+#define MD(JJ) case JJ: k_multi_dot<JJ><<<grid, TB, 0, ctx->stream>>>(n, pstride, seg_off, V, w, ws->partials, ws->ticket, d_out + j0); break;
         switch (J) { MD(1) MD(2) MD(3) MD(4) MD(5) MD(6) MD(7) MD(8) }
 #undef MD
         PLB_LAUNCHED(ctx);
     }
+    if (ws->allreduce && plb_comm_allreduce(ctx, d_out, (size_t)k, PLB_OP_SUM)) return 2;
     return 0;
 }
 

@@ -14,7 +14,20 @@ struct plb_reduce_ws {
     double* partials;          // [PLB_DOT_CHUNK * max_blocks]
     unsigned int* ticket;      // zero-initialised, self-resetting
     int max_blocks;
+    // slab-distributed vectors: `nplanes` planes of `pstride` doubles whose owned rows are the
+    // segment [seg_off, seg_off + seg_len) of each plane (halo rows are skipped by the reductions);
+    // nplanes == 0: plain contiguous vectors of n doubles.  `allreduce`: sum the results over the
+    // ranks of the context's communicator before they are used.
+    int nplanes;
+    long long pstride, seg_off, seg_len;
+    bool allreduce;
 };
+
+inline void plb_reduce_shape(plb_reduce_ws* ws, int nplanes, long long pstride, long long seg_off,
+                             long long seg_len, bool allreduce) {
+    ws->nplanes = nplanes, ws->pstride = pstride, ws->seg_off = seg_off, ws->seg_len = seg_len;
+    ws->allreduce = allreduce;
+}
 
 int plb_reduce_ws_init(plb_ctx* ctx, plb_reduce_ws* ws);
 void plb_reduce_ws_free(plb_reduce_ws* ws);

@@ -1,0 +1,151 @@
+// comm.cu -- one NCCL communicator per context (one process per GPU) for the z-slab solver:
+// halo rows over NVLink with grouped ncclSend/ncclRecv, Krylov dot products and the other small
+// reductions with ncclAllReduce.  NCCL is loaded with dlopen at run time (torch has normally loaded
+// its bundled libnccl.so.2 already, which is then reused), so the library has no link-time
+// dependency on it and single-GPU use never touches it.
+#include <dlfcn.h>
+
+#include "comm.cuh"
+
+namespace {
+
+// the few NCCL entry points used (signatures from nccl.h 2.27/2.28; ABI-stable since 2.7)
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm_t;
+enum { NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3, NCCL_DOUBLE = 8 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+} api;
+
+int load_api(plb_ctx* ctx) {
+    if (api.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) PLB_FAIL(ctx, "plb_comm: cannot dlopen libnccl.so.2 (%s)", dlerror());
+#define SYM(field, name)                                                     \
+    *(void**)(&api.field) = dlsym(api.lib, name);                            \
+    if (!api.field) PLB_FAIL(ctx, "plb_comm: NCCL symbol %s not found", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+}
+
+#define PLB_NCCL(ctx, call)                                                                     \
+    do {                                                                                        \
+        int r_ = (call);                                                                        \
+        if (r_ != 0) PLB_FAIL(ctx, "%s:%d: %s: %s", __FILE__, __LINE__, #call, api.GetErrorString(r_)); \
+    } while (0)
+
+}  // namespace
+
+struct plb_comm {
+    int rank = 0, size = 1;
+    nccl_comm_t comm = nullptr;
+};
+
+int plb_comm_rank(const plb_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
+int plb_comm_size(const plb_ctx* ctx) { return ctx->comm ? ctx->comm->size : 1; }
+
+int plb_comm_allreduce(plb_ctx* ctx, double* d_buf, size_t count, int op) {
+    if (!ctx->comm || ctx->comm->size == 1) return 0;
+    int nop = op == PLB_OP_SUM ? NCCL_SUM : (op == PLB_OP_MAX ? NCCL_MAX : NCCL_MIN);
+    PLB_NCCL(ctx, api.AllReduce(d_buf, d_buf, count, NCCL_DOUBLE, nop, ctx->comm->comm, ctx->stream));
+    return 0;
+}
+
+// Exchange one halo row per plane with the z-neighbours.  `base` points at local row 0 of plane 0;
+// local rows are [lo, hi] in global numbering with owned rows [r0, r1): rank > 0 has a halo row
+// below (lo = r0 - 1), rank < size-1 one above (hi = r1).
+int plb_comm_halo_exchange(plb_ctx* ctx, double* base, int nplanes, size_t plane_stride, int ld, int ncols,
+                           int lo, int r0, int r1) {
+    plb_comm* c = ctx->comm;
+    if (!c || c->size == 1) return 0;
+    const bool has_dn = c->rank > 0, has_up = c->rank < c->size - 1;
+    PLB_NCCL(ctx, api.GroupStart());
+    for (int p = 0; p < nplanes; p++) {
+        double* pl = base + (size_t)p * plane_stride;
+        if (has_dn) {
+            // my first owned row -> lower neighbour's upper halo; its last owned row -> my lower halo
+            PLB_NCCL(ctx, api.Send(pl + (size_t)(r0 - lo) * ld, ncols, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+            PLB_NCCL(ctx, api.Recv(pl + (size_t)(r0 - 1 - lo) * ld, ncols, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+        }
+        if (has_up) {
+            PLB_NCCL(ctx, api.Send(pl + (size_t)(r1 - 1 - lo) * ld, ncols, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+            PLB_NCCL(ctx, api.Recv(pl + (size_t)(r1 - lo) * ld, ncols, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+        }
+    }
+    PLB_NCCL(ctx, api.GroupEnd());
+    return 0;
+}
+
+extern "C" {
+
+int plb_comm_unique_id(plb_ctx* ctx, char* h_id128) {
+    if (!ctx || !h_id128) return 1;
+    if (load_api(ctx)) return 2;
+    nccl_uid id;
+    PLB_NCCL(ctx, api.GetUniqueId(&id));
+    memcpy(h_id128, id.internal, 128);
+    return 0;
+}
+
+int plb_comm_init(plb_ctx* ctx, int rank, int size, const char* h_id128) {
+    if (!ctx || size < 1 || rank < 0 || rank >= size) return 1;
+    if (ctx->comm) PLB_FAIL(ctx, "plb_comm_init: communicator already initialised");
+    if (load_api(ctx)) return 2;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    plb_comm* c = new plb_comm();
+    c->rank = rank, c->size = size;
+    nccl_uid id;
+    memcpy(id.internal, h_id128, 128);
+    int r = api.CommInitRank(&c->comm, size, id, rank);
+    if (r != 0) {
+        delete c;
+        PLB_FAIL(ctx, "ncclCommInitRank: %s", api.GetErrorString(r));
+    }
+    ctx->comm = c;
+    return 0;
+}
+
+int plb_comm_info(plb_ctx* ctx, int* h_rank, int* h_size) {
+    if (!ctx) return 1;
+    *h_rank = plb_comm_rank(ctx), *h_size = plb_comm_size(ctx);
+    return 0;
+}
+
+// in-place all-reduce of a device buffer of doubles (op: 0 sum, 1 max, 2 min) on the context's stream
+int plb_allreduce(plb_ctx* ctx, double* d_buf, long long count, int op) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return plb_comm_allreduce(ctx, d_buf, (size_t)count, op);
+}
+
+void plb_comm_destroy(plb_ctx* ctx) {
+    if (!ctx || !ctx->comm) return;
+    if (ctx->comm->comm) api.CommDestroy(ctx->comm->comm);
+    delete ctx->comm;
+    ctx->comm = nullptr;
+}
+
+}  // extern "C"

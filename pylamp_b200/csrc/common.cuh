@@ -7,8 +7,11 @@
 
 #include "../../include/pylamp_b200.h"
 
+struct plb_comm;
+
 struct plb_ctx {
     int device;
+    plb_comm* comm;        // z-slab communicator (NULL: single GPU)
     cudaStream_t stream;
     bool own_stream;
     char err[1024];

@@ -31,10 +31,13 @@ int plb_ctx_create(int device, plb_ctx** out) {
     return 0;
 }
 
+extern "C" void plb_comm_destroy(plb_ctx* ctx);
+
 void plb_ctx_destroy(plb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    plb_comm_destroy(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->prof_ev) {

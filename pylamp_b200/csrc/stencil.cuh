@@ -10,6 +10,7 @@
 
 struct LevelDev {
     int nz, nxx, ld;
+    int i0, i1;           // node rows [i0, i1) handled by this rank (z-slab); single GPU: [0, nz)
     const double* idz;    // [nz]  1/(gz[i+1]-gz[i]),   i <= nz-2   (0 beyond)
     const double* idzc;   // [nz]  1/(gz[i+1]-gz[i-1]), 1 <= i <= nz-2 (0 elsewhere)
     const double* idx;    // [nxx] 1/(gx[j+1]-gx[j])

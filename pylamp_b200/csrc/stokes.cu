@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "blas1.cuh"
+#include "comm.cuh"
 #include "fgmres.cuh"
 #include "stencil.cuh"
 
@@ -20,7 +21,13 @@ inline dim3 block2d() { return dim3(BX, BY); }
 
 struct Level {
     int nz = 0, nxx = 0, ld = 0;
-    size_t plane = 0;
+    // z-slab ownership (global row numbers): owned node rows [i0, i1), stored rows [lo, hi]
+    // (one halo row towards each existing neighbour).  Replicated levels: i0 = lo = 0, i1 = nz.
+    int i0 = 0, i1 = 0, lo = 0, hi = 0;
+    bool dist = false;
+    size_t plane = 0;      // doubles per LOCAL plane = (hi - lo + 1) * ld
+    size_t full = 0;       // doubles per full plane = nz * ld (coefficient fields are replicated)
+    long long shift = 0;   // lo * ld: kernels index with global rows through shifted pointers
     std::vector<double> gz, gx;
     double *idz = nullptr, *idzc = nullptr, *idx = nullptr, *idxc = nullptr;
     const double *etas = nullptr, *etan = nullptr;
@@ -29,11 +36,11 @@ struct Level {
     int vz_i0, vz_i1, vz_j0, vz_j1, vx_i0, vx_i1, vx_j0, vx_j1;
     double sl_z0 = 1, sl_z1 = 1;
     int ns_z0 = 0, ns_z1 = 0;
-    double *X = nullptr, *T = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;   // 2 planes each
+    double *X = nullptr, *T = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;   // 2 local planes each
     double lmax = 0;
     LevelDev dev() const {
         LevelDev L;
-        L.nz = nz, L.nxx = nxx, L.ld = ld;
+        L.nz = nz, L.nxx = nxx, L.ld = ld, L.i0 = i0, L.i1 = i1;
         L.idz = idz, L.idzc = idzc, L.idx = idx, L.idxc = idxc;
         L.etas = etas, L.etan = etan, L.proper = proper;
         L.vz_i0 = vz_i0, L.vz_i1 = vz_i1, L.vz_j0 = vz_j0, L.vz_j1 = vz_j1;
@@ -42,6 +49,10 @@ struct Level {
         L.ns_z0 = ns_z0, L.ns_z1 = ns_z1;
         return L;
     }
+    // pointer to a local array as the kernels see it (global row indexing)
+    double* sh(double* p) const { return p - shift; }
+    const double* sh(const double* p) const { return p - shift; }
+    dim3 grid() const { return grid2d(i1 - i0, nxx); }
 };
 
 }  // namespace
@@ -112,8 +123,8 @@ __global__ void __launch_bounds__(BX* BY)
 k_stokes_full(LevelDev L, FullArgs a, const double* __restrict__ vz, const double* __restrict__ vx,
               const double* __restrict__ p, double* __restrict__ yz, double* __restrict__ yx,
               double* __restrict__ yp) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     const int nz = L.nz, nxx = L.nxx, ld = L.ld;
     const long long o = (long long)i * ld + j;
     const double Kc = a.Kc;
@@ -169,8 +180,8 @@ k_stokes_full(LevelDev L, FullArgs a, const double* __restrict__ vz, const doubl
 __global__ void __launch_bounds__(BX* BY)
 k_stokes_rhs(LevelDev L, const double* __restrict__ rho, double g_z, double g_x,
              double* __restrict__ bz, double* __restrict__ bx, double* __restrict__ bp) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j;
     bz[o] = is_vz_row(L, i, j) ? -0.5 * (rho[o] + rho[o + 1]) * g_z : 0.0;
     bx[o] = is_vx_row(L, i, j) ? -0.5 * (rho[o] + rho[o + L.ld]) * g_x : 0.0;
@@ -194,6 +205,16 @@ k_deinterleave(long long n, const double* __restrict__ x, double* __restrict__ a
     }
 }
 
+// full-size interleaved vector (reference layout) -> local planes, owned rows only
+__global__ void __launch_bounds__(BX* BY)
+k_deinterleave_rows(LevelDev L, const double* __restrict__ x, double* __restrict__ a, double* __restrict__ b,
+                    double* __restrict__ c) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
+    const long long o = (long long)i * L.ld + j, t = (long long)i * L.nxx + j;
+    a[o] = x[3 * t], b[o] = x[3 * t + 1], c[o] = x[3 * t + 2];
+}
+
 // -------------------------------------------------------------------------------------------
 // reduced (BC-eliminated) saddle-point operator with the weighted-norm row scaling
 //   RESID: out = W (b - A x)   else   out = W (A x);   W_v = 1/sqrt|diag K|, W_p = sqrt(eta_n)/Kc
@@ -205,8 +226,8 @@ k_stokes_op(LevelDev L, double Kc, const double* __restrict__ vz, const double* 
             const double* __restrict__ p, const double* __restrict__ bz, const double* __restrict__ bx,
             const double* __restrict__ bp, double* __restrict__ oz, double* __restrict__ ox,
             double* __restrict__ op) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     const int ld = L.ld;
     const long long o = (long long)i * ld + j;
     if (is_interior(L, i, j)) {
@@ -257,8 +278,8 @@ __global__ void __launch_bounds__(BX* BY)
 k_precond_rhs(LevelDev L, double Kc, const double* __restrict__ rz, const double* __restrict__ rx,
               const double* __restrict__ rp, double* __restrict__ zp, double* __restrict__ bvz,
               double* __restrict__ bvx) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     const int ld = L.ld, nz = L.nz, nxx = L.nxx;
     const long long o = (long long)i * ld + j;
     if (is_interior(L, i, j) && i <= nz - 3 && j <= nxx - 3) {
@@ -304,8 +325,8 @@ __global__ void __launch_bounds__(BX* BY)
 k_cheb(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
        const double* __restrict__ bz, const double* __restrict__ bx, double* __restrict__ dz,
        double* __restrict__ dx, double* __restrict__ oz, double* __restrict__ ox, double cd, double cr) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j;
     const bool rz = is_vz_row(L, i, j), rx = is_vx_row(L, i, j);
     if (is_interior(L, i, j)) {
@@ -362,8 +383,8 @@ __global__ void __launch_bounds__(BX* BY)
 k_vel_op(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
          const double* __restrict__ bz, const double* __restrict__ bx, double* __restrict__ rz,
          double* __restrict__ rx) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j;
     if (MODE == 0 && is_interior(L, i, j)) {
         const double bzv = bz[o], bxv = bx[o];
@@ -393,8 +414,8 @@ k_vel_op(LevelDev L, const double* __restrict__ xz, const double* __restrict__ x
 // deterministic pseudo-random start vector for the power iteration (rows + slaves)
 __global__ void __launch_bounds__(BX* BY)
 k_fill_random(LevelDev L, double* __restrict__ xz, double* __restrict__ xx) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     unsigned long long h = ((unsigned long long)i * 2654435761ull) ^ ((unsigned long long)j * 40503ull + 12345ull);
     h ^= h >> 13, h *= 0x9E3779B97F4A7C15ull, h ^= h >> 29;
     double u = (double)(h & 0xFFFFFF) / 16777216.0 - 0.5;
@@ -408,8 +429,8 @@ k_fill_random(LevelDev L, double* __restrict__ xz, double* __restrict__ xx) {
 __global__ void __launch_bounds__(BX* BY)
 k_restrict(LevelDev F, LevelDev Cc, const double* __restrict__ rz, const double* __restrict__ rx,
            double* __restrict__ bz, double* __restrict__ bx) {
-    const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
-    if (I >= Cc.nz || J >= Cc.nxx) return;
+    const int J = blockIdx.x * BX + threadIdx.x, I = Cc.i0 + blockIdx.y * BY + threadIdx.y;
+    if (I >= Cc.i1 || J >= Cc.nxx) return;
     const long long oc = (long long)I * Cc.ld + J;
     const int ldf = F.ld;
     double s = 0;
@@ -467,8 +488,8 @@ __global__ void __launch_bounds__(BX* BY)
 k_prolong_add(LevelDev F, LevelDev Cc, const double* __restrict__ ez, const double* __restrict__ ex,
               const double* __restrict__ xz, const double* __restrict__ xx, double* __restrict__ oz,
               double* __restrict__ ox) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= F.nz || j >= F.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = F.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= F.i1 || j >= F.nxx) return;
     const long long o = (long long)i * F.ld + j;
     const int ldc = Cc.ld;
     if (is_vz_row(F, i, j)) {
@@ -549,8 +570,8 @@ __device__ __forceinline__ int unk_vx(const LevelDev& L, int i, int j) {
 
 // probe k = unit vector of unknown k (with its slaves) in its own pair of planes
 __global__ void k_probe_set(LevelDev L, int n, size_t plane, double* __restrict__ probes) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     if (is_vz_row(L, i, j)) store_vz(L, probes + (size_t)unk_vz(L, i, j) * 2 * plane, i, j, 1.0);
     if (is_vx_row(L, i, j)) store_vx(L, probes + (size_t)unk_vx(L, i, j) * 2 * plane + plane, i, j, 1.0);
 }
@@ -667,7 +688,8 @@ k_dense_solve(LevelDev L, int n, const double* __restrict__ inv, const double* _
 __global__ void __launch_bounds__(256) k_row_mean(LevelDev L, const double* __restrict__ bz, double* __restrict__ m) {
     const int i = blockIdx.x;
     double s = 0;
-    if (i >= L.vz_i0 && i <= L.vz_i1)
+    const bool mine = i >= L.i0 && i < L.i1 && i >= L.vz_i0 && i <= L.vz_i1;
+    if (mine)
         for (int j = L.vz_j0 + threadIdx.x; j <= L.vz_j1; j += blockDim.x) s += bz[(long long)i * L.ld + j];
     s = warp_sum(s);
     __shared__ double sm[8];
@@ -675,7 +697,7 @@ __global__ void __launch_bounds__(256) k_row_mean(LevelDev L, const double* __re
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int q = 1; q < 8; q++) s += sm[q];
-        m[i] = (i >= L.vz_i0 && i <= L.vz_i1) ? s / (L.vz_j1 - L.vz_j0 + 1) : 0.0;
+        m[i] = mine ? s / (L.vz_j1 - L.vz_j0 + 1) : 0.0;
     }
 }
 // P_h per cell row with P_h(row 3) = 0 (the anchor row): -2 Kc idzc[i] (P_h[i] - P_h[i-1]) = m[i]
@@ -690,8 +712,8 @@ __global__ void k_scan_ph(LevelDev L, double Kc, const double* __restrict__ m, d
 }
 __global__ void __launch_bounds__(BX* BY)
 k_sub_row_mean(LevelDev L, const double* __restrict__ m, double* __restrict__ bz) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     if (is_vz_row(L, i, j)) bz[(long long)i * L.ld + j] -= m[i];
 }
 
@@ -699,8 +721,8 @@ k_sub_row_mean(LevelDev L, const double* __restrict__ m, double* __restrict__ bz
 __global__ void __launch_bounds__(BX* BY)
 k_solution_out(LevelDev L, const double* __restrict__ vz, const double* __restrict__ vx,
                const double* __restrict__ p, const double* __restrict__ ph, double* __restrict__ x) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= L.nz || j >= L.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j, t = (long long)i * L.nxx + j;
     double pv = p[o];
     if ((i == 0 || i == L.nz - 2) && (j == 0 || j == L.nxx - 2)) pv = (j == 0) ? p[o + 1] : p[o - 1];
@@ -744,19 +766,65 @@ void free_level(Level& L) {
         if (p) cudaFree(p);
 }
 
+int halo(plb_stokes* op, const Level& L, double* local, int nplanes) {
+    if (!L.dist) return 0;
+    return plb_comm_halo_exchange(op->ctx, local, nplanes, L.plane, L.ld, L.nxx, L.lo, L.i0, L.i1);
+}
+
+// reductions over 2-plane (velocity) or 3-plane vectors of level L: owned rows only, summed over ranks
+void reduce_shape(plb_stokes* op, const Level& L, int nplanes) {
+    if (L.dist)
+        plb_reduce_shape(&op->rws, nplanes, (long long)L.plane, (long long)(L.i0 - L.lo) * L.ld,
+                         (long long)(L.i1 - L.i0) * L.ld, true);
+    else
+        plb_reduce_shape(&op->rws, 0, 0, 0, 0, false);
+}
+
 int build_levels(plb_stokes* op, const double* h_gz, const double* h_gx) {
     plb_ctx* ctx = op->ctx;
-    int nz = op->nz, nxx = op->nxx;
-    std::vector<double> gz(h_gz, h_gz + nz), gx(h_gx, h_gx + nxx);
-    for (int l = 0;; l++) {
+    const int R = plb_comm_size(ctx), rank = plb_comm_rank(ctx);
+    // grid sizes of all levels
+    std::vector<std::vector<double>> GZ, GX;
+    {
+        std::vector<double> gz(h_gz, h_gz + op->nz), gx(h_gx, h_gx + op->nxx);
+        for (;;) {
+            GZ.push_back(gz), GX.push_back(gx);
+            int cz = (int)gz.size() - 1, cx = (int)gx.size() - 1;
+            if ((cz % 2) || (cx % 2) || std::min(cz, cx) / 2 < 4) break;
+            std::vector<double> ngz, ngx;
+            for (size_t i = 0; i < gz.size(); i += 2) ngz.push_back(gz[i]);
+            for (size_t j = 0; j < gx.size(); j += 2) ngx.push_back(gx[j]);
+            gz.swap(ngz), gx.swap(ngx);
+        }
+    }
+    const int nlev = (int)GZ.size();
+    for (int l = 0; l < nlev; l++) {
         Level L;
-        L.nz = nz, L.nxx = nxx, L.ld = nxx, L.plane = (size_t)nz * nxx;
-        L.gz = gz, L.gx = gx;
+        const int nz = (int)GZ[l].size(), nxx = (int)GX[l].size();
+        L.nz = nz, L.nxx = nxx, L.ld = nxx, L.full = (size_t)nz * nxx;
+        L.gz = GZ[l], L.gx = GX[l];
+        // slab-distributed while every rank keeps an even number (>= 4) of cell rows; the coarsest
+        // level is always replicated (dense solve)
+        const int cells = nz - 1;
+        const bool prev_dist = l == 0 ? true : op->lv[l - 1].dist;
+        L.dist = R > 1 && prev_dist && l < nlev - 1 && cells % R == 0 && (cells / R) >= 4 && (cells / R) % 2 == 0;
+        if (R > 1 && l == 0 && !L.dist)
+            PLB_FAIL(ctx, "plb_stokes_create: %d cell rows cannot be split into %d even slabs of >= 4 rows", cells, R);
+        if (L.dist) {
+            const int c = cells / R;
+            L.i0 = rank * c, L.i1 = (rank + 1) * c + (rank == R - 1 ? 1 : 0);
+            L.lo = rank > 0 ? L.i0 - 1 : 0, L.hi = rank < R - 1 ? L.i1 : nz - 1;
+        } else {
+            L.i0 = 0, L.i1 = nz, L.lo = 0, L.hi = nz - 1;
+        }
+        L.plane = (size_t)(L.hi - L.lo + 1) * L.ld;
+        L.shift = (long long)L.lo * L.ld;
         L.proper = l > 0;
         if (l == 0) {
             L.vz_i0 = 1, L.vz_i1 = nz - 2, L.vz_j0 = 1, L.vz_j1 = nxx - 3;
             L.vx_i0 = 1, L.vx_i1 = nz - 3, L.vx_j0 = 1, L.vx_j1 = nxx - 2;
             // slave factors of the tangential wall rows (pylamp_stokes.py:163-175, :202-214)
+            const std::vector<double>& gz = L.gz;
             if (op->bc[0] == PLB_BC_NOSLIP) {
                 double d2 = gz[2] - gz[0], d1 = gz[1] - gz[0];
                 L.sl_z0 = (1 / d2) / (1 / d2 + 1 / d1);
@@ -772,20 +840,14 @@ int build_levels(plb_stokes* op, const double* h_gz, const double* h_gx) {
         }
         if (level_metrics(ctx, L)) return 2;
         if (l > 0) {
-            if (zalloc(ctx, &L.etas_own, L.plane) || zalloc(ctx, &L.etan_own, L.plane)) return 2;
+            // coefficient fields are full-size on every rank (coarsened redundantly: no communication)
+            if (zalloc(ctx, &L.etas_own, L.full) || zalloc(ctx, &L.etan_own, L.full)) return 2;
             L.etas = L.etas_own, L.etan = L.etan_own;
         }
         if (zalloc(ctx, &L.X, 2 * L.plane) || zalloc(ctx, &L.T, 2 * L.plane) || zalloc(ctx, &L.b, 2 * L.plane) ||
             zalloc(ctx, &L.r, 2 * L.plane) || zalloc(ctx, &L.d, 2 * L.plane))
             return 2;
         op->lv.push_back(L);
-        int cz = nz - 1, cx = nxx - 1;
-        if ((cz % 2) || (cx % 2) || std::min(cz, cx) / 2 < 4) break;
-        std::vector<double> ngz, ngx;
-        for (int i = 0; i < nz; i += 2) ngz.push_back(gz[i]);
-        for (int j = 0; j < nxx; j += 2) ngx.push_back(gx[j]);
-        gz.swap(ngz), gx.swap(ngx);
-        nz = cz / 2 + 1, nxx = cx / 2 + 1;
     }
     return 0;
 }
@@ -795,7 +857,7 @@ int n_unknowns(const Level& L) {
 }
 
 // nu Chebyshev steps on level l.  `from_zero`: the iterate is zero on entry.  Writes alternate
-// between the two buffers; returns the buffer holding the result.
+// between the two buffers; returns the buffer holding the result (halo rows exchanged).
 double* smooth(plb_stokes* op, int l, const double* b, double* cur, double* other, bool from_zero, int nu) {
     Level& L = op->lv[l];
     plb_ctx* ctx = op->ctx;
@@ -811,23 +873,27 @@ double* smooth(plb_stokes* op, int l, const double* b, double* cur, double* othe
             double rn = 1.0 / (2 * sigma - rho);
             cd = rn * rho, cr = 2 * rn / delta, rho = rn;
         }
-        plb_prof_scope prof_(ctx, l == 0 ? PLB_K_CHEB0 : -1, ((k == 0 && from_zero) ? 64.0 : 96.0) * (double)P);
-        if (k == 0 && from_zero) {
-            // result goes to `cur` (no input needed)
-            k_cheb<true><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(
-                D, nullptr, nullptr, b, b + P, L.d, L.d + P, cur, cur + P, cd, cr);
-        } else {
-            k_cheb<false><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(
-                D, cur, cur + P, b, b + P, L.d, L.d + P, other, other + P, cd, cr);
-            std::swap(cur, other);
+        {
+            plb_prof_scope prof_(ctx, l == 0 ? PLB_K_CHEB0 : -1, ((k == 0 && from_zero) ? 64.0 : 96.0) * (double)P);
+            if (k == 0 && from_zero) {
+                // result goes to `cur` (no input needed)
+                k_cheb<true><<<L.grid(), block2d(), 0, ctx->stream>>>(D, nullptr, nullptr, L.sh(b), L.sh(b + P), L.sh(L.d),
+                                                                      L.sh(L.d + P), L.sh(cur), L.sh(cur + P), cd, cr);
+            } else {
+                k_cheb<false><<<L.grid(), block2d(), 0, ctx->stream>>>(D, L.sh(cur), L.sh(cur + P), L.sh(b), L.sh(b + P),
+                                                                       L.sh(L.d), L.sh(L.d + P), L.sh(other),
+                                                                       L.sh(other + P), cd, cr);
+                std::swap(cur, other);
+            }
+            ctx->launches++;
         }
-        ctx->launches++;
+        if (halo(op, L, cur, 2)) return nullptr;
     }
     return cur;
 }
 
-// one V-cycle for K x = b on level l; the result lands in `xout` (2 planes).  Buffers alternate
-// so that the (2 nu + 1)-th write hits xout.
+// one V-cycle for K x = b on level l; the result lands in `xout` (2 local planes, halos valid).
+// Buffers alternate so that the (2 nu + 1)-th write hits xout.
 int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
     Level& L = op->lv[l];
     plb_ctx* ctx = op->ctx;
@@ -851,15 +917,26 @@ int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
     double* other = L.T;
     // write 1 -> xout, 2 -> T, 3 -> xout ...: after nu writes the iterate is in (nu odd ? xout : T)
     double* cur = smooth(op, l, b, xout, other, true, op->nu);
+    if (!cur) return 2;
     double* oth = (cur == xout) ? other : xout;
     Level& Cl = op->lv[l + 1];
-    const LevelDev DC = Cl.dev();
+    LevelDev DC = Cl.dev();
     {
         plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGXFER0 : -1, 84.0 * (double)P);
-        k_vel_op<0><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, cur, cur + P, b, b + P, L.r, L.r + P);
+        k_vel_op<0><<<L.grid(), block2d(), 0, ctx->stream>>>(D, L.sh(cur), L.sh(cur + P), L.sh(b), L.sh(b + P),
+                                                            L.sh(L.r), L.sh(L.r + P));
         PLB_LAUNCHED(ctx);
-        k_restrict<<<grid2d(Cl.nz, Cl.nxx), block2d(), 0, ctx->stream>>>(D, DC, L.r, L.r + P, Cl.b, Cl.b + Cl.plane);
+        if (halo(op, L, L.r, 2)) return 2;
+        if (L.dist && !Cl.dist) {
+            // transition to the replicated levels: every rank restricts the coarse rows under its own
+            // fine rows into the full-size coarse right-hand side, then the pieces are summed
+            PLB_CUDA(ctx, cudaMemsetAsync(Cl.b, 0, sizeof(double) * 2 * Cl.plane, ctx->stream));
+            DC.i0 = L.i0 / 2, DC.i1 = (L.i1 + 1) / 2;
+        }
+        k_restrict<<<grid2d(DC.i1 - DC.i0, Cl.nxx), block2d(), 0, ctx->stream>>>(D, DC, L.sh(L.r), L.sh(L.r + P),
+                                                                              Cl.sh(Cl.b), Cl.sh(Cl.b + Cl.plane));
         PLB_LAUNCHED(ctx);
+        if (L.dist && !Cl.dist && plb_comm_allreduce(ctx, Cl.b, 2 * Cl.plane, PLB_OP_SUM)) return 2;
     }
     {
         plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGCOARSE : -1);
@@ -867,12 +944,14 @@ int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
     }
     {
         plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGXFER0 : -1, 36.0 * (double)P);
-        k_prolong_add<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, DC, Cl.X, Cl.X + Cl.plane, cur, cur + P,
-                                                                       oth, oth + P);
+        k_prolong_add<<<L.grid(), block2d(), 0, ctx->stream>>>(D, Cl.dev(), Cl.sh(Cl.X), Cl.sh(Cl.X + Cl.plane),
+                                                              L.sh(cur), L.sh(cur + P), L.sh(oth), L.sh(oth + P));
         PLB_LAUNCHED(ctx);
+        if (halo(op, L, oth, 2)) return 2;
     }
     std::swap(cur, oth);
     cur = smooth(op, l, b, cur, oth, false, op->nu);
+    if (!cur) return 2;
     PLB_CUDA(ctx, cudaGetLastError());
     if (cur != xout) PLB_FAIL(ctx, "internal: V-cycle buffer parity");
     return 0;
@@ -881,7 +960,7 @@ int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
 int setup_hierarchy(plb_stokes* op) {
     plb_ctx* ctx = op->ctx;
     const int nlev = (int)op->lv.size();
-    // coarse viscosities
+    // coarse viscosities: full grids, computed redundantly on every rank
     for (int l = 1; l < nlev; l++) {
         Level &F = op->lv[l - 1], &Cc = op->lv[l];
         k_coarsen_eta<<<grid2d(Cc.nz, Cc.nxx), block2d(), 0, ctx->stream>>>(
@@ -895,22 +974,24 @@ int setup_hierarchy(plb_stokes* op) {
         const LevelDev D = L.dev();
         const size_t P = L.plane;
         double *x = L.X, *y = L.T;
+        reduce_shape(op, L, 2);
         PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 2 * P, ctx->stream));
         PLB_CUDA(ctx, cudaMemsetAsync(y, 0, sizeof(double) * 2 * P, ctx->stream));
-        k_fill_random<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, x, x + P);
+        k_fill_random<<<L.grid(), block2d(), 0, ctx->stream>>>(D, L.sh(x), L.sh(x + P));
         PLB_LAUNCHED(ctx);
+        if (halo(op, L, x, 2)) return 2;
         double* s = op->d_scal + 900;
-        for (int it = 0; it < npow; it++) {
-            k_vel_op<1><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, x, x + P, nullptr, nullptr, y, y + P);
+        for (int it = 0; it <= npow; it++) {
+            k_vel_op<1><<<L.grid(), block2d(), 0, ctx->stream>>>(D, L.sh(x), L.sh(x + P), nullptr, nullptr, L.sh(y),
+                                                                L.sh(y + P));
             PLB_LAUNCHED(ctx);
             if (plb_dot(ctx, &op->rws, 2 * P, y, y, s)) return 2;
+            if (it == npow) break;          // last application: Rayleigh-type estimate below
             if (plb_scale_rsqrt2(ctx, 2 * P, s, y, nullptr)) return 2;
+            if (halo(op, L, y, 2)) return 2;
             std::swap(x, y);
         }
-        // Rayleigh-type estimate: || D^-1 K x || with ||x|| = 1 (over rows + slaves)
-        k_vel_op<1><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(D, x, x + P, nullptr, nullptr, y, y + P);
-        PLB_LAUNCHED(ctx);
-        if (plb_dot(ctx, &op->rws, 2 * P, y, y, s)) return 2;
+        // || D^-1 K x || / || x || (over the momentum rows and their slaves)
         if (plb_dot(ctx, &op->rws, 2 * P, x, x, s + 1)) return 2;
         double h[2];
         if (plb_read_scalars(ctx, s, 2, h)) return 2;
@@ -919,7 +1000,8 @@ int setup_hierarchy(plb_stokes* op) {
         PLB_CUDA(ctx, cudaMemsetAsync(L.X, 0, sizeof(double) * 2 * P, ctx->stream));
         PLB_CUDA(ctx, cudaMemsetAsync(L.T, 0, sizeof(double) * 2 * P, ctx->stream));
     }
-    // dense inverse on the coarsest level
+    reduce_shape(op, op->lv[0], 3);
+    // dense inverse on the coarsest level (replicated)
     Level& Lc = op->lv[nlev - 1];
     const int n = n_unknowns(Lc);
     if (op->cinv) cudaFree(op->cinv), op->cinv = nullptr;
@@ -1043,7 +1125,7 @@ int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_
     double* d = op->d_scal + 920;
     k_set1<<<1, 1, 0, ctx->stream>>>(d, INFINITY);
     PLB_LAUNCHED(ctx);
-    k_min2<<<plb_grid_for(ctx, (long long)L.plane, 256, 8), 256, 0, ctx->stream>>>((long long)L.plane, d_etas, d_etan, d);
+    k_min2<<<plb_grid_for(ctx, (long long)L.full, 256, 8), 256, 0, ctx->stream>>>((long long)L.full, d_etas, d_etan, d);
     PLB_LAUNCHED(ctx);
     double mineta;
     if (plb_read_scalars(ctx, d, 1, &mineta)) return 2;
@@ -1066,6 +1148,7 @@ int plb_stokes_rhs(plb_stokes* op, double* d_rhs) {
     if (!op) return 1;
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_rhs: coefficients not set");
+    if (op->lv[0].dist) PLB_FAIL(ctx, "plb_stokes_rhs: not available on a slab-distributed operator");
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ensure_krylov(op)) return 2;
     Level& L = op->lv[0];
@@ -1083,6 +1166,7 @@ int plb_stokes_apply(plb_stokes* op, const double* d_x, double* d_y) {
     if (!op) return 1;
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_apply: coefficients not set");
+    if (op->lv[0].dist) PLB_FAIL(ctx, "plb_stokes_apply: not available on a slab-distributed operator");
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ensure_krylov(op)) return 2;
     Level& L = op->lv[0];
@@ -1105,6 +1189,7 @@ int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2) {
     if (!op) return 1;
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_vcycle: coefficients not set");
+    if (op->lv[0].dist) PLB_FAIL(ctx, "plb_stokes_vcycle: not available on a slab-distributed operator");
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!op->hierarchy && setup_hierarchy(op)) return 2;
     PLB_CUDA(ctx, cudaMemsetAsync(d_x2, 0, sizeof(double) * 2 * op->lv[0].plane, ctx->stream));
@@ -1130,43 +1215,44 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     const size_t P = L.plane;
     const double Kc = op->Kc;
     double *x = op->xs, *r = op->r3, *b = op->b3;
-    const dim3 g = grid2d(L.nz, L.nxx), blk = block2d();
+    const dim3 g = L.grid(), blk = block2d();
+    // kernels index with global rows: shifted views of the local (slab) vectors
+    auto V3 = [&](double* v, int pl) { return L.sh(v + (size_t)pl * P); };
+    auto C3 = [&](const double* v, int pl) { return L.sh(v + (size_t)pl * P); };
+    reduce_shape(op, L, 3);
     if (d_rhs) {
-        // caller's right-hand side in the reference layout; entries on wall/ghost/corner/anchor rows
-        // are homogeneous in the reference (pylamp_stokes.py never writes them) and are ignored
-        k_deinterleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, d_rhs, b, b + P,
-                                                                                      b + 2 * P);
+        // caller's right-hand side in the reference layout (full size); entries on wall/ghost/corner/
+        // anchor rows are homogeneous in the reference (pylamp_stokes.py never writes them): ignored
+        k_deinterleave_rows<<<g, blk, 0, ctx->stream>>>(D, d_rhs, V3(b, 0), V3(b, 1), V3(b, 2));
     } else {
-        k_stokes_rhs<<<g, blk, 0, ctx->stream>>>(D, op->rho, op->g_z, op->g_x, b, b + P, b + 2 * P);
+        k_stokes_rhs<<<g, blk, 0, ctx->stream>>>(D, op->rho, op->g_z, op->g_x, V3(b, 0), V3(b, 1), V3(b, 2));
     }
     PLB_LAUNCHED(ctx);
     double* ph = nullptr;
     if (op->hydrostatic) {
         double* m = op->d_scal + 1024;        // [nz] row means, then [nz] P_h
         ph = m + L.nz;
-        k_row_mean<<<L.nz, 256, 0, ctx->stream>>>(D, b, m);
+        k_row_mean<<<L.nz, 256, 0, ctx->stream>>>(D, C3(b, 0), m);
         PLB_LAUNCHED(ctx);
+        if (L.dist && plb_comm_allreduce(ctx, m, (size_t)L.nz, PLB_OP_SUM)) return 2;   // rows of other slabs
         k_scan_ph<<<1, 1, 0, ctx->stream>>>(D, Kc, m, ph);
         PLB_LAUNCHED(ctx);
-        k_sub_row_mean<<<g, blk, 0, ctx->stream>>>(D, m, b);
+        k_sub_row_mean<<<g, blk, 0, ctx->stream>>>(D, m, V3(b, 0));
         PLB_LAUNCHED(ctx);
     }
-    auto residual = [&](double* out) -> int {
+    auto stokes_resid = [&](double* xx, double* out) -> int {
+        if (halo(op, L, xx, 3)) return 2;
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 88.0 * (double)P);
-        k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, x, x + P, x + 2 * P, b, b + P, b + 2 * P, out, out + P,
-                                                      out + 2 * P);
+        k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2), C3(b, 0), C3(b, 1),
+                                                      C3(b, 2), V3(out, 0), V3(out, 1), V3(out, 2));
         PLB_LAUNCHED(ctx);
         return 0;
     };
+    auto residual = [&](double* out) -> int { return stokes_resid(x, out); };
     // || W b ||: the scaled norm of the right-hand side (W b is the residual of x = 0 and the
     // operator is linear, so evaluate it with a zero iterate in the scratch vector)
     PLB_CUDA(ctx, cudaMemsetAsync(op->t3, 0, sizeof(double) * 3 * P, ctx->stream));
-    {
-        double* z0 = op->t3;
-        k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, z0, z0 + P, z0 + 2 * P, b, b + P, b + 2 * P, r, r + P,
-                                                      r + 2 * P);
-        PLB_LAUNCHED(ctx);
-    }
+    if (stokes_resid(op->t3, r)) return 2;
     double bn2;
     if (plb_dot(ctx, &op->rws, 3 * P, r, r, op->d_scal + 910)) return 2;
     if (plb_read_scalars(ctx, op->d_scal + 910, 1, &bn2)) return 2;
@@ -1177,21 +1263,27 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
     int vcycles = 0;
     auto apply = [&](const double* z, double* c) -> int {
+        // z comes out of `precond` with valid halo rows
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 64.0 * (double)P);
-        k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, z, z + P, z + 2 * P, nullptr, nullptr, nullptr, c,
-                                                       c + P, c + 2 * P);
+        k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr, nullptr, nullptr,
+                                                       V3(c, 0), V3(c, 1), V3(c, 2));
         PLB_LAUNCHED(ctx);
         return 0;
     };
     auto precond = [&](const double* rr, double* z) -> int {
+        // the pressure residual of the row below is read across the slab boundary
+        if (halo(op, L, const_cast<double*>(rr) + 2 * P, 1)) return 2;
         {
             plb_prof_scope prof_(ctx, PLB_K_PRECRHS, 80.0 * (double)P);
-            k_precond_rhs<<<g, blk, 0, ctx->stream>>>(D, Kc, rr, rr + P, rr + 2 * P, z + 2 * P, L.b, L.b + P);
+            k_precond_rhs<<<g, blk, 0, ctx->stream>>>(D, Kc, C3(rr, 0), C3(rr, 1), C3(rr, 2), V3(z, 2), L.sh(L.b),
+                                                      L.sh(L.b + P));
             PLB_LAUNCHED(ctx);
             PLB_CUDA(ctx, cudaMemsetAsync(z, 0, sizeof(double) * 2 * P, ctx->stream));
         }
         vcycles++;
-        return vcycle(op, 0, L.b, z);
+        if (vcycle(op, 0, L.b, z)) return 2;
+        reduce_shape(op, L, 3);                      // the V-cycle set per-level shapes
+        return halo(op, L, z + 2 * P, 1);            // velocity halos are valid after the last sweep
     };
     plb_fgmres_result res;
     op->kry.reorth_thresh = op->kry_reorth;
@@ -1208,7 +1300,11 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     op->have_prev = res.converged || res.relres <= op->rtol_accept;
     if (h_iters) *h_iters = total;
     if (h_relres) *h_relres = res.relres;
-    k_solution_out<<<g, blk, 0, ctx->stream>>>(D, x, x + P, x + 2 * P, ph, d_x);
+    // full-size interleaved solution; a slab rank fills its own rows and leaves the rest zero (the
+    // host side sums the pieces, e.g. with plb_allreduce)
+    if (L.dist) PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * 3 * L.full, ctx->stream));
+    if (halo(op, L, x + 2 * P, 1)) return 2;         // corner pressures copy their x-neighbour only: no z halo needed, kept for symmetry
+    k_solution_out<<<g, blk, 0, ctx->stream>>>(D, C3(x, 0), C3(x, 1), C3(x, 2), ph, d_x);
     PLB_LAUNCHED(ctx);
     if (!res.converged && res.relres > op->rtol_accept)
         PLB_FAIL(ctx, "plb_stokes_solve: not converged after %d iterations (relres %.3e > rtol %.3e, "

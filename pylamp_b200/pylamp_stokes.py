@@ -126,6 +126,8 @@ class StokesOperator:
         self.iterations, self.relres = it.value, rr.value
         if rc != 0 and raise_on_fail:
             self.ctx.check(rc)
+        if self.ctx.comm_info()[1] > 1:
+            self.ctx.allreduce(x)       # every slab rank filled its own rows: sum the pieces
         return x.cpu().numpy() if host else x
 
     @property
