@@ -239,6 +239,7 @@ int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, do
     };
     auto precond = [&](const double* v, double* z) -> int { return plb_copy(ctx, n, v, z); };
     plb_fgmres_result res;
+    op->kry.pyth_thresh = 0.5;      // rtol is near the fp64 limit here: keep the Arnoldi norms exact
     if (bnorm > 0) {
         if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol, maxit, &res)) return 2;
     } else {

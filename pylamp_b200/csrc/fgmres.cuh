@@ -13,6 +13,7 @@
 // Basis vectors are allocated on first use.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -25,6 +26,7 @@ struct plb_fgmres_ws {
     double* d_scal = nullptr;  // >= m + 8 device scalars
     double* h_coef = nullptr;  // pinned host staging, >= m + 8 doubles
     double reorth_thresh = 1e-4;   // second Gram-Schmidt pass if |w_after|^2 < thresh * |w_before|^2
+    double pyth_thresh = 1e-2;     // norm by Pythagoras only if |w_after|^2 > thresh * |w_before|^2
 };
 
 struct plb_fgmres_result {
@@ -128,7 +130,7 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
             for (int j = 0; j <= k; j++) hcol[j] = ws->h_coef[j], sumh2 += hcol[j] * hcol[j];
             double w2_after = w2_before - sumh2;
             double hn;
-            if (w2_after > 1e-2 * w2_before) {
+            if (w2_after > ws->pyth_thresh * w2_before) {
                 hn = sqrt(w2_after);
                 if (plb_multi_axpy2(ctx, n, k + 1, S, Vp.data(), w, nullptr, nullptr, 1.0 / hn)) return 2;
             } else {
@@ -165,6 +167,7 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
             total++;
             res->iters = total;
             res->relres = fabs(g[k + 1]) / bnorm;
+            if (getenv("PLB_DEBUG_FGMRES")) fprintf(stderr, "  fgmres it %d est %.6e hn %.6e h0 %.6e\n", total, res->relres, hn, hcol[0]);
             if (fabs(g[k + 1]) <= rtol * bnorm || hn == 0) {
                 k++;
                 inner_conv = true;

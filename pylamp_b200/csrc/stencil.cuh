@@ -33,12 +33,17 @@ __device__ __forceinline__ bool is_vz_row(const LevelDev& L, int i, int j) {
 __device__ __forceinline__ bool is_vx_row(const LevelDev& L, int i, int j) {
     return i >= L.vx_i0 && i <= L.vx_i1 && j >= L.vx_j0 && j <= L.vx_j1;
 }
-// continuity rows: every real cell except the four corners and the pressure anchor (3,2)
+// continuity rows of the SOLVER: every real cell except the four corners.  The reference replaces
+// the continuity row of cell (3,2) by the pressure anchor P(3,2) = 0 (pylamp_stokes.py:525-551);
+// pinning one pressure leaves a near-null mode (eigenvalue ~ 1/N) that costs GMRES a long plateau
+// (iteration counts halve without it: oracle/mg_prototype.py).  The solver therefore keeps that
+// cell's continuity row -- it is a linear combination of the others for closed boundaries, the
+// reference's solution satisfies it -- iterates on the consistent singular system
+// (null space: constant pressure) and shifts the pressure to P(3,2) = 0 at the end.
 __device__ __forceinline__ bool is_p_row(const LevelDev& L, int i, int j) {
     if (i > L.nz - 2 || j > L.nxx - 2) return false;
     bool corner = (i == 0 || i == L.nz - 2) && (j == 0 || j == L.nxx - 2);
-    bool anchor = (i == 3 && j == 2);
-    return !corner && !anchor;
+    return !corner;
 }
 
 struct VzCoef {

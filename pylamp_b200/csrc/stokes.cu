@@ -76,7 +76,7 @@ struct plb_stokes {
     plb_fgmres_ws kry;
     double *xs = nullptr, *r3 = nullptr, *b3 = nullptr, *t3 = nullptr, *gz_d = nullptr, *gx_d = nullptr;
     // parameters
-    int hydrostatic = 1, warm_start = 0;
+    int hydrostatic = 1, warm_start = 0, debug_halo = 0;
     bool have_prev = false;
     double floor_est = 0;         // attainable scaled residual learnt from a stalled solve
     int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
@@ -717,15 +717,22 @@ k_sub_row_mean(LevelDev L, const double* __restrict__ m, double* __restrict__ bz
     if (is_vz_row(L, i, j)) bz[(long long)i * L.ld + j] -= m[i];
 }
 
+// value of the iterate's pressure in the anchor cell (3,2) (zero on ranks that do not own row 3)
+__global__ void k_get_anchor(LevelDev L, const double* __restrict__ p, double* out) {
+    *out = (3 >= L.i0 && 3 < L.i1) ? p[3LL * L.ld + 2] : 0.0;
+}
+
 // final solution: planar -> interleaved with the slaved corner pressures filled in
 __global__ void __launch_bounds__(BX* BY)
 k_solution_out(LevelDev L, const double* __restrict__ vz, const double* __restrict__ vx,
-               const double* __restrict__ p, const double* __restrict__ ph, double* __restrict__ x) {
+               const double* __restrict__ p, const double* __restrict__ ph, const double* __restrict__ panchor,
+               double* __restrict__ x) {
     const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
     if (i >= L.i1 || j >= L.nxx) return;
     const long long o = (long long)i * L.ld + j, t = (long long)i * L.nxx + j;
     double pv = p[o];
     if ((i == 0 || i == L.nz - 2) && (j == 0 || j == L.nxx - 2)) pv = (j == 0) ? p[o + 1] : p[o - 1];
+    pv -= *panchor;                        // P(3,2) = 0 like the reference's anchor row
     if (ph) pv += ph[i];
     if (i == L.nz - 1 || j == L.nxx - 1) pv = 0;
     x[3 * t] = vz[o], x[3 * t + 1] = vx[o], x[3 * t + 2] = pv;
@@ -1108,6 +1115,7 @@ int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     else if (!strcmp(name, "rtol_accept")) op->rtol_accept = value;
     else if (!strcmp(name, "hydrostatic")) op->hydrostatic = (int)value;
     else if (!strcmp(name, "warm_start")) op->warm_start = (int)value;
+    else if (!strcmp(name, "debug_halo")) op->debug_halo = (int)value;
     else if (!strcmp(name, "reorth_thresh")) op->kry_reorth = value;
     else PLB_FAIL(ctx, "plb_stokes_set_param: unknown parameter '%s'", name);
     return 0;
@@ -1184,16 +1192,30 @@ int plb_stokes_apply(plb_stokes* op, const double* d_x, double* d_y) {
     return 0;
 }
 
-// one multigrid V-cycle on the velocity block of level 0 (planar 2-plane vectors): test hook
+// one multigrid V-cycle on the velocity block of level 0: test hook.  b, x: two full-size planes
+// [vz | vx]; a slab rank reads its own rows of b and fills its own rows of x (others zero).
 int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2) {
     if (!op) return 1;
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_vcycle: coefficients not set");
-    if (op->lv[0].dist) PLB_FAIL(ctx, "plb_stokes_vcycle: not available on a slab-distributed operator");
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ensure_krylov(op)) return 2;
     if (!op->hierarchy && setup_hierarchy(op)) return 2;
-    PLB_CUDA(ctx, cudaMemsetAsync(d_x2, 0, sizeof(double) * 2 * op->lv[0].plane, ctx->stream));
-    return vcycle(op, 0, d_b2, d_x2);
+    Level& L = op->lv[0];
+    const size_t P = L.plane, rows = (size_t)(L.i1 - L.i0) * L.ld, off_l = (size_t)(L.i0 - L.lo) * L.ld,
+                 off_g = (size_t)L.i0 * L.ld;
+    double* z = op->t3;
+    PLB_CUDA(ctx, cudaMemsetAsync(z, 0, sizeof(double) * 2 * P, ctx->stream));
+    PLB_CUDA(ctx, cudaMemsetAsync(L.b, 0, sizeof(double) * 2 * P, ctx->stream));
+    for (int p = 0; p < 2; p++)
+        PLB_CUDA(ctx, cudaMemcpyAsync(L.b + p * P + off_l, d_b2 + p * L.full + off_g, sizeof(double) * rows,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    if (vcycle(op, 0, L.b, z)) return 2;
+    PLB_CUDA(ctx, cudaMemsetAsync(d_x2, 0, sizeof(double) * 2 * L.full, ctx->stream));
+    for (int p = 0; p < 2; p++)
+        PLB_CUDA(ctx, cudaMemcpyAsync(d_x2 + p * L.full + off_g, z + p * P + off_l, sizeof(double) * rows,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
 }
 
 int plb_stokes_last_stats(plb_stokes* op, double* h_out) {
@@ -1264,6 +1286,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     int vcycles = 0;
     auto apply = [&](const double* z, double* c) -> int {
         // z comes out of `precond` with valid halo rows
+        if (op->debug_halo && halo(op, L, const_cast<double*>(z), 3)) return 2;
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 64.0 * (double)P);
         k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr, nullptr, nullptr,
                                                        V3(c, 0), V3(c, 1), V3(c, 2));
@@ -1303,8 +1326,11 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     // full-size interleaved solution; a slab rank fills its own rows and leaves the rest zero (the
     // host side sums the pieces, e.g. with plb_allreduce)
     if (L.dist) PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * 3 * L.full, ctx->stream));
-    if (halo(op, L, x + 2 * P, 1)) return 2;         // corner pressures copy their x-neighbour only: no z halo needed, kept for symmetry
-    k_solution_out<<<g, blk, 0, ctx->stream>>>(D, C3(x, 0), C3(x, 1), C3(x, 2), ph, d_x);
+    double* panchor = op->d_scal + 930;
+    k_get_anchor<<<1, 1, 0, ctx->stream>>>(D, C3(x, 2), panchor);
+    PLB_LAUNCHED(ctx);
+    if (L.dist && plb_comm_allreduce(ctx, panchor, 1, PLB_OP_SUM)) return 2;
+    k_solution_out<<<g, blk, 0, ctx->stream>>>(D, C3(x, 0), C3(x, 1), C3(x, 2), ph, panchor, d_x);
     PLB_LAUNCHED(ctx);
     if (!res.converged && res.relres > op->rtol_accept)
         PLB_FAIL(ctx, "plb_stokes_solve: not converged after %d iterations (relres %.3e > rtol %.3e, "

@@ -113,6 +113,8 @@ class StokesOperator:
         bd = _dev(b2, self.ctx).reshape(-1)
         x = torch.empty_like(bd)
         self.ctx.check(self.ctx.lib.plb_stokes_vcycle(self.h, bd.data_ptr(), x.data_ptr()))
+        if self.ctx.comm_info()[1] > 1:
+            self.ctx.allreduce(x)
         return x
 
     def solve(self, rhs=None, rtol=DEFAULT_RTOL, maxit=DEFAULT_MAXIT, raise_on_fail=True):

@@ -9,6 +9,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]) + 1
 params = dict(kv.split('=') for kv in sys.argv[2:])
+rtol = float(params.pop('rtol', 1e-11))
 dev = torch.device('cuda', local)
 g = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
 gm = (g[1:] + g[:-1]) / 2
@@ -25,7 +26,7 @@ ctx = _lib.default_context(local)
 A1 = S.StokesOperator([n, n], grid, etas, etan, rho, [1, 1, 1, 1], ctx=ctx)
 for k, v in params.items(): A1.set_param(k, float(v))
 torch.cuda.synchronize(); t = time.time()
-x1 = A1.solve(None, rtol=1e-11, maxit=400)
+x1 = A1.solve(None, rtol=rtol, maxit=400)
 torch.cuda.synchronize(); t1 = time.time() - t
 it1 = A1.iterations
 A1.close()
@@ -34,8 +35,9 @@ A = S.StokesOperator([n, n], grid, etas, etan, rho, [1, 1, 1, 1], ctx=ctx)
 for k, v in params.items(): A.set_param(k, float(v))
 for rep in range(2):
     dist.barrier(); torch.cuda.synchronize(); t = time.time()
-    x = A.solve(None, rtol=1e-11, maxit=400)
+    x = A.solve(None, rtol=rtol, maxit=400)
     torch.cuda.synchronize(); tn = time.time() - t
+    if rank == 0: print('   slab rep', rep, A.stats, '%.3fs' % tn, flush=True)
 err = [float(torch.linalg.norm(x[k::3] - x1[k::3]) / torch.linalg.norm(x1[k::3])) for k in range(3)]
 print("rank %d/%d n=%d: single-GPU %d its %.3fs | slab %d its %.3fs relres %.2e | rel diff vz,vx,P %s" %
       (rank, world, n, it1, t1, A.iterations, tn, A.relres, ["%.1e" % e for e in err]), flush=True)
