@@ -4,7 +4,7 @@
 //
 // Reference behaviour restated (never copied): pylamp_trac.py:30-158 (grid2trac), :161-318
 // (trac2grid), :321-388 (RK); pylamp2.py:291-303, :471-476, :558-572, :588-593.
-#include "common.cuh"
+#include "comm.cuh"
 
 namespace {
 
@@ -22,6 +22,11 @@ __device__ __forceinline__ long long cell_of(double x, double lmin, double len, 
 __global__ void k_minmax_init(double* out) {
     out[0] = out[2] = 1e300;
     out[1] = out[3] = -1e300;
+}
+
+__global__ void k_minmax_flip(double* out) {
+    out[0] = -out[0];
+    out[2] = -out[2];
 }
 
 __global__ void __launch_bounds__(256) k_marker_minmax(long long M, const double2* __restrict__ x,
@@ -414,14 +419,24 @@ void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& 
 extern "C" {
 
 int plb_marker_minmax(plb_ctx* ctx, long long M, const double* d_tr_x, double* h_out) {
-    if (!ctx || M <= 0) return 1;
+    if (!ctx || M < 0) return 1;
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (plb_ws_reserve(ctx, 64)) return 2;
     double* d = (double*)ctx->ws;
     k_minmax_init<<<1, 1, 0, ctx->stream>>>(d);
     PLB_LAUNCHED(ctx);
-    k_marker_minmax<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d);
-    PLB_LAUNCHED(ctx);
+    if (M > 0) {
+        k_marker_minmax<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d);
+        PLB_LAUNCHED(ctx);
+    }
+    if (plb_comm_size(ctx) > 1) {
+        // global extent over all ranks' markers: one MAX all-reduce of (-zmin, zmax, -xmin, xmax)
+        k_minmax_flip<<<1, 1, 0, ctx->stream>>>(d);
+        PLB_LAUNCHED(ctx);
+        if (plb_comm_allreduce(ctx, d, 4, PLB_OP_MAX)) return 2;
+        k_minmax_flip<<<1, 1, 0, ctx->stream>>>(d);
+        PLB_LAUNCHED(ctx);
+    }
     PLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, d, 4 * sizeof(double), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -477,6 +492,9 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
         }
         PLB_LAUNCHED(ctx);
     }
+    // marker-parallel ranks (each holds a share of the markers, the grids are replicated): sum the
+    // raw node sums over the ranks before dividing
+    if (plb_comm_size(ctx) > 1 && plb_comm_allreduce(ctx, w, nplanes * plane, PLB_OP_SUM)) return 2;
     k_t2g_finalise<<<plb_grid_for(ctx, (long long)nz * nxx, 256, 8), 256, 0, ctx->stream>>>(
         a, crop_z0, crop_x0, nz, nxx, ld);
     PLB_LAUNCHED(ctx);

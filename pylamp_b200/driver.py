@@ -1,6 +1,10 @@
 """Device-resident thin driver: one pass of the reference's loop body (pylamp2.py:273-594) built
 from the same module-level functions pylamp2.py calls, with all state kept in HBM.
 
+Multi-GPU (one process per GPU, `ctx.init_comm()`): the grids are replicated, every rank owns a
+share of the markers (trac2grid sums the node sums with an NCCL all-reduce inside the library) and
+the Stokes solve is z-slab distributed (halo rows + all-reduced dot products); see DESIGN.md §7.
+
 The unmodified reference driver can also be run against the drop-in modules, but
 its inline NumPy steps then bounce every marker through host memory each call; this driver keeps
 markers (SoA columns) and grid fields on the GPU and is what `bench.py` times.
@@ -230,5 +234,9 @@ def timestep(s, o, want_kelem=True, phases=False):
         raise NotImplementedError("marker deletion (fence disabled / FLOWTHRU): SURVEY.md §8f-1")
     markers.fence(s.tr_x, s.L, EPS)
     s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=want_kelem)
+    if ctx.comm_info()[1] > 1:
+        # marker-parallel ranks: per-cell counts of the whole cloud
+        import torch.distributed as dist
+        dist.all_reduce(s.count)
     ph.mark("fence_count")
     return s

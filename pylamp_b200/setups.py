@@ -144,23 +144,28 @@ def solcx_fields(n, eta_right=1e6):
     return nx, L, grid, gridmp, etas, etan, rho
 
 
-def convection_device(ncell=4096, per_side=4, seed=11, Ra=1e6, Lbox=1e6, device="cuda"):
+def convection_device(ncell=4096, per_side=4, seed=11, Ra=1e6, Lbox=1e6, device="cuda", rank=0, world=1):
     """`convection` generated directly in HBM with torch (the 4096^2 case has 2.7e8 markers: ~32 GB
     of host arrays otherwise).  Same lattice/ordering/physics; the jitter comes from torch's RNG,
     so positions differ from the NumPy generator's (benchmarks only -- parity tests use `convection`).
+    With world > 1 each rank generates the markers of its share of the cell rows (marker-parallel
+    ranks: the cell-major order makes every share a contiguous z-slab of the cloud).
     Returns (nx, L, tr_x (M,2) cuda, cols list of 13 (M,) cuda tensors, opts)."""
     import torch
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
+    g.manual_seed(seed + 1000 * rank)
     nx, L = [ncell + 1, ncell + 1], [Lbox, Lbox]
     ns = ncell * per_side
     dev = torch.device(device)
+    r0, r1 = (rank * ncell) // world, ((rank + 1) * ncell) // world
+    nrow = r1 - r0
     ci = torch.arange(ncell, device=dev, dtype=torch.float64)
+    cz = torch.arange(r0, r1, device=dev, dtype=torch.float64)
     si = torch.arange(per_side, device=dev, dtype=torch.float64)
     # cell-major ordering (cell i, cell j, sub i, sub j)
-    z = ((ci.view(-1, 1, 1, 1) * per_side + si.view(1, 1, -1, 1) + 0.5) / ns).expand(ncell, ncell, per_side, per_side)
-    x = ((ci.view(1, -1, 1, 1) * per_side + si.view(1, 1, 1, -1) + 0.5) / ns).expand(ncell, ncell, per_side, per_side)
-    M = ncell * ncell * per_side * per_side
+    z = ((cz.view(-1, 1, 1, 1) * per_side + si.view(1, 1, -1, 1) + 0.5) / ns).expand(nrow, ncell, per_side, per_side)
+    x = ((ci.view(1, -1, 1, 1) * per_side + si.view(1, 1, 1, -1) + 0.5) / ns).expand(nrow, ncell, per_side, per_side)
+    M = nrow * ncell * per_side * per_side
     tr_x = torch.empty((M, 2), dtype=torch.float64, device=dev)
     tr_x[:, 0] = z.reshape(-1)
     tr_x[:, 1] = x.reshape(-1)
