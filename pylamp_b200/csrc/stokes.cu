@@ -77,6 +77,7 @@ struct plb_stokes {
     double *xs = nullptr, *r3 = nullptr, *b3 = nullptr, *t3 = nullptr, *gz_d = nullptr, *gx_d = nullptr;
     // parameters
     int hydrostatic = 1, warm_start = 0, debug_halo = 0;
+    int lmax_every = 1, lmax_age = -1;   // eigenvalue estimates: recompute every n-th set_coeffs
     bool have_prev = false;
     double floor_est = 0;         // attainable scaled residual learnt from a stalled solve
     int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
@@ -974,9 +975,14 @@ int setup_hierarchy(plb_stokes* op) {
             F.nz, F.nxx, F.ld, F.etas, F.etan, Cc.nz, Cc.nxx, Cc.ld, Cc.etas_own, Cc.etan_own, op->coarsen_wide);
         PLB_LAUNCHED(ctx);
     }
-    // largest eigenvalue of D^-1 K per level by power iteration
+    // largest eigenvalue of D^-1 K per level by power iteration.  The estimate (with its 10 % safety
+    // margin) is reused for `lmax_every` consecutive coefficient updates: the viscosity field of a
+    // time-stepping run changes by a fraction of a cell per step and the Chebyshev interval only
+    // needs an upper bound.
     const int npow = 12;
-    for (int l = 0; l < nlev; l++) {
+    const bool fresh = op->lmax_age < 0 || op->lmax_age >= op->lmax_every;
+    op->lmax_age = fresh ? 1 : op->lmax_age + 1;
+    for (int l = 0; l < nlev && fresh; l++) {
         Level& L = op->lv[l];
         const LevelDev D = L.dev();
         const size_t P = L.plane;
@@ -1116,6 +1122,7 @@ int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     else if (!strcmp(name, "hydrostatic")) op->hydrostatic = (int)value;
     else if (!strcmp(name, "warm_start")) op->warm_start = (int)value;
     else if (!strcmp(name, "debug_halo")) op->debug_halo = (int)value;
+    else if (!strcmp(name, "lmax_every")) op->lmax_every = (int)value;
     else if (!strcmp(name, "reorth_thresh")) op->kry_reorth = value;
     else PLB_FAIL(ctx, "plb_stokes_set_param: unknown parameter '%s'", name);
     return 0;
