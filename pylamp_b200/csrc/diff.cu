@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "blas1.cuh"
+#include "comm.cuh"
 #include "fgmres.cuh"
 
 namespace {
@@ -22,6 +23,7 @@ inline dim3 block2d() { return dim3(BX, BY); }
 
 struct DiffDev {
     int nz, nxx, ld;
+    int i0, i1;                   // rows handled by this rank (z-slab); single GPU: [0, nz)
     const double *idz, *idx;      // 1/(g[k+1]-g[k])
     const double *idzm, *idxm;    // 1/(gmp[k]-gmp[k-1]), k >= 1
     const double *T, *kz, *kx, *cp, *rho, *H;
@@ -92,8 +94,8 @@ __device__ __forceinline__ double row_apply(const DiffDev& D, const Row& r, cons
 template <int MODE>
 __global__ void __launch_bounds__(BX* BY)
 k_diff(DiffDev D, const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y) {
-    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
-    if (i >= D.nz || j >= D.nxx) return;
+    const int j = blockIdx.x * BX + threadIdx.x, i = D.i0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= D.i1 || j >= D.nxx) return;
     const long long o = (long long)i * D.ld + j;
     Row r = diff_row(D, i, j);
     if (MODE == 1) {
@@ -117,7 +119,12 @@ struct plb_diff {
     plb_reduce_ws rws{};
     double* d_scal = nullptr;
     plb_fgmres_ws kry;
-    double* xs = nullptr;
+    double *xs = nullptr, *xl = nullptr;   // local work vectors (slab rows + halos)
+    // z-slab ownership when the context has a communicator: rows [i0, i1), stored rows [lo, hi]
+    int i0 = 0, i1 = 0, lo = 0, hi = 0;
+    bool dist = false;
+    size_t plane = 0;                      // local plane size
+    long long shift = 0;
     int m = 40;
     int last_iters = 0;
     double last_relres = 0;
@@ -158,9 +165,20 @@ int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_
         return 2;
     }
     PLB_CUDA(ctx, cudaMalloc(&op->d_scal, sizeof(double) * 1024));
-    PLB_CUDA(ctx, cudaMalloc(&op->xs, sizeof(double) * (size_t)nz * ld));
+    const int R = plb_comm_size(ctx), rank = plb_comm_rank(ctx);
+    op->dist = R > 1 && nz >= 4 * R;
+    if (op->dist) {
+        op->i0 = (int)((long long)rank * nz / R), op->i1 = (int)((long long)(rank + 1) * nz / R);
+        op->lo = rank > 0 ? op->i0 - 1 : 0, op->hi = rank < R - 1 ? op->i1 : nz - 1;
+    } else {
+        op->i0 = 0, op->i1 = nz, op->lo = 0, op->hi = nz - 1;
+    }
+    op->plane = (size_t)(op->hi - op->lo + 1) * ld;
+    op->shift = (long long)op->lo * ld;
+    PLB_CUDA(ctx, cudaMalloc(&op->xs, sizeof(double) * op->plane));
+    PLB_CUDA(ctx, cudaMalloc(&op->xl, sizeof(double) * op->plane));
     DiffDev& D = op->dev;
-    D.nz = nz, D.nxx = nxx, D.ld = ld;
+    D.nz = nz, D.nxx = nxx, D.ld = ld, D.i0 = op->i0, D.i1 = op->i1;
     D.idz = op->idz, D.idx = op->idx, D.idzm = op->idzm, D.idxm = op->idxm;
     for (int w = 0; w < 4; w++) D.bc[w] = h_bc[w], D.bcval[w] = h_bcvalue[w];
     *out = op;
@@ -171,7 +189,7 @@ void plb_diff_destroy(plb_diff* op) {
     if (!op) return;
     cudaSetDevice(op->ctx->device);
     cudaStreamSynchronize(op->ctx->stream);
-    double* ptrs[] = {op->idz, op->idx, op->idzm, op->idxm, op->d_scal, op->xs};
+    double* ptrs[] = {op->idz, op->idx, op->idzm, op->idxm, op->d_scal, op->xs, op->xl};
     for (double* p : ptrs) if (p) cudaFree(p);
     plb_fgmres_free(&op->kry);
     plb_reduce_ws_free(&op->rws);
@@ -192,7 +210,9 @@ int plb_diff_rhs(plb_diff* op, double* d_rhs) {
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_diff_rhs: coefficients not set");
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
-    k_diff<1><<<grid2d(op->nz, op->nxx), block2d(), 0, ctx->stream>>>(op->dev, nullptr, nullptr, d_rhs);
+    DiffDev D = op->dev;
+    D.i0 = 0, D.i1 = op->nz;                 // whole grid (fields are replicated on every rank)
+    k_diff<1><<<grid2d(op->nz, op->nxx), block2d(), 0, ctx->stream>>>(D, nullptr, nullptr, d_rhs);
     PLB_LAUNCHED(ctx);
     return 0;
 }
@@ -202,7 +222,9 @@ int plb_diff_apply(plb_diff* op, const double* d_x, double* d_y) {
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_diff_apply: coefficients not set");
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
-    k_diff<0><<<grid2d(op->nz, op->nxx), block2d(), 0, ctx->stream>>>(op->dev, d_x, nullptr, d_y);
+    DiffDev D = op->dev;
+    D.i0 = 0, D.i1 = op->nz;
+    k_diff<0><<<grid2d(op->nz, op->nxx), block2d(), 0, ctx->stream>>>(D, d_x, nullptr, d_y);
     PLB_LAUNCHED(ctx);
     return 0;
 }
@@ -213,27 +235,39 @@ int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, do
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_diff_solve: coefficients not set");
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const long long n = (long long)op->nz * op->ld;
+    const long long n = (long long)op->plane;            // local vector length (slab rows + halos)
     if (op->kry.m != op->m && plb_fgmres_alloc(ctx, &op->kry, op->m, n, op->d_scal)) return 2;
     const DiffDev D = op->dev;
-    const dim3 g = grid2d(op->nz, op->nxx), blk = block2d();
-    double* x = d_x;
-    // bnorm = || D^-1 b ||: residual of x = 0
-    PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
-    auto residual = [&](double* out) -> int {
-        k_diff<2><<<g, blk, 0, ctx->stream>>>(D, x, d_rhs, out);
+    const dim3 g = grid2d(op->i1 - op->i0, op->nxx), blk = block2d();
+    const long long sh = op->shift;
+    const size_t own_off = (size_t)(op->i0 - op->lo) * op->ld, own_len = (size_t)(op->i1 - op->i0) * op->ld;
+    if (op->dist) plb_reduce_shape(&op->rws, 1, n, (long long)own_off, (long long)own_len, true);
+    else plb_reduce_shape(&op->rws, 0, 0, 0, 0, false);
+    auto halo = [&](double* v) -> int {
+        if (!op->dist) return 0;
+        return plb_comm_halo_exchange(ctx, v, 1, op->plane, op->ld, op->nxx, op->lo, op->i0, op->i1);
+    };
+    double* x = op->xl;
+    // the caller's right-hand side is a full-size vector: global indexing, no shift
+    auto resid_of = [&](double* xx, double* out) -> int {
+        if (halo(xx)) return 2;
+        k_diff<2><<<g, blk, 0, ctx->stream>>>(D, xx - sh, d_rhs, out - sh);
         PLB_LAUNCHED(ctx);
         return 0;
     };
-    if (residual(op->xs)) return 2;
+    auto residual = [&](double* out) -> int { return resid_of(x, out); };
+    // bnorm = || D^-1 b ||: residual of x = 0
+    PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+    if (resid_of(x, op->xs)) return 2;
     double bn2;
     if (plb_dot(ctx, &op->rws, n, op->xs, op->xs, op->d_scal + 900)) return 2;
     if (plb_read_scalars(ctx, op->d_scal + 900, 1, &bn2)) return 2;
     const double bnorm = sqrt(bn2);
-    // initial guess: the current temperature field (the rhs is -T_old - dt*H/(rho*cp))
-    PLB_CUDA(ctx, cudaMemcpyAsync(x, D.T, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // initial guess: the current temperature field (the rhs is -T_old - dt*H/(rho*cp)); local rows
+    PLB_CUDA(ctx, cudaMemcpyAsync(x, D.T + sh, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     auto apply = [&](const double* z, double* w) -> int {
-        k_diff<3><<<g, blk, 0, ctx->stream>>>(D, z, nullptr, w);
+        if (halo(const_cast<double*>(z))) return 2;
+        k_diff<3><<<g, blk, 0, ctx->stream>>>(D, z - sh, nullptr, w - sh);
         PLB_LAUNCHED(ctx);
         return 0;
     };
@@ -249,6 +283,10 @@ int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, do
     op->last_iters = res.iters, op->last_relres = res.relres;
     if (h_iters) *h_iters = res.iters;
     if (h_relres) *h_relres = res.relres;
+    // full-size result: a slab rank fills its own rows, the rest stays zero (summed by the host side)
+    if (op->dist) PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * (size_t)op->nz * op->ld, ctx->stream));
+    PLB_CUDA(ctx, cudaMemcpyAsync(d_x + (size_t)op->i0 * op->ld, x + own_off, sizeof(double) * own_len,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
     if (!res.converged && res.relres > 1e3 * rtol)
         PLB_FAIL(ctx, "plb_diff_solve: not converged after %d iterations (relres %.3e > rtol %.3e)", res.iters,
                  res.relres, rtol);

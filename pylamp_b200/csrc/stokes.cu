@@ -4,6 +4,7 @@
 // system with a block-triangular preconditioner (viscosity-scaled pressure mass + one geometric
 // multigrid V-cycle with Chebyshev-Jacobi smoothing on the velocity block).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -806,6 +807,8 @@ int build_levels(plb_stokes* op, const double* h_gz, const double* h_gx) {
         }
     }
     const int nlev = (int)GZ.size();
+    int min_rows = 64;
+    if (const char* e = getenv("PLB_DIST_MIN_ROWS")) min_rows = atoi(e);
     for (int l = 0; l < nlev; l++) {
         Level L;
         const int nz = (int)GZ[l].size(), nxx = (int)GX[l].size();
@@ -815,7 +818,10 @@ int build_levels(plb_stokes* op, const double* h_gz, const double* h_gx) {
         // level is always replicated (dense solve)
         const int cells = nz - 1;
         const bool prev_dist = l == 0 ? true : op->lv[l - 1].dist;
-        L.dist = R > 1 && prev_dist && l < nlev - 1 && cells % R == 0 && (cells / R) >= 4 && (cells / R) % 2 == 0;
+        // ... and, below `min_rows` rows per rank, a level costs less replicated (every rank smooths the
+        // whole small grid) than the latency of its halo exchanges
+        L.dist = R > 1 && prev_dist && l < nlev - 1 && cells % R == 0 && (cells / R) >= 4 && (cells / R) % 2 == 0 &&
+                 (l == 0 || cells / R >= min_rows);
         if (R > 1 && l == 0 && !L.dist)
             PLB_FAIL(ctx, "plb_stokes_create: %d cell rows cannot be split into %d even slabs of >= 4 rows", cells, R);
         if (L.dist) {

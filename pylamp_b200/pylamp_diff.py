@@ -95,6 +95,8 @@ class DiffusionOperator:
                                          int(maxit), x.data_ptr(), C.byref(it), C.byref(rr))
         self.iterations, self.relres = it.value, rr.value
         self.ctx.check(rc)
+        if self.ctx.comm_info()[1] > 1:
+            self.ctx.allreduce(x)       # every slab rank filled its own rows
         return x.cpu().numpy() if host else x
 
     def close(self):
