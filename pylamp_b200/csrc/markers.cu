@@ -84,53 +84,125 @@ __device__ __forceinline__ double seg_reduce(double v, int lane, int run_end) {
     return v;
 }
 
+// per-marker contribution: cell, the four corner weights and the (transformed) field values
+template <int K>
+struct T2GMarker {
+    long long cell;        // ie * nxe + je, or -1 if outside (cannot happen after the ghost extension)
+    double w[4];
+    double v[K];
+};
+
+template <int K>
+__device__ __forceinline__ T2GMarker<K> t2g_load(const T2GArgs& a, const double2* __restrict__ trx, long long m) {
+    T2GMarker<K> r;
+    const double2 p = trx[m];
+    const long long ie = cell_of(p.x, a.z0, a.zlen, a.nze);
+    const long long je = cell_of(p.y, a.x0, a.xlen, a.nxe);
+    r.cell = -1;
+#pragma unroll
+    for (int c = 0; c < 4; c++) r.w[c] = 0;
+#pragma unroll
+    for (int f = 0; f < K; f++) r.v[f] = 0;
+    if (ie < 0 || ie > a.nze - 2 || je < 0 || je > a.nxe - 2) return r;
+    const double gz0 = a.axz[ie], gz1 = a.axz[ie + 1], gx0 = a.axx[je], gx1 = a.axx[je + 1];
+    const double az = (p.x - gz0) / (gz1 - gz0);      // pylamp_trac.py:247
+    const double ax = (p.y - gx0) / (gx1 - gx0);
+    const double bz = 1 - az, bx = 1 - ax;            // :249
+    r.w[0] = (1 - ax) * (1 - az);                     // node (i  , j  )   :252
+    r.w[1] = (1 - ax) * (1 - bz);                     // node (i+1, j  )
+    r.w[2] = (1 - bx) * (1 - az);                     // node (i  , j+1)
+    r.w[3] = (1 - bx) * (1 - bz);                     // node (i+1, j+1)
+    r.cell = ie * a.nxe + je;
+#pragma unroll
+    for (int f = 0; f < K; f++) {
+        const double val = a.f[f][m];
+        r.v[f] = (a.scheme[f] & PLB_AVG_ARITHMETIC) ? val : log(val);
+    }
+    return r;
+}
+
+// add an aggregate (sums over some markers of ONE cell) straight to the planes
+template <int K>
+__device__ __forceinline__ void t2g_flush(const T2GArgs& a, long long cell, const double (&w)[4], double cntv,
+                                          const double (&vw)[K][4]) {
+    const long long idx[4] = {cell, cell + a.nxe, cell + 1, cell + a.nxe + 1};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (a.wsum) atomicAdd(a.wsum + idx[c], w[c]);
+        if (a.cnt) atomicAdd(a.cnt + idx[c], cntv);
+    }
+#pragma unroll
+    for (int f = 0; f < K; f++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            atomicAdd(a.acc[f] + idx[c], (a.scheme[f] & PLB_AVG_WEIGHTED) ? vw[f][c] : vw[f][0]);
+}
+
+// Each thread takes T2G_U consecutive markers and sums those of one cell in registers (while the
+// cloud is cell-ordered that is all of them); the per-thread sums then go through the warp-level
+// segmented reduction, so a run of markers of one cell costs one atomic per (node, quantity) and
+// the shuffle count per marker drops by T2G_U.  When a thread's markers straddle cells, the sums
+// of the earlier cells are added with plain atomics.  Correct for any marker order.
+constexpr int T2G_U = 4;
+
 template <int K>
 __global__ void __launch_bounds__(256)
 k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const long long nchunk = (M + T2G_U - 1) / T2G_U;             // one chunk per thread
     long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; base < M; base += stride) {
-        long long m = base + lane;
-        bool valid = m < M;
-        long long cell = -1 - lane;          // invalid lanes form runs of their own
-        double w[4] = {0, 0, 0, 0};
-        double v[K];
+    for (; base < nchunk; base += stride) {
+        const long long ch = base + lane;
+        long long cell = -1 - lane;          // lanes without a valid aggregate form runs of their own
+        double w[4] = {0, 0, 0, 0}, cntv = 0;
+        double vw[K][4];                     // weighted: sum v*w[c]; unweighted: sum v in [f][0]
 #pragma unroll
-        for (int f = 0; f < K; f++) v[f] = 0;
-        long long ie = 0, je = 0;
-        if (valid) {
-            double2 p = trx[m];
-            ie = cell_of(p.x, a.z0, a.zlen, a.nze);
-            je = cell_of(p.y, a.x0, a.xlen, a.nxe);
-            if (ie < 0 || ie > a.nze - 2 || je < 0 || je > a.nxe - 2) {
-                valid = false;               // cannot happen after the ghost extension
-            } else {
-                double gz0 = a.axz[ie], gz1 = a.axz[ie + 1], gx0 = a.axx[je], gx1 = a.axx[je + 1];
-                double az = (p.x - gz0) / (gz1 - gz0);      // pylamp_trac.py:247
-                double ax = (p.y - gx0) / (gx1 - gx0);
-                double bz = 1 - az, bx = 1 - ax;            // :249
-                w[0] = (1 - ax) * (1 - az);                 // node (i  , j  )   :252
-                w[1] = (1 - ax) * (1 - bz);                 // node (i+1, j  )
-                w[2] = (1 - bx) * (1 - az);                 // node (i  , j+1)
-                w[3] = (1 - bx) * (1 - bz);                 // node (i+1, j+1)
-                cell = ie * a.nxe + je;
+        for (int f = 0; f < K; f++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) vw[f][c] = 0;
+        bool valid = false;
+        if (ch < nchunk) {
+            const long long m0 = ch * T2G_U;
+#pragma unroll
+            for (int u = 0; u < T2G_U; u++) {
+                if (m0 + u >= M) break;
+                const T2GMarker<K> r = t2g_load<K>(a, trx, m0 + u);
+                if (r.cell < 0) continue;
+                if (valid && r.cell != cell) {           // cell change inside the chunk: flush, restart
+                    t2g_flush<K>(a, cell, w, cntv, vw);
+                    cntv = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) w[c] = 0;
+#pragma unroll
+                    for (int f = 0; f < K; f++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) vw[f][c] = 0;
+                }
+                valid = true;
+                cell = r.cell;
+                cntv += 1.0;
+#pragma unroll
+                for (int c = 0; c < 4; c++) w[c] += r.w[c];
 #pragma unroll
                 for (int f = 0; f < K; f++) {
-                    double val = a.f[f][m];
-                    v[f] = (a.scheme[f] & PLB_AVG_ARITHMETIC) ? val : log(val);
+                    if (a.scheme[f] & PLB_AVG_WEIGHTED) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) vw[f][c] += r.v[f] * r.w[c];
+                    } else {
+                        vw[f][0] += r.v[f];
+                    }
                 }
             }
         }
-        long long prev = __shfl_up_sync(full, cell, 1);
-        bool head = (lane == 0) || (prev != cell);
-        unsigned heads = __ballot_sync(full, head);
-        unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
-        int run_end = after ? lane + __ffs(after) - 1 : 31;
-        bool emit = head && valid;
-        long long n00 = ie * a.nxe + je;
-        long long idx[4] = {n00, n00 + a.nxe, n00 + 1, n00 + a.nxe + 1};
+        const long long prev = __shfl_up_sync(full, cell, 1);
+        const bool head = (lane == 0) || (prev != cell);
+        const unsigned heads = __ballot_sync(full, head);
+        const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
+        const int run_end = after ? lane + __ffs(after) - 1 : 31;
+        const bool emit = head && valid;
+        const long long idx[4] = {cell, cell + a.nxe, cell + 1, cell + a.nxe + 1};
         if (a.wsum) {
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -139,7 +211,7 @@ k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
             }
         }
         if (a.cnt) {
-            double s = seg_reduce(valid ? 1.0 : 0.0, lane, run_end);
+            double s = seg_reduce(cntv, lane, run_end);
             if (emit) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) atomicAdd(a.cnt + idx[c], s);
@@ -150,11 +222,11 @@ k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
             if (a.scheme[f] & PLB_AVG_WEIGHTED) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    double s = seg_reduce(v[f] * w[c], lane, run_end);
+                    double s = seg_reduce(vw[f][c], lane, run_end);
                     if (emit) atomicAdd(a.acc[f] + idx[c], s);
                 }
             } else {
-                double s = seg_reduce(v[f], lane, run_end);
+                double s = seg_reduce(vw[f][0], lane, run_end);
                 if (emit) {
 #pragma unroll
                     for (int c = 0; c < 4; c++) atomicAdd(a.acc[f] + idx[c], s);
@@ -410,7 +482,7 @@ k_sub(long long M, const double* __restrict__ a, const double* __restrict__ b,
 template <int K>
 void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& a) {
     int threads = 256;
-    int grid = plb_grid_for(ctx, M, threads, 8);
+    int grid = plb_grid_for(ctx, (M + T2G_U - 1) / T2G_U, threads, 8);
     k_t2g_scatter<K><<<grid, threads, 0, ctx->stream>>>(M, x, a);
 }
 
