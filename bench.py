@@ -146,7 +146,7 @@ def run_b200(args):
                                                        rank=rank, world=world)
     s = driver.State(nx, L, tr_x, cols, device=local)
     o = driver.Options(**opts)
-    o.stokes_params = {"warm_start": 1, "gcr_m": args.gmres_m, "lmax_every": 8}
+    o.stokes_params = {"warm_start": 2, "gcr_m": args.gmres_m, "lmax_every": 8}
     M = s.ntrac
     if world > 1:
         tm = torch.tensor([M], dtype=torch.int64, device="cuda")
@@ -231,7 +231,7 @@ def run_b200(args):
                        "%d GPUs: z-slab Stokes solve (NCCL halo send/recv + all-reduced dots), marker-parallel "
                        "MIC with all-reduced node sums, replicated grids and heat solve" % world,
                        "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
-                       "stokes_rtol": o.stokes_rtol, "stokes_solver": "FGMRES(%d) + GMG V(3,3) Chebyshev-Jacobi, warm start, eigenvalue estimates every 8 steps" % args.gmres_m},
+                       "stokes_rtol": o.stokes_rtol, "stokes_solver": "FGMRES(%d) + GMG V(3,3) Chebyshev-Jacobi, warm start by linear extrapolation of the last two solutions, eigenvalue estimates every 8 steps" % args.gmres_m},
             "stokes_dof_per_s": 3.0 * N / (ms_step * 1e-3),
             "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "phases_ms_per_step": phase_ms, "kernel_breakdown": breakdown}

@@ -171,7 +171,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
  * "cheb_ratio" (8), "dense_max" (largest coarse level solved by a dense inverse, 640),
  * "nu_coarse" (60), "rtol_accept" (1e-8: a solve stalled at its fp64 floor is accepted below
  * this), "hydrostatic" (1: solve for the deviation from the lithostatic pressure), "warm_start"
- * (0/1: start from the previous solve's iterate), "reorth_thresh" (1e-4), "lmax_every" (1: the
+ * (0: zero start, 1: start from the previous solve's iterate, 2: linear extrapolation of the last two), "reorth_thresh" (1e-4), "lmax_every" (1: the
  * smoother's eigenvalue estimates are recomputed on every n-th coefficient update) */
 int plb_stokes_set_param(plb_stokes* op, const char* name, double value);
 /* test hook: one multigrid V-cycle x = V(b) on the velocity block; b, x are two planes

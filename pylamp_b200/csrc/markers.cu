@@ -362,14 +362,32 @@ k_grid2trac(long long M, const double2* __restrict__ trx, int method, G2TGrid g,
 // ---------------------------------------------------------------------------------------------
 // RK4 with the reference's (1/6)(k1+k2+k3+k4) update, pylamp_trac.py:347-388
 // ---------------------------------------------------------------------------------------------
+// RK stage velocity: same arithmetic as locate() + veldiv() with the divisions hoisted -- the two
+// reciprocal cell sizes serve the local coordinates and both Meyer-Jenny coefficients, and the cell
+// lookup multiplies by (n-1)/len instead of dividing (a marker sitting exactly on a cell face may
+// then be assigned to the neighbouring cell, where the continuous interpolant has the same value).
+// fp64 division is what bounds this kernel: 2 per stage instead of 6.
 __device__ __forceinline__ void vel_at(const double* __restrict__ fz, const double* __restrict__ fx,
-                                       const G2TGrid& g, double z, double x, double& vz, double& vx) {
-    Cell c = locate(g, z, x);
-    if (c.bad) {
+                                       const G2TGrid& g, double sz, double sx, double z, double x,
+                                       double& vz, double& vx) {
+    long long ie = (long long)floor((z - g.z0) * sz), je = (long long)floor((x - g.x0) * sx);
+    if (ie < 0 || ie > g.nz - 2 || je < 0 || je > g.nxx - 2) {
         vz = 0, vx = 0;                                    // defval=0, :361
         return;
     }
-    veldiv(fz, fx, g, c, vz, vx);
+    const double gz0 = g.gz[ie], gz1 = g.gz[ie + 1], gx0 = g.gx[je], gx1 = g.gx[je + 1];
+    const double hz = gz1 - gz0, hx = gx1 - gx0;
+    const double rz = 1.0 / hz, rx = 1.0 / hx;
+    const double dzn = (z - gz0) * rz, dxn = (x - gx0) * rx;
+    const double* pz = fz + ie * g.ld + je;
+    const double* px = fx + ie * g.ld + je;
+    const double z00 = __ldg(pz), z01 = __ldg(pz + 1), z10 = __ldg(pz + g.ld), z11 = __ldg(pz + g.ld + 1);
+    const double x00 = __ldg(px), x01 = __ldg(px + 1), x10 = __ldg(px + g.ld), x11 = __ldg(px + g.ld + 1);
+    const double c10 = (0.5 * hx * rz) * (z00 - z10 + z11 - z01);
+    const double c20 = (0.5 * hz * rx) * (x00 - x01 + x11 - x10);
+    const double w00 = (1 - dxn) * (1 - dzn), w01 = dxn * (1 - dzn), w10 = (1 - dxn) * dzn, w11 = dxn * dzn;
+    vx = w00 * x00 + w01 * x01 + w10 * x10 + w11 * x11 + dxn * (1 - dxn) * c10;
+    vz = w00 * z00 + w01 * z01 + w10 * z10 + w11 * z11 + dzn * (1 - dzn) * c20;
 }
 
 __global__ void __launch_bounds__(256)
@@ -378,22 +396,24 @@ k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ f
       double2* __restrict__ vout) {
     const double hdt = 0.5 * dt;
     const double sixth_dt = (1.0 / 6.0) * dt;
+    const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
+    const double rdt = 1.0 / dt;
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
          m += (long long)gridDim.x * blockDim.x) {
         double2 p = trx[m];
         double k1z, k1x, k2z, k2x, k3z, k3x, k4z, k4x;
-        vel_at(fz, fx, g, p.x, p.y, k1z, k1x);
-        vel_at(fz, fx, g, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
-        vel_at(fz, fx, g, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
-        vel_at(fz, fx, g, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
+        vel_at(fz, fx, g, sz, sx, p.x, p.y, k1z, k1x);
+        vel_at(fz, fx, g, sz, sx, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
+        vel_at(fz, fx, g, sz, sx, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
+        vel_at(fz, fx, g, sz, sx, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
         double2 q;
         q.x = p.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // :385 (unweighted sum)
         q.y = p.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
         xout[m] = q;
         if (vout) {
             double2 v;
-            v.x = (q.x - p.x) / dt;                           // :386
-            v.y = (q.y - p.y) / dt;
+            v.x = (q.x - p.x) * rdt;                          // :386
+            v.y = (q.y - p.y) * rdt;
             vout[m] = v;
         }
     }

@@ -79,7 +79,8 @@ struct plb_stokes {
     // parameters
     int hydrostatic = 1, warm_start = 0, debug_halo = 0;
     int lmax_every = 1, lmax_age = -1;   // eigenvalue estimates: recompute every n-th set_coeffs
-    bool have_prev = false;
+    bool have_prev = false, have_prev2 = false;
+    double* xprev = nullptr;
     double floor_est = 0;         // attainable scaled residual learnt from a stalled solve
     int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
     double cheb_ratio = 8.0, kry_reorth = 1e-4;
@@ -719,6 +720,16 @@ k_sub_row_mean(LevelDev L, const double* __restrict__ m, double* __restrict__ bz
     if (is_vz_row(L, i, j)) bz[(long long)i * L.ld + j] -= m[i];
 }
 
+// warm start by linear extrapolation in time: a <- 2a - b (new initial guess), b <- a (old iterate)
+__global__ void __launch_bounds__(256) k_extrapolate(long long n, double* __restrict__ a, double* __restrict__ b) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        const double x1 = a[t], x2 = b[t];
+        a[t] = 2 * x1 - x2;
+        b[t] = x1;
+    }
+}
+
 // value of the iterate's pressure in the anchor cell (3,2) (zero on ranks that do not own row 3)
 __global__ void k_get_anchor(LevelDev L, const double* __restrict__ p, double* out) {
     *out = (3 >= L.i0 && 3 < L.i1) ? p[3LL * L.ld + 2] : 0.0;
@@ -1105,7 +1116,7 @@ void plb_stokes_destroy(plb_stokes* op) {
     cudaStreamSynchronize(op->ctx->stream);
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
-    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d};
+    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->xprev};
     for (double* p : ptrs) if (p) cudaFree(p);
     plb_reduce_ws_free(&op->rws);
     delete op;
@@ -1294,8 +1305,20 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     const double bnorm = sqrt(bn2);
     // initial guess: the previous solve's iterate (deviation from its hydrostatic pressure) when
     // warm starts are enabled, otherwise zero
-    if (!(op->warm_start && op->have_prev))
+    if (!(op->warm_start && op->have_prev)) {
         PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
+        op->have_prev2 = false;
+    } else if (op->warm_start >= 2) {
+        // second-order start: extrapolate the last two converged iterates (equal step lengths assumed)
+        if (!op->xprev && zalloc(ctx, &op->xprev, 3 * P)) return 2;
+        if (op->have_prev2) {
+            k_extrapolate<<<plb_grid_for(ctx, (long long)(3 * P), 256, 8), 256, 0, ctx->stream>>>((long long)(3 * P), x, op->xprev);
+            PLB_LAUNCHED(ctx);
+        } else {
+            PLB_CUDA(ctx, cudaMemcpyAsync(op->xprev, x, sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, ctx->stream));
+            op->have_prev2 = true;
+        }
+    }
     int vcycles = 0;
     auto apply = [&](const double* z, double* c) -> int {
         // z comes out of `precond` with valid halo rows
