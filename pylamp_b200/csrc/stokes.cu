@@ -79,6 +79,9 @@ struct plb_stokes {
     // parameters
     int hydrostatic = 1, warm_start = 0, debug_halo = 0;
     int lmax_every = 1, lmax_age = -1;   // eigenvalue estimates: recompute every n-th set_coeffs
+    // CUDA graph of the V-cycle below level `graph_level` (small, launch-latency-bound, replicated levels)
+    int graph_level = -1, graph_launches = 0, use_graph = 1;
+    cudaGraphExec_t graph_exec = nullptr;
     bool have_prev = false, have_prev2 = false;
     double* xprev = nullptr;
     double floor_est = 0;         // attainable scaled residual learnt from a stalled solve
@@ -965,7 +968,12 @@ int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
     }
     {
         plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGCOARSE : -1);
-        if (vcycle(op, l + 1, Cl.b, Cl.X)) return 2;
+        if (op->graph_exec && l + 1 == op->graph_level) {
+            PLB_CUDA(ctx, cudaGraphLaunch(op->graph_exec, ctx->stream));
+            ctx->launches += op->graph_launches;
+        } else if (vcycle(op, l + 1, Cl.b, Cl.X)) {
+            return 2;
+        }
     }
     {
         plb_prof_scope prof_(ctx, l == 0 ? PLB_K_MGXFER0 : -1, 36.0 * (double)P);
@@ -1034,7 +1042,8 @@ int setup_hierarchy(plb_stokes* op) {
     // dense inverse on the coarsest level (replicated)
     Level& Lc = op->lv[nlev - 1];
     const int n = n_unknowns(Lc);
-    if (op->cinv) cudaFree(op->cinv), op->cinv = nullptr;
+    if (op->cinv && op->nc != n) cudaFree(op->cinv), op->cinv = nullptr;     // (kept: the CUDA graph holds it)
+    if (n > op->dense_max && op->cinv) cudaFree(op->cinv), op->cinv = nullptr;
     op->nc = 0;
     if (n <= op->dense_max) {
         const LevelDev D = Lc.dev();
@@ -1044,7 +1053,7 @@ int setup_hierarchy(plb_stokes* op) {
         if (zalloc(ctx, &probes, (size_t)n * 2 * P) || zalloc(ctx, &M, (size_t)n * 2 * n)) return 2;
         PLB_CUDA(ctx, cudaMalloc(&fail, sizeof(int)));
         PLB_CUDA(ctx, cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
-        PLB_CUDA(ctx, cudaMalloc(&op->cinv, sizeof(double) * (size_t)n * n));
+        if (!op->cinv) PLB_CUDA(ctx, cudaMalloc(&op->cinv, sizeof(double) * (size_t)n * n));
         k_probe_set<<<grid2d(Lc.nz, Lc.nxx), block2d(), 0, ctx->stream>>>(D, n, P, probes);
         PLB_LAUNCHED(ctx);
         dim3 g = grid2d(Lc.nz, Lc.nxx);
@@ -1061,6 +1070,41 @@ int setup_hierarchy(plb_stokes* op) {
         cudaFree(probes), cudaFree(M), cudaFree(fail);
         if (hfail) PLB_FAIL(ctx, "Stokes MG: singular coarse-level operator");
         op->nc = n;
+    }
+    // capture the V-cycle of the small levels (<= 1025 rows, replicated: no NCCL calls inside) into a
+    // CUDA graph: those levels are launch-latency-bound (~10 launches of a few microseconds each)
+    // (kernel arguments only change with the eigenvalue estimates: re-capture only then)
+    if (op->graph_exec && (fresh || !op->use_graph)) cudaGraphExecDestroy(op->graph_exec), op->graph_exec = nullptr;
+    if (!op->graph_exec) op->graph_level = -1;
+    if (op->use_graph && !op->graph_exec) {
+        int lg = -1;
+        for (int l = 1; l < nlev; l++)
+            if (!op->lv[l].dist && op->lv[l].nz <= 1025) { lg = l; break; }
+        if (lg > 0 && lg < nlev) {
+            Level& Lg = op->lv[lg];
+            cudaGraph_t graph = nullptr;
+            const long long before = ctx->launches;
+            PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            // the context usually runs on the legacy default stream (torch's), which cannot capture:
+            // record on a private stream, replay on the context's
+            cudaStream_t run_stream = ctx->stream, cap = nullptr;
+            PLB_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+            ctx->stream = cap;
+            cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+            int rc = e == cudaSuccess ? vcycle(op, lg, Lg.b, Lg.X) : 2;
+            if (e == cudaSuccess) e = cudaStreamEndCapture(cap, &graph);
+            ctx->stream = run_stream;
+            cudaStreamDestroy(cap);
+            if (rc || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                PLB_FAIL(ctx, "Stokes MG: CUDA graph capture of the coarse V-cycle failed (%s)", cudaGetErrorString(e));
+            }
+            op->graph_launches = (int)(ctx->launches - before);
+            ctx->launches = before;
+            PLB_CUDA(ctx, cudaGraphInstantiate(&op->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            op->graph_level = lg;
+        }
     }
     op->hierarchy = true;
     return 0;
@@ -1116,6 +1160,7 @@ void plb_stokes_destroy(plb_stokes* op) {
     cudaStreamSynchronize(op->ctx->stream);
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
+    if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
     double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->xprev};
     for (double* p : ptrs) if (p) cudaFree(p);
     plb_reduce_ws_free(&op->rws);
@@ -1140,6 +1185,7 @@ int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     else if (!strcmp(name, "warm_start")) op->warm_start = (int)value;
     else if (!strcmp(name, "debug_halo")) op->debug_halo = (int)value;
     else if (!strcmp(name, "lmax_every")) op->lmax_every = (int)value;
+    else if (!strcmp(name, "use_graph")) op->use_graph = (int)value, op->hierarchy = false;
     else if (!strcmp(name, "reorth_thresh")) op->kry_reorth = value;
     else PLB_FAIL(ctx, "plb_stokes_set_param: unknown parameter '%s'", name);
     return 0;
