@@ -213,8 +213,16 @@ def run_b200(args):
     if dom is not None:
         c, ms, by = prof[dom]
         ach = by / (ms * 1e-3) / 1e9
+        traffic = None
+        try:        # DRAM bytes per launch from the committed ncu --set full capture (same kernel, same grid)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = "k_cheb" if dom == 0 else None
+            if key and tr[key]["grid_nodes"] == list(nx) and world == 1:
+                traffic = tr[key]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": CLASS_NAMES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "launches_timed": c, "avg_launch_ms": ms / c,
+                    "frac": ach / peak, "traffic": traffic, "launches_timed": c, "avg_launch_ms": ms / c,
                     "algorithmic_bytes_per_launch": by / c, "peak_source": peak_src,
                     "share_of_step": ms / (ms_step * args.steps)}
     breakdown = {CLASS_NAMES[k]: {"launch_groups": v[0], "ms_per_step": v[1] / args.steps,
