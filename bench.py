@@ -302,7 +302,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--gmres-m", type=int, default=30, help="FGMRES restart length of the Stokes solve")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
-    ap.add_argument("--ref-ncell", type=int, default=192, help="--impl reference sample size")
+    ap.add_argument("--ref-ncell", type=int, default=256, help="--impl reference sample size")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -52,6 +52,7 @@ class Options:
         self.stokes_maxit = 600
         self.stokes_params = {"warm_start": 1}     # start each solve from the previous step's iterate
         self.heat_rtol = 1e-13
+        self.resort_every = 0         # > 0: re-order the markers by cell every n-th step
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -133,6 +134,8 @@ def timestep(s, o, want_kelem=True, phases=False):
     ph = s.phases = _Phases(phases)
     ph.mark("start")
     s.it += 1
+    if o.resort_every and s.it > 1 and (s.it - 1) % o.resort_every == 0:
+        s.tr_x, s.cols, _ = markers.sort_by_cell(s.tr_x, s.cols, s.nx, s.L)
     nx, grid, gridmp = s.nx, s.grid, s.gridmp
     cols, tr_x = s.cols, s.tr_x
     # marker property update, pylamp2.py:291-303

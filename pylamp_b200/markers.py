@@ -80,3 +80,23 @@ def subgrid_stage1(dt, dz, dx, Told, T, cp, rho, k):
 def subgrid_stage2(Tsg, back, T_out):
     """T = Tsg - back, pylamp2.py:480."""
     _ctx(Tsg).call("plb_subgrid_stage2", Tsg.shape[0], Tsg.data_ptr(), back.data_ptr(), T_out.data_ptr())
+
+
+def sort_by_cell(tr_x, cols, nx, L, extra=()):
+    """Physically re-order the marker arrays by cell index (cell-major, like the setups generate
+    them).  The results of every kernel are order-independent (up to fp64 summation order in
+    trac2grid); a cell-ordered cloud keeps trac2grid's run aggregation effective -- one atomic per
+    cell run instead of one per marker -- and the grid gathers of grid2trac/RK4 cache-local.
+    Returns (tr_x, cols, extra) as new tensors.  Device-side (torch) sort: plumbing, not a kernel."""
+    kelem, _ = cell_index_count(tr_x, nx, L, want_kelem=True)
+    order = torch.argsort(kelem)
+    del kelem
+    tr_x = tr_x.index_select(0, order)
+    seen, out = {}, []
+    for c in cols:                      # columns may alias each other (shared zero column)
+        key = c.data_ptr()
+        if key not in seen:
+            seen[key] = c.index_select(0, order)
+        out.append(seen[key])
+    extra = [e.index_select(0, order) for e in extra]
+    return tr_x, out, extra

@@ -168,3 +168,24 @@ def test_large_random_cloud_vs_oracle(T):
     vg, xg = T.RK(x, ng, vels, nx, dt)
     assert np.allclose(xg, xr, rtol=1e-10, atol=0)
     assert _rel(vg, vr) < 1e-9
+
+
+def test_sort_by_cell_keeps_results(T):
+    """A shuffled cloud and its cell-sorted version give the same grids (order-independent sums)."""
+    from pylamp_b200 import markers
+    rng = np.random.default_rng(9)
+    nx, L = [65, 49], [1.0, 0.75]
+    grid = O.make_grids(nx, L)[0]
+    M = 200000
+    x = rng.random((M, 2)) * L
+    f = rng.uniform(1, 2, M)
+    xd, fd = torch.as_tensor(x).cuda(), torch.as_tensor(f).cuda()
+    xs, (fs,), _ = markers.sort_by_cell(xd, [fd], nx, L)
+    k, _ = markers.cell_index_count(xs, nx, L)
+    assert bool((k[1:] >= k[:-1]).all())
+    out_a, out_b = [np.zeros(nx)], [np.zeros(nx)]
+    T.trac2grid(x, f[:, None], None, grid, out_a, nx, avgscheme=[5])
+    T.trac2grid(xs.cpu().numpy(), fs.cpu().numpy()[:, None], None, grid, out_b, nx, avgscheme=[5])
+    ref = [np.zeros(nx)]
+    O.trac2grid(x, f[:, None], None, grid, ref, nx, avgscheme=[5])
+    assert np.allclose(out_a[0], ref[0], rtol=1e-12) and np.allclose(out_b[0], ref[0], rtol=1e-12)
