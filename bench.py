@@ -146,7 +146,8 @@ def run_b200(args):
                                                        rank=rank, world=world)
     s = driver.State(nx, L, tr_x, cols, device=local)
     o = driver.Options(**opts)
-    o.stokes_params = {"warm_start": 2, "gcr_m": args.gmres_m, "lmax_every": 8}
+    o.heat_rtol = args.heat_rtol
+    o.stokes_params = {"warm_start": 2, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu}
     M = s.ntrac
     if world > 1:
         tm = torch.tensor([M], dtype=torch.int64, device="cuda")
@@ -239,7 +240,7 @@ def run_b200(args):
                        "%d GPUs: z-slab Stokes solve (NCCL halo send/recv + all-reduced dots), marker-parallel "
                        "MIC with all-reduced node sums, replicated grids and heat solve" % world,
                        "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
-                       "stokes_rtol": o.stokes_rtol, "stokes_solver": "FGMRES(%d) + GMG V(3,3) Chebyshev-Jacobi, warm start by linear extrapolation of the last two solutions, eigenvalue estimates every 8 steps" % args.gmres_m},
+                       "stokes_rtol": o.stokes_rtol, "heat_rtol": o.heat_rtol, "smoother_steps": args.nu, "stokes_solver": "FGMRES(%d) + GMG V(nu,nu) Chebyshev-Jacobi (--nu), warm start by linear extrapolation of the last two solutions, eigenvalue estimates every 8 steps" % args.gmres_m},
             "stokes_dof_per_s": 3.0 * N / (ms_step * 1e-3),
             "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "phases_ms_per_step": phase_ms, "kernel_breakdown": breakdown}
@@ -300,6 +301,8 @@ def main():
     ap.add_argument("--ncell", type=int, default=4096, help="cells per side of the GPU workload")
     ap.add_argument("--per-side", type=int, default=4, help="markers per cell side (16/cell)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--heat-rtol", type=float, default=1e-11, help="tolerance of the energy solve")
+    ap.add_argument("--nu", type=int, default=2, help="Chebyshev steps per pre-/post-smoothing")
     ap.add_argument("--gmres-m", type=int, default=30, help="FGMRES restart length of the Stokes solve")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
     ap.add_argument("--ref-ncell", type=int, default=256, help="--impl reference sample size")
