@@ -102,10 +102,11 @@ def test_convection_small():
         assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
 
 
-def test_convection_257_warm_started_steps():
-    """Larger grid (256^2 cells, 1.0e6 markers), the bench's solver settings (FGMRES(30), warm start):
-    every step within 1e-8 of the oracle's direct solve."""
-    sg, so, errs = _run_both(setups.convection(ncell=256), 2, tol_fields=1e-8,
-                             stokes_params={"warm_start": 1, "gcr_m": 30})
+def test_convection_257_bench_solver_settings():
+    """Larger grid (256^2 cells, 1.0e6 markers) with exactly bench.py's solver settings -- FGMRES(30),
+    V(2,2), extrapolated warm start, eigenvalue estimates reused, heat rtol 1e-11: every step within
+    1e-8 of the oracle's direct solve, positions within 1e-10."""
+    sg, so, errs = _run_both(setups.convection(ncell=256), 3, tol_fields=1e-8, heat_rtol=1e-11,
+                             stokes_params={"warm_start": 2, "gcr_m": 30, "nu": 2, "lmax_every": 8})
     for e in errs:
         assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
