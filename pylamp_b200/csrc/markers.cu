@@ -65,19 +65,29 @@ struct T2GArgs {
     double* cnt;                   // marker count per node (unweighted schemes)
     const double* axz;
     const double* axx;
+    const double* riz;             // 1/(axz[i+1]-axz[i])
+    const double* rix;
     int nze, nxe;
     double z0, zlen, x0, xlen;
+    double sz, sx;                 // (nze-1)/zlen, (nxe-1)/xlen
     int k;
 };
+
+__global__ void k_axis_recip(int n, const double* __restrict__ ax, double* __restrict__ r) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) r[i] = 1.0 / (ax[i + 1] - ax[i]);
+    else if (i == n - 1) r[i] = 0.0;
+}
 
 // (A shared-memory transpose variant of this reduction was measured slower: 50 vs 37 ms per 4096^2
 // step -- 105 registers and 35 KB smem per block cost more occupancy than the shuffles cost issue slots.)
 // Warp-aggregated scatter: contiguous lanes of a warp that fall in the same cell (the common
 // case once the markers are cell-ordered) are combined by a segmented shuffle reduction, so
 // only the first lane of each run issues the global fp64 reductions.  Correct for any order.
-__device__ __forceinline__ double seg_reduce(double v, int lane, int run_end) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+// `span` (warp-uniform) = longest remaining run length in lanes - 1: shuffle distances beyond it
+// cannot contribute, so short runs (the cell-ordered case: 16 markers = 4 lanes) need 2 steps, not 5
+__device__ __forceinline__ double seg_reduce(double v, int lane, int run_end, int span = 31) {
+    for (int o = 1; o <= span; o <<= 1) {
         double t = __shfl_down_sync(0xffffffffu, v, o);
         if (lane + o <= run_end) v += t;
     }
@@ -96,17 +106,30 @@ template <int K>
 __device__ __forceinline__ T2GMarker<K> t2g_load(const T2GArgs& a, const double2* __restrict__ trx, long long m) {
     T2GMarker<K> r;
     const double2 p = trx[m];
-    const long long ie = cell_of(p.x, a.z0, a.zlen, a.nze);
-    const long long je = cell_of(p.y, a.x0, a.xlen, a.nxe);
+    // Cell lookup by multiplication: unlike the per-cell count (plb_cell_index_count), the node sums do
+    // not depend on which of two cells a marker sitting exactly on a cell face is assigned to (its
+    // weights towards the far nodes are 0 either way), so the exact mul-then-divide of the reference
+    // is not needed here; fp64 division is what bounds this kernel.
+    // (Unweighted schemes count markers per assigned cell, so they keep the exact lookup.)
+    long long ie, je;
+    if (a.cnt) {
+        ie = cell_of(p.x, a.z0, a.zlen, a.nze);
+        je = cell_of(p.y, a.x0, a.xlen, a.nxe);
+    } else {
+        ie = (long long)floor((p.x - a.z0) * a.sz);
+        je = (long long)floor((p.y - a.x0) * a.sx);
+        // a marker on the upper edge of the (extended) axis belongs to the last cell
+        if (ie == a.nze - 1 && p.x <= a.axz[a.nze - 1]) ie = a.nze - 2;
+        if (je == a.nxe - 1 && p.y <= a.axx[a.nxe - 1]) je = a.nxe - 2;
+    }
     r.cell = -1;
 #pragma unroll
     for (int c = 0; c < 4; c++) r.w[c] = 0;
 #pragma unroll
     for (int f = 0; f < K; f++) r.v[f] = 0;
     if (ie < 0 || ie > a.nze - 2 || je < 0 || je > a.nxe - 2) return r;
-    const double gz0 = a.axz[ie], gz1 = a.axz[ie + 1], gx0 = a.axx[je], gx1 = a.axx[je + 1];
-    const double az = (p.x - gz0) / (gz1 - gz0);      // pylamp_trac.py:247
-    const double ax = (p.y - gx0) / (gx1 - gx0);
+    const double az = (p.x - a.axz[ie]) * a.riz[ie];   // pylamp_trac.py:247 (reciprocal spacing)
+    const double ax = (p.y - a.axx[je]) * a.rix[je];
     const double bz = 1 - az, bx = 1 - ax;            // :249
     r.w[0] = (1 - ax) * (1 - az);                     // node (i  , j  )   :252
     r.w[1] = (1 - ax) * (1 - bz);                     // node (i+1, j  )
@@ -201,17 +224,18 @@ k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
         const unsigned heads = __ballot_sync(full, head);
         const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
         const int run_end = after ? lane + __ffs(after) - 1 : 31;
+        const int span = __reduce_max_sync(full, run_end - lane);
         const bool emit = head && valid;
         const long long idx[4] = {cell, cell + a.nxe, cell + 1, cell + a.nxe + 1};
         if (a.wsum) {
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                double s = seg_reduce(w[c], lane, run_end);
+                double s = seg_reduce(w[c], lane, run_end, span);
                 if (emit) atomicAdd(a.wsum + idx[c], s);
             }
         }
         if (a.cnt) {
-            double s = seg_reduce(cntv, lane, run_end);
+            double s = seg_reduce(cntv, lane, run_end, span);
             if (emit) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) atomicAdd(a.cnt + idx[c], s);
@@ -222,11 +246,11 @@ k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
             if (a.scheme[f] & PLB_AVG_WEIGHTED) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    double s = seg_reduce(vw[f][c], lane, run_end);
+                    double s = seg_reduce(vw[f][c], lane, run_end, span);
                     if (emit) atomicAdd(a.acc[f] + idx[c], s);
                 }
             } else {
-                double s = seg_reduce(vw[f][0], lane, run_end);
+                double s = seg_reduce(vw[f][0], lane, run_end, span);
                 if (emit) {
 #pragma unroll
                     for (int c = 0; c < 4; c++) atomicAdd(a.acc[f] + idx[c], s);
@@ -560,8 +584,15 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
     }
     size_t plane = (size_t)nze * nxe;
     size_t nplanes = k + (any_w ? 1 : 0) + (any_c ? 1 : 0);
-    if (plb_ws_reserve(ctx, nplanes * plane * sizeof(double))) return 2;
+    if (plb_ws_reserve(ctx, (nplanes * plane + nze + nxe) * sizeof(double))) return 2;
     double* w = (double*)ctx->ws;
+    double* recip = w + nplanes * plane;
+    k_axis_recip<<<plb_blocks(nze, 256), 256, 0, ctx->stream>>>(nze, d_axis_z, recip);
+    PLB_LAUNCHED(ctx);
+    k_axis_recip<<<plb_blocks(nxe, 256), 256, 0, ctx->stream>>>(nxe, d_axis_x, recip + nze);
+    PLB_LAUNCHED(ctx);
+    a.riz = recip, a.rix = recip + nze;
+    a.sz = (double)(nze - 1) / zlen, a.sx = (double)(nxe - 1) / xlen;
     for (int f = 0; f < k; f++) a.acc[f] = w + (size_t)f * plane;
     size_t nxt = k;
     if (any_w) a.wsum = w + (nxt++) * plane;

@@ -3,6 +3,7 @@
 // scipy.sparse.linalg.spsolve at pylamp2.py:360: flexible GCR on the BC-eliminated saddle-point
 // system with a block-triangular preconditioner (viscosity-scaled pressure mass + one geometric
 // multigrid V-cycle with Chebyshev-Jacobi smoothing on the velocity block).
+#include <cuda_pipeline.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -77,7 +78,7 @@ struct plb_stokes {
     plb_fgmres_ws kry;
     double *xs = nullptr, *r3 = nullptr, *b3 = nullptr, *t3 = nullptr, *gz_d = nullptr, *gx_d = nullptr;
     // parameters
-    int hydrostatic = 1, warm_start = 0, debug_halo = 0;
+    int hydrostatic = 1, warm_start = 0, debug_halo = 0, tile_smoother = 1;
     int lmax_every = 1, lmax_age = -1;   // eigenvalue estimates: recompute every n-th set_coeffs
     // CUDA graph of the V-cycle below level `graph_level` (small, launch-latency-bound, replicated levels)
     int graph_level = -1, graph_launches = 0, use_graph = 1;
@@ -379,6 +380,125 @@ k_cheb(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
             d = cd * dx[o] + cr * r;
             dx[o] = d;
             store_vx(L, ox, i, j, xx[o] + d);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory-staged variant of the (non-first) Chebyshev-Jacobi sweep.  A CTA of 256 threads
+// owns a 16 x 64 tile of nodes; the four stencil inputs (vz, vx with a one-node halo; eta_s, eta_n
+// with their one-sided halos) are staged with asynchronous 8-byte global->shared copies (LDGSTS,
+// no register staging), b and d are read straight into registers meanwhile, and each thread then
+// computes 4 nodes from shared memory.  Nodes on the domain boundary take the generic path.
+// Same arithmetic as rows_interior().
+// ---------------------------------------------------------------------------------------------
+constexpr int TLX = 64, TLZ = 16, TLP = TLX + 2, TLE = TLX + 1;
+
+__global__ void __launch_bounds__(256)
+k_cheb_tile(LevelDev L, int row_lo, int row_hi, const double* __restrict__ xz, const double* __restrict__ xx,
+            const double* __restrict__ bz, const double* __restrict__ bx, double* __restrict__ dz,
+            double* __restrict__ dx, double* __restrict__ oz, double* __restrict__ ox, double cd, double cr) {
+    __shared__ double sz[(TLZ + 2) * TLP], sx[(TLZ + 2) * TLP], ses[(TLZ + 1) * TLE], sen[(TLZ + 1) * TLE];
+    const int tid = threadIdx.x;
+    const int i00 = L.i0 + blockIdx.y * TLZ, j00 = blockIdx.x * TLX;
+    const int ld = L.ld;
+    // ---- stage the tiles (rows outside the stored range [row_lo,row_hi] or the grid read as 0)
+    for (int e = tid; e < (TLZ + 2) * TLP; e += 256) {
+        const int r = e / TLP, c = e - r * TLP;
+        const int gi = i00 - 1 + r, gj = j00 - 1 + c;
+        if (gi >= row_lo && gi <= row_hi && gj >= 0 && gj < L.nxx) {
+            const long long o = (long long)gi * ld + gj;
+            __pipeline_memcpy_async(&sz[e], &xz[o], 8);
+            __pipeline_memcpy_async(&sx[e], &xx[o], 8);
+        } else {
+            sz[e] = 0.0, sx[e] = 0.0;
+        }
+    }
+    for (int e = tid; e < (TLZ + 1) * TLE; e += 256) {
+        const int r = e / TLE, c = e - r * TLE;
+        {   // eta_s rows i00..i00+TLZ, cols j00..j00+TLX (full-size replicated field: global rows)
+            const int gi = i00 + r, gj = j00 + c;
+            if (gi < L.nz && gj < L.nxx) __pipeline_memcpy_async(&ses[e], &L.etas[(long long)gi * ld + gj], 8);
+            else ses[e] = 0.0;
+        }
+        {   // eta_n rows i00-1.., cols j00-1..
+            const int gi = i00 - 1 + r, gj = j00 - 1 + c;
+            if (gi >= 0 && gi < L.nz && gj >= 0 && gj < L.nxx) __pipeline_memcpy_async(&sen[e], &L.etan[(long long)gi * ld + gj], 8);
+            else sen[e] = 0.0;
+        }
+    }
+    __pipeline_commit();
+    // ---- per-thread nodes: column tx, rows ty + 4k
+    const int tx = tid & 63, ty = tid >> 6;
+    const int j = j00 + tx;
+    const double idx_j = (j < L.nxx) ? L.idx[j] : 0.0, idx_m = (j >= 1 && j < L.nxx) ? L.idx[j - 1] : 0.0;
+    const double idxc_j = (j < L.nxx) ? L.idxc[j] : 0.0, idxc_p = (j + 1 < L.nxx) ? L.idxc[j + 1] : 0.0;
+    __pipeline_wait_prior(0);
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const int r = ty + 4 * k, i = i00 + r;
+        if (i >= L.i1 || j >= L.nxx) continue;
+        const long long o = (long long)i * ld + j;
+        const double vbz = bz[o], vbx = bx[o], vdz = dz[o], vdx = dx[o];     // issued before the smem reads
+        const bool rowz = is_vz_row(L, i, j), rowx = is_vx_row(L, i, j);
+        if (!is_interior(L, i, j)) {
+            // boundary nodes: generic path on global memory (same as k_cheb<false>)
+            if (rowz) {
+                VzCoef c = vz_coef(L, i, j);
+                double q = (bz[o] - kvz_apply(L, c, xz, xx, i, j)) / c.diag;
+                double d = cd * dz[o] + cr * q;
+                dz[o] = d;
+                store_vz(L, oz, i, j, xz[o] + d);
+            }
+            if (rowx) {
+                VxCoef c = vx_coef(L, i, j);
+                double q = (bx[o] - kvx_apply(L, c, xz, xx, i, j)) / c.diag;
+                double d = cd * dx[o] + cr * q;
+                dx[o] = d;
+                store_vx(L, ox, i, j, xx[o] + d);
+            }
+            continue;
+        }
+        const double* pz = &sz[(r + 1) * TLP + tx + 1];
+        const double* px = &sx[(r + 1) * TLP + tx + 1];
+        const double* pes = &ses[r * TLE + tx];
+        const double* pen = &sen[(r + 1) * TLE + tx + 1];
+        const double enC = pen[0], enM0 = pen[-TLE], en0M = pen[-1];
+        const double esC = pes[0], es0P = pes[1], esP0 = pes[TLE];
+        const double idz_i = L.idz[i], idz_m = L.idz[i - 1], idzc_i = L.idzc[i], idzc_p = L.idzc[i + 1];
+        const double z00 = pz[0], zP0 = pz[TLP], zM0 = pz[-TLP], z0P = pz[1], z0M = pz[-1], zPM = pz[TLP - 1];
+        const double x00 = px[0], x0P = px[1], x0M = px[-1], xP0 = px[TLP], xM0 = px[-TLP], xMP = px[-TLP + 1];
+        double kz, dgz, kx, dgx;
+        {
+            double cN = 4 * enC * idz_i * idzc_i, cS = 4 * enM0 * idz_m * idzc_i;
+            double cE = 2 * es0P * idxc_p * idx_j, cW = 2 * esC * idxc_j * idx_j;
+            double xE = 2 * es0P * idzc_i * idx_j, xW = 2 * esC * idzc_i * idx_j;
+            if (L.proper && j + 1 == L.nxx - 1) cE = 0, xE = 0;
+            dgz = -(cN + cS + cE + cW);
+            kz = cN * zP0 + cS * zM0 + cE * z0P + cW * z0M + dgz * z00 + xE * (x0P - xMP) - xW * (x00 - xM0);
+        }
+        {
+            double cE = 4 * enC * idx_j * idxc_j, cW = 4 * en0M * idx_m * idxc_j;
+            double cS = 2 * esP0 * idzc_p * idz_i, cN = 2 * esC * idzc_i * idz_i;
+            double xS = 2 * esP0 * idxc_j * idz_i, xN = 2 * esC * idxc_j * idz_i;
+            double wall = 0;
+            if (L.proper && i + 1 == L.nz - 1) {
+                if (L.ns_z1) wall = 2 * esP0 * idz_i * idz_i;
+                cS = 0, xS = 0;
+            }
+            dgx = -(cE + cW + cS + cN + wall);
+            kx = cE * x0P + cW * x0M + cS * xP0 + cN * xM0 + dgx * x00 + xS * (zP0 - zPM) - xN * (z00 - z0M);
+        }
+        if (rowz) {
+            double d = cd * vdz + cr * ((vbz - kz) / dgz);
+            dz[o] = d;
+            store_vz(L, oz, i, j, z00 + d);
+        }
+        if (rowx) {
+            double d = cd * vdx + cr * ((vbx - kx) / dgx);
+            dx[o] = d;
+            store_vx(L, ox, i, j, x00 + d);
         }
     }
 }
@@ -908,9 +1028,16 @@ double* smooth(plb_stokes* op, int l, const double* b, double* cur, double* othe
                 k_cheb<true><<<L.grid(), block2d(), 0, ctx->stream>>>(D, nullptr, nullptr, L.sh(b), L.sh(b + P), L.sh(L.d),
                                                                       L.sh(L.d + P), L.sh(cur), L.sh(cur + P), cd, cr);
             } else {
-                k_cheb<false><<<L.grid(), block2d(), 0, ctx->stream>>>(D, L.sh(cur), L.sh(cur + P), L.sh(b), L.sh(b + P),
-                                                                       L.sh(L.d), L.sh(L.d + P), L.sh(other),
-                                                                       L.sh(other + P), cd, cr);
+                if (op->tile_smoother && L.nxx >= 1024) {
+                    const dim3 tg((L.nxx + TLX - 1) / TLX, (L.i1 - L.i0 + TLZ - 1) / TLZ);
+                    k_cheb_tile<<<tg, 256, 0, ctx->stream>>>(D, L.lo, L.hi, L.sh(cur), L.sh(cur + P), L.sh(b), L.sh(b + P),
+                                                             L.sh(L.d), L.sh(L.d + P), L.sh(other), L.sh(other + P), cd,
+                                                             cr);
+                } else {
+                    k_cheb<false><<<L.grid(), block2d(), 0, ctx->stream>>>(D, L.sh(cur), L.sh(cur + P), L.sh(b),
+                                                                           L.sh(b + P), L.sh(L.d), L.sh(L.d + P),
+                                                                           L.sh(other), L.sh(other + P), cd, cr);
+                }
                 std::swap(cur, other);
             }
             ctx->launches++;
@@ -1184,6 +1311,7 @@ int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     else if (!strcmp(name, "hydrostatic")) op->hydrostatic = (int)value;
     else if (!strcmp(name, "warm_start")) op->warm_start = (int)value;
     else if (!strcmp(name, "debug_halo")) op->debug_halo = (int)value;
+    else if (!strcmp(name, "tile_smoother")) op->tile_smoother = (int)value, op->hierarchy = false, op->lmax_age = -1;
     else if (!strcmp(name, "lmax_every")) op->lmax_every = (int)value;
     else if (!strcmp(name, "use_graph")) op->use_graph = (int)value, op->hierarchy = false;
     else if (!strcmp(name, "reorth_thresh")) op->kry_reorth = value;
