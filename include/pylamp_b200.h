@@ -134,6 +134,15 @@ int plb_subgrid_stage1(plb_ctx* ctx, long long M, double dt, double dz, double d
                        const double* d_rho, const double* d_k, double* d_Tsg, double* d_dT);
 int plb_subgrid_stage2(plb_ctx* ctx, long long M, const double* d_Tsg, const double* d_back,
                        double* d_T);
+/* fused form of the marker temperature update + subgrid diffusion, pylamp2.py:448-480 (same
+ * arithmetic as grid2trac + the two stages above, one pass over the markers per stage):
+ * stage 1: T1 = T + interp(d_field = T_new - T_grid); Tsg, dT from T (old) and T1; T is not written
+ * stage 2: T = Tsg - interp(d_field = f_sgc).   Markers outside the grid are counted (stopOnError). */
+int plb_subgrid_fused(plb_ctx* ctx, int stage, long long M, const double* d_tr_x, const double* d_field,
+                      const double* d_grid_z, int nz, const double* d_grid_x, int nxx, int ld, double z0,
+                      double zlen, double x0, double xlen, double dt, double dz, double dx, double* d_T,
+                      const double* d_cp, const double* d_rho, const double* d_k, double* d_Tsg, double* d_dT,
+                      long long* h_n_outside);
 /* max over a field region / generic reductions used by the dt selection, pylamp2.py:339-366.
  * h_out = max of a (nz x nxx, ld) field (signed max, quirk 6).  Synchronises. */
 int plb_field_max(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_f, double* h_out);

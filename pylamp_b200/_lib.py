@@ -44,6 +44,8 @@ _PROTOS = {
     "plb_centre_velocities": (I, [VP, I, I, I, VP, VP, IP, I, VP, VP]),
     "plb_subgrid_stage1": (I, [VP, LL, D, D, D, VP, VP, VP, VP, VP, VP, VP]),
     "plb_subgrid_stage2": (I, [VP, LL, VP, VP, VP]),
+    "plb_subgrid_fused": (I, [VP, I, LL, VP, VP, VP, I, VP, I, I, D, D, D, D, D, D, D, VP, VP, VP, VP, VP, VP,
+                              C.POINTER(LL)]),
     "plb_field_max": (I, [VP, I, I, I, VP, DP]),
     "plb_max_diffusivity2": (I, [VP, I, I, I, VP, VP, VP, DP]),
     "plb_stokes_create": (I, [VP, I, I, I, DP, DP, IP, C.POINTER(VP)]),

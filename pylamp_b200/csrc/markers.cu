@@ -523,6 +523,54 @@ k_sub(long long M, const double* __restrict__ a, const double* __restrict__ b,
         out[m] = a[m] - b[m];
 }
 
+// Fused marker temperature update of pylamp2.py:448-475: T1 = T + interp(dT_grid) (:453-455), then the
+// subgrid relaxation Tsg = Told - (Told - T1) exp(-d dt / tau), dT = Tsg - T1 (:472-475) with Told = T.
+// One pass over the markers instead of clone + grid2trac + add + stage 1 (same arithmetic).
+__global__ void __launch_bounds__(256)
+k_subgrid_fused1(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ dTg,
+                 double dt, double fac, const double* __restrict__ T, const double* __restrict__ cp,
+                 const double* __restrict__ rho, const double* __restrict__ k, double* __restrict__ Tsg,
+                 double* __restrict__ dT, unsigned long long* n_outside) {
+    const double d = 0.5;
+    unsigned bad_local = 0;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        const double2 p = trx[m];
+        const Cell c = locate(g, p.x, p.y);
+        if (c.bad) {
+            bad_local++;
+            continue;
+        }
+        const double told = T[m];
+        const double t1 = told + bilin(dTg, g.ld, c);
+        const double tau = cp[m] * rho[m] / (k[m] * fac);
+        const double tsg = told - (told - t1) * exp(-d * dt / tau);
+        Tsg[m] = tsg;
+        dT[m] = tsg - t1;
+    }
+    bad_local = __reduce_add_sync(0xffffffffu, bad_local);
+    if ((threadIdx.x & 31) == 0 && bad_local) atomicAdd(n_outside, (unsigned long long)bad_local);
+}
+
+// T = Tsg - interp(f_sgc), pylamp2.py:479-480
+__global__ void __launch_bounds__(256)
+k_subgrid_fused2(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ sgc,
+                 const double* __restrict__ Tsg, double* __restrict__ T, unsigned long long* n_outside) {
+    unsigned bad_local = 0;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        const double2 p = trx[m];
+        const Cell c = locate(g, p.x, p.y);
+        if (c.bad) {
+            bad_local++;
+            continue;
+        }
+        T[m] = Tsg[m] - bilin(sgc, g.ld, c);
+    }
+    bad_local = __reduce_add_sync(0xffffffffu, bad_local);
+    if ((threadIdx.x & 31) == 0 && bad_local) atomicAdd(n_outside, (unsigned long long)bad_local);
+}
+
 template <int K>
 void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& a) {
     int threads = 256;
@@ -736,6 +784,38 @@ int plb_subgrid_stage2(plb_ctx* ctx, long long M, const double* d_Tsg, const dou
     if (M > 0) {
         k_sub<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, d_Tsg, d_back, d_T);   // :480
         PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int plb_subgrid_fused(plb_ctx* ctx, int stage, long long M, const double* d_tr_x, const double* d_field,
+                      const double* d_grid_z, int nz, const double* d_grid_x, int nxx, int ld, double z0,
+                      double zlen, double x0, double xlen, double dt, double dz, double dx, double* d_T,
+                      const double* d_cp, const double* d_rho, const double* d_k, double* d_Tsg, double* d_dT,
+                      long long* h_n_outside) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (plb_ws_reserve(ctx, 64)) return 2;
+    unsigned long long* d_bad = (unsigned long long*)ctx->ws;
+    PLB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->stream));
+    G2TGrid g = {d_grid_z, d_grid_x, nz, nxx, ld, z0, zlen, x0, xlen};
+    if (M > 0) {
+        plb_prof_scope prof_(ctx, PLB_K_G2T, (stage == 1 ? 64.0 : 32.0) * (double)M);
+        const int grid = plb_grid_for(ctx, M, 256, 8);
+        if (stage == 1) {
+            const double fac = (2 / dx) * (2 / dx) + (2 / dz) * (2 / dz);        // pylamp2.py:473
+            k_subgrid_fused1<<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, g, d_field, dt, fac, d_T, d_cp,
+                                                            d_rho, d_k, d_Tsg, d_dT, d_bad);
+        } else {
+            k_subgrid_fused2<<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, g, d_field, d_Tsg, d_T, d_bad);
+        }
+        PLB_LAUNCHED(ctx);
+    }
+    if (h_n_outside) {
+        unsigned long long* hp = (unsigned long long*)ctx->h_pinned;
+        PLB_CUDA(ctx, cudaMemcpyAsync(hp, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *h_n_outside = (long long)*hp;
     }
     return 0;
 }

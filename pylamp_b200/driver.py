@@ -210,20 +210,19 @@ def timestep(s, o, want_kelem=True, phases=False):
                 raise Exception("stopOnError in grid2trac")
             T.copy_(interp)
         else:                                                                       # :448-480
-            old_T = T.clone() if o.do_subgrid_heatdiff else None
             dT_grid = newtemp - s.f_T
-            nbad = g2t(ctx, tr_x, grid, [dT_grid], nx, INTERP_METHOD_LINEAR, float("nan"), [interp])
-            if nbad:
-                raise Exception("stopOnError in grid2trac")
-            T.add_(interp)
-            if o.do_subgrid_heatdiff:                                               # :471-480
-                Tsg, dT = markers.subgrid_stage1(tstep, s.dx[IZ], s.dx[IX], old_T, T, cols[TR_HCP],
-                                                 cols[TR_RHO], cols[TR_HCD])
+            if o.do_subgrid_heatdiff:
+                # fused: T1 = T + interp(dT_grid); Tsg, dT (:453-475); f_sgc = trac2grid(dT) (:478);
+                # T = Tsg - interp(f_sgc) (:479-480)
+                Tsg, dT = markers.subgrid_fused(1, tr_x, grid, dT_grid, T, tstep, s.dx[IZ], s.dx[IX],
+                                                cols[TR_HCP], cols[TR_RHO], cols[TR_HCD])
                 t2g(ctx, tr_x, [dT], [INTERP_AVG_ARITHW], grid, [s.f_sgc], mm)
-                nbad = g2t(ctx, tr_x, grid, [s.f_sgc], nx, INTERP_METHOD_LINEAR, float("nan"), [interp])
+                markers.subgrid_fused(2, tr_x, grid, s.f_sgc, T, Tsg=Tsg)
+            else:
+                nbad = g2t(ctx, tr_x, grid, [dT_grid], nx, INTERP_METHOD_LINEAR, float("nan"), [interp])
                 if nbad:
                     raise Exception("stopOnError in grid2trac")
-                markers.subgrid_stage2(Tsg, interp, T)
+                T.add_(interp)
         s.newtemp = newtemp
         ph.mark("grid2trac_T_subgrid")
     # velocities to cell centres + BC ring, RK4, pylamp2.py:491-550

@@ -100,3 +100,26 @@ def sort_by_cell(tr_x, cols, nx, L, extra=()):
         out.append(seen[key])
     extra = [e.index_select(0, order) for e in extra]
     return tr_x, out, extra
+
+
+def subgrid_fused(stage, tr_x, grid, field, T, dt=0.0, dz=1.0, dx=1.0, cp=None, rho=None, k=None, Tsg=None,
+                  dT=None):
+    """Fused marker temperature update + subgrid diffusion (pylamp2.py:448-480), one pass per stage.
+    stage 1 returns (Tsg, dT) from T (left untouched) and field = T_new - T_grid;
+    stage 2 writes T = Tsg - interp(field = f_sgc).  Raises like grid2trac(stopOnError=True)."""
+    import numpy as np
+    ctx = _ctx(tr_x)
+    gz, gx = np.asarray(grid[IZ], dtype=np.float64), np.asarray(grid[IX], dtype=np.float64)
+    gz_d = torch.as_tensor(gz).to(tr_x.device)
+    gx_d = torch.as_tensor(gx).to(tr_x.device)
+    if stage == 1:
+        Tsg, dT = torch.empty_like(T), torch.empty_like(T)
+    nbad = C.c_longlong(0)
+    p = lambda t: t.data_ptr() if t is not None else None
+    ctx.call("plb_subgrid_fused", stage, tr_x.shape[0], tr_x.data_ptr(), field.data_ptr(), gz_d.data_ptr(),
+             field.shape[0], gx_d.data_ptr(), field.shape[1], field.stride(0), float(gz[0]),
+             float(gz[-1] - gz[0]), float(gx[0]), float(gx[-1] - gx[0]), float(dt), float(dz), float(dx),
+             T.data_ptr(), p(cp), p(rho), p(k), p(Tsg), p(dT), C.byref(nbad))
+    if nbad.value:
+        raise Exception("stopOnError in grid2trac")
+    return Tsg, dT
