@@ -105,7 +105,7 @@ def test_solve_golden_small_nonuniform(S, golden_kernels):
                     gcr_m=200)      # node-wise random viscosity: Krylov needs a long recurrence
 
 
-@pytest.mark.parametrize("n", [65, 129])
+@pytest.mark.parametrize("n", [65, 129, 257])
 def test_solve_solcx(S, n):
     """BASELINE.json configs[1]: SolCx-type, viscosity jump 1e6 (2x2 coarsening is exact here)."""
     nx, L, grid, gridmp, etas, etan, rho = setups.solcx_fields(n)
