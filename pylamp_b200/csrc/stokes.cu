@@ -394,15 +394,12 @@ k_cheb(LevelDev L, const double* __restrict__ xz, const double* __restrict__ xx,
 // ---------------------------------------------------------------------------------------------
 constexpr int TLX = 64, TLZ = 16, TLP = TLX + 2, TLE = TLX + 1;
 
-__global__ void __launch_bounds__(256)
-k_cheb_tile(LevelDev L, int row_lo, int row_hi, const double* __restrict__ xz, const double* __restrict__ xx,
-            const double* __restrict__ bz, const double* __restrict__ bx, double* __restrict__ dz,
-            double* __restrict__ dx, double* __restrict__ oz, double* __restrict__ ox, double cd, double cr) {
-    __shared__ double sz[(TLZ + 2) * TLP], sx[(TLZ + 2) * TLP], ses[(TLZ + 1) * TLE], sen[(TLZ + 1) * TLE];
-    const int tid = threadIdx.x;
-    const int i00 = L.i0 + blockIdx.y * TLZ, j00 = blockIdx.x * TLX;
-    const int ld = L.ld;
-    // ---- stage the tiles (rows outside the stored range [row_lo,row_hi] or the grid read as 0)
+// issue the asynchronous copies of the velocity and viscosity tiles of the tile whose first node is
+// (i00, j00); rows outside the stored range [row_lo,row_hi] or the grid read as 0.  No commit/wait.
+__device__ __forceinline__ void stage_tiles(const LevelDev& L, int row_lo, int row_hi, int i00, int j00,
+                                            const double* __restrict__ xz, const double* __restrict__ xx,
+                                            double* sz, double* sx, double* ses, double* sen) {
+    const int tid = threadIdx.x, ld = L.ld;
     for (int e = tid; e < (TLZ + 2) * TLP; e += 256) {
         const int r = e / TLP, c = e - r * TLP;
         const int gi = i00 - 1 + r, gj = j00 - 1 + c;
@@ -427,6 +424,60 @@ k_cheb_tile(LevelDev L, int row_lo, int row_hi, const double* __restrict__ xz, c
             else sen[e] = 0.0;
         }
     }
+}
+
+struct TileRows {
+    double kz, dgz, kx, dgx;      // (K v)_vz, its diagonal, (K v)_vx, its diagonal
+    double z00, x00, zP0, x0P;    // centre values and the two neighbours the continuity row needs
+};
+
+// both momentum rows of interior node (i,j) = tile-local (r, tx) from the staged tiles
+__device__ __forceinline__ TileRows rows_from_tiles(const LevelDev& L, int i, int j, int r, int tx, const double* sz,
+                                                    const double* sx, const double* ses, const double* sen,
+                                                    double idx_j, double idx_m, double idxc_j, double idxc_p) {
+    const double* pz = &sz[(r + 1) * TLP + tx + 1];
+    const double* px = &sx[(r + 1) * TLP + tx + 1];
+    const double* pes = &ses[r * TLE + tx];
+    const double* pen = &sen[(r + 1) * TLE + tx + 1];
+    const double enC = pen[0], enM0 = pen[-TLE], en0M = pen[-1];
+    const double esC = pes[0], es0P = pes[1], esP0 = pes[TLE];
+    const double idz_i = L.idz[i], idz_m = L.idz[i - 1], idzc_i = L.idzc[i], idzc_p = L.idzc[i + 1];
+    const double z00 = pz[0], zP0 = pz[TLP], zM0 = pz[-TLP], z0P = pz[1], z0M = pz[-1], zPM = pz[TLP - 1];
+    const double x00 = px[0], x0P = px[1], x0M = px[-1], xP0 = px[TLP], xM0 = px[-TLP], xMP = px[-TLP + 1];
+    TileRows t;
+    t.z00 = z00, t.x00 = x00, t.zP0 = zP0, t.x0P = x0P;
+    {
+        double cN = 4 * enC * idz_i * idzc_i, cS = 4 * enM0 * idz_m * idzc_i;
+        double cE = 2 * es0P * idxc_p * idx_j, cW = 2 * esC * idxc_j * idx_j;
+        double xE = 2 * es0P * idzc_i * idx_j, xW = 2 * esC * idzc_i * idx_j;
+        if (L.proper && j + 1 == L.nxx - 1) cE = 0, xE = 0;
+        t.dgz = -(cN + cS + cE + cW);
+        t.kz = cN * zP0 + cS * zM0 + cE * z0P + cW * z0M + t.dgz * z00 + xE * (x0P - xMP) - xW * (x00 - xM0);
+    }
+    {
+        double cE = 4 * enC * idx_j * idxc_j, cW = 4 * en0M * idx_m * idxc_j;
+        double cS = 2 * esP0 * idzc_p * idz_i, cN = 2 * esC * idzc_i * idz_i;
+        double xS = 2 * esP0 * idxc_j * idz_i, xN = 2 * esC * idxc_j * idz_i;
+        double wall = 0;
+        if (L.proper && i + 1 == L.nz - 1) {
+            if (L.ns_z1) wall = 2 * esP0 * idz_i * idz_i;
+            cS = 0, xS = 0;
+        }
+        t.dgx = -(cE + cW + cS + cN + wall);
+        t.kx = cE * x0P + cW * x0M + cS * xP0 + cN * xM0 + t.dgx * x00 + xS * (zP0 - zPM) - xN * (z00 - z0M);
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+k_cheb_tile(LevelDev L, int row_lo, int row_hi, const double* __restrict__ xz, const double* __restrict__ xx,
+            const double* __restrict__ bz, const double* __restrict__ bx, double* __restrict__ dz,
+            double* __restrict__ dx, double* __restrict__ oz, double* __restrict__ ox, double cd, double cr) {
+    __shared__ double sz[(TLZ + 2) * TLP], sx[(TLZ + 2) * TLP], ses[(TLZ + 1) * TLE], sen[(TLZ + 1) * TLE];
+    const int tid = threadIdx.x;
+    const int i00 = L.i0 + blockIdx.y * TLZ, j00 = blockIdx.x * TLX;
+    const int ld = L.ld;
+    stage_tiles(L, row_lo, row_hi, i00, j00, xz, xx, sz, sx, ses, sen);
     __pipeline_commit();
     // ---- per-thread nodes: column tx, rows ty + 4k
     const int tx = tid & 63, ty = tid >> 6;
@@ -446,60 +497,101 @@ k_cheb_tile(LevelDev L, int row_lo, int row_hi, const double* __restrict__ xz, c
             // boundary nodes: generic path on global memory (same as k_cheb<false>)
             if (rowz) {
                 VzCoef c = vz_coef(L, i, j);
-                double q = (bz[o] - kvz_apply(L, c, xz, xx, i, j)) / c.diag;
-                double d = cd * dz[o] + cr * q;
+                double q = (vbz - kvz_apply(L, c, xz, xx, i, j)) / c.diag;
+                double d = cd * vdz + cr * q;
                 dz[o] = d;
                 store_vz(L, oz, i, j, xz[o] + d);
             }
             if (rowx) {
                 VxCoef c = vx_coef(L, i, j);
-                double q = (bx[o] - kvx_apply(L, c, xz, xx, i, j)) / c.diag;
-                double d = cd * dx[o] + cr * q;
+                double q = (vbx - kvx_apply(L, c, xz, xx, i, j)) / c.diag;
+                double d = cd * vdx + cr * q;
                 dx[o] = d;
                 store_vx(L, ox, i, j, xx[o] + d);
             }
             continue;
         }
-        const double* pz = &sz[(r + 1) * TLP + tx + 1];
-        const double* px = &sx[(r + 1) * TLP + tx + 1];
-        const double* pes = &ses[r * TLE + tx];
-        const double* pen = &sen[(r + 1) * TLE + tx + 1];
-        const double enC = pen[0], enM0 = pen[-TLE], en0M = pen[-1];
-        const double esC = pes[0], es0P = pes[1], esP0 = pes[TLE];
-        const double idz_i = L.idz[i], idz_m = L.idz[i - 1], idzc_i = L.idzc[i], idzc_p = L.idzc[i + 1];
-        const double z00 = pz[0], zP0 = pz[TLP], zM0 = pz[-TLP], z0P = pz[1], z0M = pz[-1], zPM = pz[TLP - 1];
-        const double x00 = px[0], x0P = px[1], x0M = px[-1], xP0 = px[TLP], xM0 = px[-TLP], xMP = px[-TLP + 1];
-        double kz, dgz, kx, dgx;
-        {
-            double cN = 4 * enC * idz_i * idzc_i, cS = 4 * enM0 * idz_m * idzc_i;
-            double cE = 2 * es0P * idxc_p * idx_j, cW = 2 * esC * idxc_j * idx_j;
-            double xE = 2 * es0P * idzc_i * idx_j, xW = 2 * esC * idzc_i * idx_j;
-            if (L.proper && j + 1 == L.nxx - 1) cE = 0, xE = 0;
-            dgz = -(cN + cS + cE + cW);
-            kz = cN * zP0 + cS * zM0 + cE * z0P + cW * z0M + dgz * z00 + xE * (x0P - xMP) - xW * (x00 - xM0);
-        }
-        {
-            double cE = 4 * enC * idx_j * idxc_j, cW = 4 * en0M * idx_m * idxc_j;
-            double cS = 2 * esP0 * idzc_p * idz_i, cN = 2 * esC * idzc_i * idz_i;
-            double xS = 2 * esP0 * idxc_j * idz_i, xN = 2 * esC * idxc_j * idz_i;
-            double wall = 0;
-            if (L.proper && i + 1 == L.nz - 1) {
-                if (L.ns_z1) wall = 2 * esP0 * idz_i * idz_i;
-                cS = 0, xS = 0;
-            }
-            dgx = -(cE + cW + cS + cN + wall);
-            kx = cE * x0P + cW * x0M + cS * xP0 + cN * xM0 + dgx * x00 + xS * (zP0 - zPM) - xN * (z00 - z0M);
-        }
+        const TileRows t = rows_from_tiles(L, i, j, r, tx, sz, sx, ses, sen, idx_j, idx_m, idxc_j, idxc_p);
         if (rowz) {
-            double d = cd * vdz + cr * ((vbz - kz) / dgz);
+            double d = cd * vdz + cr * ((vbz - t.kz) / t.dgz);
             dz[o] = d;
-            store_vz(L, oz, i, j, z00 + d);
+            store_vz(L, oz, i, j, t.z00 + d);
         }
         if (rowx) {
-            double d = cd * vdx + cr * ((vbx - kx) / dgx);
+            double d = cd * vdx + cr * ((vbx - t.kx) / t.dgx);
             dx[o] = d;
-            store_vx(L, ox, i, j, x00 + d);
+            store_vx(L, ox, i, j, t.x00 + d);
         }
+    }
+}
+
+// shared-memory-staged variant of k_stokes_op (pressure staged as a fifth tile)
+template <bool RESID>
+__global__ void __launch_bounds__(256)
+k_stokes_op_tile(LevelDev L, int row_lo, int row_hi, double Kc, const double* __restrict__ vz,
+                 const double* __restrict__ vx, const double* __restrict__ p, const double* __restrict__ bz,
+                 const double* __restrict__ bx, const double* __restrict__ bp, double* __restrict__ oz,
+                 double* __restrict__ ox, double* __restrict__ op) {
+    __shared__ double sz[(TLZ + 2) * TLP], sx[(TLZ + 2) * TLP], ses[(TLZ + 1) * TLE], sen[(TLZ + 1) * TLE],
+        sp[(TLZ + 1) * TLE];
+    const int tid = threadIdx.x;
+    const int i00 = L.i0 + blockIdx.y * TLZ, j00 = blockIdx.x * TLX;
+    const int ld = L.ld;
+    stage_tiles(L, row_lo, row_hi, i00, j00, vz, vx, sz, sx, ses, sen);
+    for (int e = tid; e < (TLZ + 1) * TLE; e += 256) {      // p rows i00-1.., cols j00-1.. (like eta_n)
+        const int r = e / TLE, c = e - r * TLE;
+        const int gi = i00 - 1 + r, gj = j00 - 1 + c;
+        if (gi >= row_lo && gi <= row_hi && gj >= 0 && gj < L.nxx) __pipeline_memcpy_async(&sp[e], &p[(long long)gi * ld + gj], 8);
+        else sp[e] = 0.0;
+    }
+    __pipeline_commit();
+    const int tx = tid & 63, ty = tid >> 6;
+    const int j = j00 + tx;
+    const double idx_j = (j < L.nxx) ? L.idx[j] : 0.0, idx_m = (j >= 1 && j < L.nxx) ? L.idx[j - 1] : 0.0;
+    const double idxc_j = (j < L.nxx) ? L.idxc[j] : 0.0, idxc_p = (j + 1 < L.nxx) ? L.idxc[j + 1] : 0.0;
+    __pipeline_wait_prior(0);
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const int r = ty + 4 * k, i = i00 + r;
+        if (i >= L.i1 || j >= L.nxx) continue;
+        const long long o = (long long)i * ld + j;
+        double vbz = 0, vbx = 0, vbp = 0;
+        if (RESID) vbz = bz[o], vbx = bx[o], vbp = bp[o];
+        if (!is_interior(L, i, j)) {
+            // boundary nodes: generic path (same as k_stokes_op)
+            double q = 0;
+            if (is_vz_row(L, i, j)) {
+                VzCoef c = vz_coef(L, i, j);
+                double a = kvz_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idzc[i] * (p[o] - p[o - ld]);
+                q = (RESID ? vbz - a : a) * rsqrt(-c.diag);
+            }
+            oz[o] = q;
+            q = 0;
+            if (is_vx_row(L, i, j)) {
+                VxCoef c = vx_coef(L, i, j);
+                double a = kvx_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idxc[j] * (p[o] - p[o - 1]);
+                q = (RESID ? vbx - a : a) * rsqrt(-c.diag);
+            }
+            ox[o] = q;
+            q = 0;
+            if (is_p_row(L, i, j)) {
+                double a = Kc * (L.idx[j] * (vx[o + 1] - vx[o]) + L.idz[i] * (vz[o + ld] - vz[o]));
+                q = (RESID ? vbp - a : a) * (sqrt(L.etan[o]) / Kc);
+            }
+            op[o] = q;
+            continue;
+        }
+        const TileRows t = rows_from_tiles(L, i, j, r, tx, sz, sx, ses, sen, idx_j, idx_m, idxc_j, idxc_p);
+        const double* pp = &sp[(r + 1) * TLE + tx + 1];
+        const double p00 = pp[0], pM0 = pp[-TLE], p0M = pp[-1];
+        const double en = sen[(r + 1) * TLE + tx + 1];
+        double a = t.kz - 2 * Kc * L.idzc[i] * (p00 - pM0);
+        oz[o] = is_vz_row(L, i, j) ? (RESID ? vbz - a : a) * rsqrt(-t.dgz) : 0.0;
+        a = t.kx - 2 * Kc * idxc_j * (p00 - p0M);
+        ox[o] = is_vx_row(L, i, j) ? (RESID ? vbx - a : a) * rsqrt(-t.dgx) : 0.0;
+        a = Kc * (idx_j * (t.x0P - t.x00) + L.idz[i] * (t.zP0 - t.z00));
+        op[o] = is_p_row(L, i, j) ? (RESID ? vbp - a : a) * (sqrt(en) / Kc) : 0.0;
     }
 }
 
@@ -1436,6 +1528,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     const double Kc = op->Kc;
     double *x = op->xs, *r = op->r3, *b = op->b3;
     const dim3 g = L.grid(), blk = block2d();
+    const dim3 tg((L.nxx + TLX - 1) / TLX, (L.i1 - L.i0 + TLZ - 1) / TLZ);     // tile-staged kernels
     // kernels index with global rows: shifted views of the local (slab) vectors
     auto V3 = [&](double* v, int pl) { return L.sh(v + (size_t)pl * P); };
     auto C3 = [&](const double* v, int pl) { return L.sh(v + (size_t)pl * P); };
@@ -1463,8 +1556,13 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     auto stokes_resid = [&](double* xx, double* out) -> int {
         if (halo(op, L, xx, 3)) return 2;
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 88.0 * (double)P);
-        k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2), C3(b, 0), C3(b, 1),
-                                                      C3(b, 2), V3(out, 0), V3(out, 1), V3(out, 2));
+        if (op->tile_smoother && L.nxx >= 1024)
+            k_stokes_op_tile<true><<<tg, 256, 0, ctx->stream>>>(D, L.lo, L.hi, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2),
+                                                                C3(b, 0), C3(b, 1), C3(b, 2), V3(out, 0), V3(out, 1),
+                                                                V3(out, 2));
+        else
+            k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2), C3(b, 0), C3(b, 1),
+                                                          C3(b, 2), V3(out, 0), V3(out, 1), V3(out, 2));
         PLB_LAUNCHED(ctx);
         return 0;
     };
@@ -1498,8 +1596,12 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         // z comes out of `precond` with valid halo rows
         if (op->debug_halo && halo(op, L, const_cast<double*>(z), 3)) return 2;
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 64.0 * (double)P);
-        k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr, nullptr, nullptr,
-                                                       V3(c, 0), V3(c, 1), V3(c, 2));
+        if (op->tile_smoother && L.nxx >= 1024)
+            k_stokes_op_tile<false><<<tg, 256, 0, ctx->stream>>>(D, L.lo, L.hi, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr,
+                                                                 nullptr, nullptr, V3(c, 0), V3(c, 1), V3(c, 2));
+        else
+            k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr, nullptr,
+                                                           nullptr, V3(c, 0), V3(c, 1), V3(c, 2));
         PLB_LAUNCHED(ctx);
         return 0;
     };
