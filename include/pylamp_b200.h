@@ -200,6 +200,9 @@ int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_
 void plb_diff_destroy(plb_diff* op);
 int plb_diff_set_coeffs(plb_diff* op, const double* d_T, const double* d_kz, const double* d_kx,
                         const double* d_cp, const double* d_rho, const double* d_H, double tstep);
+/* full-size (nz x ld) initial guess for the NEXT plb_diff_solve only (default: the field T); a time
+ * loop passes T + (previous step's temperature increment) */
+int plb_diff_set_initial_guess(plb_diff* op, const double* d_x0);
 /* rhs / apply / solve on (nz x nxx) vectors stored with the leading dimension ld */
 int plb_diff_rhs(plb_diff* op, double* d_rhs);
 int plb_diff_apply(plb_diff* op, const double* d_x, double* d_y);

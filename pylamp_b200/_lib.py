@@ -62,6 +62,7 @@ _PROTOS = {
     "plb_diff_create": (I, [VP, I, I, I, DP, DP, DP, DP, IP, DP, C.POINTER(VP)]),
     "plb_diff_destroy": (None, [VP]),
     "plb_diff_set_coeffs": (I, [VP, VP, VP, VP, VP, VP, VP, D]),
+    "plb_diff_set_initial_guess": (I, [VP, VP]),
     "plb_diff_rhs": (I, [VP, VP]),
     "plb_diff_apply": (I, [VP, VP, VP]),
     "plb_diff_solve": (I, [VP, VP, D, I, VP, IP, DP]),

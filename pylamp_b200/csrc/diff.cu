@@ -126,6 +126,7 @@ struct plb_diff {
     size_t plane = 0;                      // local plane size
     long long shift = 0;
     int m = 40;
+    const double* guess = nullptr;         // full-size initial guess for the next solve (NULL: T)
     int last_iters = 0;
     double last_relres = 0;
 };
@@ -205,6 +206,12 @@ int plb_diff_set_coeffs(plb_diff* op, const double* d_T, const double* d_kz, con
     return 0;
 }
 
+int plb_diff_set_initial_guess(plb_diff* op, const double* d_x0) {
+    if (!op) return 1;
+    op->guess = d_x0;
+    return 0;
+}
+
 int plb_diff_rhs(plb_diff* op, double* d_rhs) {
     if (!op) return 1;
     plb_ctx* ctx = op->ctx;
@@ -264,7 +271,9 @@ int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, do
     if (plb_read_scalars(ctx, op->d_scal + 900, 1, &bn2)) return 2;
     const double bnorm = sqrt(bn2);
     // initial guess: the current temperature field (the rhs is -T_old - dt*H/(rho*cp)); local rows
-    PLB_CUDA(ctx, cudaMemcpyAsync(x, D.T + sh, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    PLB_CUDA(ctx, cudaMemcpyAsync(x, (op->guess ? op->guess : D.T) + sh, sizeof(double) * n,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    op->guess = nullptr;
     auto apply = [&](const double* z, double* w) -> int {
         if (halo(const_cast<double*>(z))) return 2;
         k_diff<3><<<g, blk, 0, ctx->stream>>>(D, z - sh, nullptr, w - sh);

@@ -52,6 +52,7 @@ class Options:
         self.stokes_maxit = 600
         self.stokes_params = {"warm_start": 1}     # start each solve from the previous step's iterate
         self.heat_rtol = 1e-13
+        self.heat_extrapolate = True  # heat solve starts from T + the previous step's increment
         self.resort_every = 0         # > 0: re-order the markers by cell every n-th step
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -90,6 +91,7 @@ class State:
         self.trac_vel, self.tstep, self.limiter = None, None, ""
         self.kelem, self.count = None, None
         self.stokes_op, self.diff_op = None, None
+        self.prev_dT = None
         self.stats = {}
 
     @property
@@ -198,7 +200,11 @@ def timestep(s, o, want_kelem=True, phases=False):
                                                       o.bcheatvals, tstep, ctx=ctx)
         else:
             s.diff_op.set_coeffs(*args)
-        newtemp = pylamp_diff.x2t(s.diff_op.solve(None, rtol=o.heat_rtol), nx)
+        # start from T + the previous step's increment (the increments of consecutive steps are alike)
+        guess = s.f_T + s.prev_dT if (o.heat_extrapolate and s.prev_dT is not None) else None
+        newtemp = pylamp_diff.x2t(s.diff_op.solve(None, rtol=o.heat_rtol, guess=guess), nx)
+        if o.heat_extrapolate:
+            s.prev_dT = newtemp - s.f_T
         s.stats["heat_iters"] = s.diff_op.iterations
         ph.mark("heat_solve")
         T = cols[TR_TMP]

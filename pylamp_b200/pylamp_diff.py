@@ -86,8 +86,12 @@ class DiffusionOperator:
 
     __matmul__ = dot
 
-    def solve(self, rhs=None, rtol=DEFAULT_RTOL, maxit=DEFAULT_MAXIT):
+    def solve(self, rhs=None, rtol=DEFAULT_RTOL, maxit=DEFAULT_MAXIT, guess=None):
+        """x = A^-1 rhs.  `guess`: optional (nz,nxx) CUDA tensor to start from (default: f_T)."""
         host = self.host if rhs is None else not isinstance(rhs, torch.Tensor)
+        if guess is not None:
+            self._guess = _dev(guess, self.ctx)
+            self.ctx.check(self.ctx.lib.plb_diff_set_initial_guess(self.h, self._guess.data_ptr()))
         rd = None if rhs is None else _dev(rhs, self.ctx).reshape(-1)
         x = torch.empty(self.shape[0], dtype=torch.float64, device=self.ctx.torch_device)
         it, rr = C.c_int(0), C.c_double(0)
