@@ -82,6 +82,8 @@ struct plb_stokes {
     int lmax_every = 1, lmax_age = -1;   // eigenvalue estimates: recompute every n-th set_coeffs
     // CUDA graph of the V-cycle below level `graph_level` (small, launch-latency-bound, replicated levels)
     int graph_level = -1, graph_launches = 0, use_graph = 1;
+    int graph_all = -1;           // capture the WHOLE V-cycle incl. its NCCL calls (-1: only when slab-distributed)
+    double* zv = nullptr;         // fixed output buffer of the whole-cycle graph (2 local planes)
     cudaGraphExec_t graph_exec = nullptr;
     bool have_prev = false, have_prev2 = false;
     double* xprev = nullptr;
@@ -1299,8 +1301,19 @@ int setup_hierarchy(plb_stokes* op) {
         int lg = -1;
         for (int l = 1; l < nlev; l++)
             if (!op->lv[l].dist && op->lv[l].nz <= 1025) { lg = l; break; }
-        if (lg > 0 && lg < nlev) {
+        // Slab-distributed solves are bound by the host's enqueue rate (~70 kernel launches and ~35
+        // grouped NCCL send/recv calls per V-cycle): record the whole cycle, NCCL calls included, once.
+        const bool all = op->graph_all == 1 || (op->graph_all < 0 && op->lv[0].dist);
+        if (all) {
+            lg = 0;
+            if (!op->zv && zalloc(ctx, &op->zv, 2 * op->lv[0].plane)) return 2;
+        }
+        if (lg >= 0 && lg < nlev) {
             Level& Lg = op->lv[lg];
+            double* gout = lg == 0 ? op->zv : Lg.X;
+            if (lg == 0 && vcycle(op, 0, Lg.b, gout)) return 2;      // warm-up outside the capture (NCCL set-up)
+            const bool prof_was = ctx->prof_on;
+            ctx->prof_on = false;                                      // no event records inside the graph
             cudaGraph_t graph = nullptr;
             const long long before = ctx->launches;
             PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1310,9 +1323,10 @@ int setup_hierarchy(plb_stokes* op) {
             PLB_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
             ctx->stream = cap;
             cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
-            int rc = e == cudaSuccess ? vcycle(op, lg, Lg.b, Lg.X) : 2;
+            int rc = e == cudaSuccess ? vcycle(op, lg, Lg.b, gout) : 2;
             if (e == cudaSuccess) e = cudaStreamEndCapture(cap, &graph);
             ctx->stream = run_stream;
+            ctx->prof_on = prof_was;
             cudaStreamDestroy(cap);
             if (rc || e != cudaSuccess || !graph) {
                 if (graph) cudaGraphDestroy(graph);
@@ -1380,7 +1394,7 @@ void plb_stokes_destroy(plb_stokes* op) {
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
     if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
-    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->xprev};
+    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->xprev, op->zv};
     for (double* p : ptrs) if (p) cudaFree(p);
     plb_reduce_ws_free(&op->rws);
     delete op;
@@ -1405,7 +1419,8 @@ int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     else if (!strcmp(name, "debug_halo")) op->debug_halo = (int)value;
     else if (!strcmp(name, "tile_smoother")) op->tile_smoother = (int)value, op->hierarchy = false, op->lmax_age = -1;
     else if (!strcmp(name, "lmax_every")) op->lmax_every = (int)value;
-    else if (!strcmp(name, "use_graph")) op->use_graph = (int)value, op->hierarchy = false;
+    else if (!strcmp(name, "use_graph")) op->use_graph = (int)value, op->hierarchy = false, op->lmax_age = -1;
+    else if (!strcmp(name, "graph_all")) op->graph_all = (int)value, op->hierarchy = false, op->lmax_age = -1;
     else if (!strcmp(name, "reorth_thresh")) op->kry_reorth = value;
     else PLB_FAIL(ctx, "plb_stokes_set_param: unknown parameter '%s'", name);
     return 0;
@@ -1616,7 +1631,14 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
             PLB_CUDA(ctx, cudaMemsetAsync(z, 0, sizeof(double) * 2 * P, ctx->stream));
         }
         vcycles++;
-        if (vcycle(op, 0, L.b, z)) return 2;
+        if (op->graph_exec && op->graph_level == 0) {
+            plb_prof_scope prof_(ctx, PLB_K_MGCOARSE);            // (whole cycle: no per-kernel classes)
+            PLB_CUDA(ctx, cudaGraphLaunch(op->graph_exec, ctx->stream));
+            ctx->launches += op->graph_launches;
+            PLB_CUDA(ctx, cudaMemcpyAsync(z, op->zv, sizeof(double) * 2 * P, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else if (vcycle(op, 0, L.b, z)) {
+            return 2;
+        }
         reduce_shape(op, L, 3);                      // the V-cycle set per-level shapes
         return halo(op, L, z + 2 * P, 1);            // velocity halos are valid after the last sweep
     };
