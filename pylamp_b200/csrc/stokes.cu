@@ -82,7 +82,7 @@ struct plb_stokes {
     int lmax_every = 1, lmax_age = -1;   // eigenvalue estimates: recompute every n-th set_coeffs
     // CUDA graph of the V-cycle below level `graph_level` (small, launch-latency-bound, replicated levels)
     int graph_level = -1, graph_launches = 0, use_graph = 1;
-    int graph_all = -1;           // capture the WHOLE V-cycle incl. its NCCL calls (-1: only when slab-distributed)
+    int graph_all = -1;           // capture the WHOLE V-cycle (-1: on a single GPU only; 1 also captures NCCL calls)
     double* zv = nullptr;         // fixed output buffer of the whole-cycle graph (2 local planes)
     cudaGraphExec_t graph_exec = nullptr;
     bool have_prev = false, have_prev2 = false;
@@ -1301,9 +1301,12 @@ int setup_hierarchy(plb_stokes* op) {
         int lg = -1;
         for (int l = 1; l < nlev; l++)
             if (!op->lv[l].dist && op->lv[l].nz <= 1025) { lg = l; break; }
-        // Slab-distributed solves are bound by the host's enqueue rate (~70 kernel launches and ~35
-        // grouped NCCL send/recv calls per V-cycle): record the whole cycle, NCCL calls included, once.
-        const bool all = op->graph_all == 1 || (op->graph_all < 0 && op->lv[0].dist);
+        // Default on one GPU: record the WHOLE cycle (~70 launches) -- small and medium grids are bound by
+        // the host's enqueue rate (2049^2: 67 -> 53 ms per solve).  With slabs the cycle also contains
+        // ~35 grouped NCCL send/recv calls; capturing them works ("graph_all" = 1, tested on 2/4/8 GPUs)
+        // but brings nothing there (the NCCL kernels' own latency on the device timeline is the bound),
+        // so slab solves keep the graph for the replicated small levels only.
+        const bool all = op->graph_all == 1 || (op->graph_all < 0 && !op->lv[0].dist);
         if (all) {
             lg = 0;
             if (!op->zv && zalloc(ctx, &op->zv, 2 * op->lv[0].plane)) return 2;
