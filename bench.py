@@ -147,7 +147,8 @@ def run_b200(args):
     s = driver.State(nx, L, tr_x, cols, device=local)
     o = driver.Options(**opts)
     o.heat_rtol = args.heat_rtol
-    o.stokes_params = {"warm_start": 2, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu}
+    o.stokes_params = {"warm_start": 2, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu,
+                       "graph_all": 0}     # keep the V-cycle's kernels individually event-timed (whole-cycle graph: no gain at 4096^2)
     M = s.ntrac
     if world > 1:
         tm = torch.tensor([M], dtype=torch.int64, device="cuda")
