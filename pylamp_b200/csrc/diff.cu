@@ -112,6 +112,7 @@ k_diff(DiffDev D, const double* __restrict__ x, const double* __restrict__ b, do
 
 struct plb_diff {
     plb_ctx* ctx = nullptr;
+    int device = 0;
     int nz = 0, nxx = 0, ld = 0;
     double *idz = nullptr, *idx = nullptr, *idzm = nullptr, *idxm = nullptr;
     DiffDev dev{};
@@ -154,7 +155,7 @@ int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_
             PLB_FAIL(ctx, "plb_diff_create: unknown heat BC %d on wall %d", h_bc[w], w);
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     plb_diff* op = new plb_diff();
-    op->ctx = ctx, op->nz = nz, op->nxx = nxx, op->ld = ld;
+    op->ctx = ctx, op->device = ctx->device, op->nz = nz, op->nxx = nxx, op->ld = ld;
     std::vector<double> idz(nz, 0.0), idx(nxx, 0.0), idzm(nz, 0.0), idxm(nxx, 0.0);
     for (int i = 0; i + 1 < nz; i++) idz[i] = 1.0 / (h_grid_z[i + 1] - h_grid_z[i]);
     for (int j = 0; j + 1 < nxx; j++) idx[j] = 1.0 / (h_grid_x[j + 1] - h_grid_x[j]);
@@ -188,8 +189,8 @@ int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_
 
 void plb_diff_destroy(plb_diff* op) {
     if (!op) return;
-    cudaSetDevice(op->ctx->device);
-    cudaStreamSynchronize(op->ctx->stream);
+    cudaSetDevice(op->device);
+    cudaDeviceSynchronize();
     double* ptrs[] = {op->idz, op->idx, op->idzm, op->idxm, op->d_scal, op->xs, op->xl};
     for (double* p : ptrs) if (p) cudaFree(p);
     plb_fgmres_free(&op->kry);

@@ -61,6 +61,7 @@ struct Level {
 
 struct plb_stokes {
     plb_ctx* ctx = nullptr;
+    int device = 0;
     int nz = 0, nxx = 0, ld = 0;
     int bc[4] = {1, 1, 1, 1};
     std::vector<Level> lv;
@@ -1379,7 +1380,7 @@ int plb_stokes_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_gri
     }
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     plb_stokes* op = new plb_stokes();
-    op->ctx = ctx, op->nz = nz, op->nxx = nxx, op->ld = ld;
+    op->ctx = ctx, op->device = ctx->device, op->nz = nz, op->nxx = nxx, op->ld = ld;
     for (int w = 0; w < 4; w++) op->bc[w] = h_bc[w];
     if (plb_reduce_ws_init(ctx, &op->rws)) { delete op; return 2; }
     if (zalloc(ctx, &op->d_scal, 1024 + 2 * (size_t)nz)) { delete op; return 2; }
@@ -1392,8 +1393,9 @@ int plb_stokes_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_gri
 
 void plb_stokes_destroy(plb_stokes* op) {
     if (!op) return;
-    cudaSetDevice(op->ctx->device);
-    cudaStreamSynchronize(op->ctx->stream);
+    // (does not touch the context: the host side may release it first at interpreter shutdown)
+    cudaSetDevice(op->device);
+    cudaDeviceSynchronize();
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
     if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
