@@ -54,6 +54,7 @@ class Options:
         self.heat_rtol = 1e-13
         self.heat_extrapolate = True  # heat solve starts from T + the previous step's increment
         self.resort_every = 0         # > 0: re-order the markers by cell every n-th step
+        self.tracdens, self.tracdens_min = 45, 0   # marker injection (pylamp2.py:594-633); 0 = off
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -241,10 +242,26 @@ def timestep(s, o, want_kelem=True, phases=False):
     if not o.tracs_fence_enabled:
         raise NotImplementedError("marker deletion (fence disabled / FLOWTHRU): SURVEY.md §8f-1")
     markers.fence(s.tr_x, s.L, EPS)
-    s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=want_kelem)
+    s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=want_kelem or o.tracdens_min > 0)
+    if o.tracdens_min > 0:                                                          # :594-633
+        if ctx.comm_info()[1] > 1:
+            raise NotImplementedError("marker injection with marker-parallel ranks")
+        s.stats["injected"] = markers.inject_markers(s, o.tracdens, o.tracdens_min)
     if ctx.comm_info()[1] > 1:
         # marker-parallel ranks: per-cell counts of the whole cloud
         import torch.distributed as dist
         dist.all_reduce(s.count)
     ph.mark("fence_count")
     return s
+
+
+def save_npz(s, prefix, it=None):
+    """Write the two per-step `.npz` files of the reference with its exact keys (pylamp2.py:637-650:
+    `griddata.<it>.npz` = gridz, gridx, velz, velx, pres, rho, temp, tstep, time; `tracs.<it>.npz` =
+    tr_x, tr_f, tr_v), so that the reference's pylamp_post.py reads them unchanged."""
+    it = s.it if it is None else it
+    host = lambda t: t.detach().cpu().numpy() if t is not None else np.zeros(tuple(s.nx))
+    np.savez("%sgriddata.%d.npz" % (prefix, it), gridz=s.grid[IZ], gridx=s.grid[IX], velz=host(s.newvel[IZ]),
+             velx=host(s.newvel[IX]), pres=host(s.newpres), rho=host(s.f_rho), temp=host(s.newtemp),
+             tstep=it, time=s.totaltime)
+    np.savez("%stracs.%d.npz" % (prefix, it), tr_x=host(s.tr_x), tr_f=s.tr_f_host(), tr_v=host(s.trac_vel))

@@ -3,6 +3,7 @@
 CUDA float64 tensors; everything runs in the CUDA library (no CPU path)."""
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -123,3 +124,67 @@ def subgrid_fused(stage, tr_x, grid, field, T, dt=0.0, dz=1.0, dx=1.0, cp=None, 
     if nbad.value:
         raise Exception("stopOnError in grid2trac")
     return Tsg, dT
+
+
+def inject_markers(s, tracdens, tracdens_min, generator=None):
+    """Marker injection into under-populated cells on the device -- pylamp2.py:594-633.
+
+    Every cell with fewer than `tracdens_min` markers receives `tracdens - count` new markers at
+    uniformly random positions inside the cell; their properties are the mean of the cell's existing
+    markers (NaN for an empty cell, like the reference's 0/0), their TR__ID continues from the
+    current maximum exactly as the reference's per-cell loop does (each cell's first new id repeats
+    the running maximum, :614-615).  `s.kelem` / `s.count` must be current (end of `driver.timestep`).
+    The reference draws positions from NumPy's global Mersenne-Twister stream, so positions (not
+    counts, cells or properties) differ: parity is at the count/property level.
+    Implemented with torch tensor operations (device-side plumbing; no new kernel).  Returns the
+    number of injected markers."""
+    from .pylamp_const import NFTRAC, TR__ID
+    nz, nxx = int(s.nx[IZ]), int(s.nx[IX])
+    ncx = nxx - 1
+    dev = s.tr_x.device
+    count, kelem = s.count, s.kelem
+    few = count < tracdens_min
+    kmiss = torch.nonzero(few).flatten()
+    if kmiss.numel() == 0:
+        return 0
+    nmiss = (tracdens - count[kmiss]).to(torch.int64)
+    total = int(nmiss.sum().item())
+    ncell_m = kmiss.numel()
+    # existing markers of the deficient cells -> per-cell property means
+    lut = torch.full((count.numel(),), -1, dtype=torch.int64, device=dev)
+    lut[kmiss] = torch.arange(ncell_m, device=dev)
+    slot = lut[kelem]
+    idx = torch.nonzero(slot >= 0).flatten()
+    slot = slot[idx]
+    cnt = count[kmiss].to(torch.float64)
+    rep = torch.repeat_interleave(torch.arange(ncell_m, device=dev), nmiss)
+    # ids: cell c starts at the running maximum: max0 + sum_{c'<c} (n_c' - 1)
+    max0 = s.cols[TR__ID].max()
+    start = max0 + torch.cumsum(nmiss - 1, 0).to(torch.float64) - (nmiss - 1).to(torch.float64)
+    within = torch.arange(total, device=dev, dtype=torch.float64) - \
+        torch.repeat_interleave((torch.cumsum(nmiss, 0) - nmiss).to(torch.float64), nmiss)
+    new_cols, seen = [], {}
+    for k in range(NFTRAC):
+        col = s.cols[k]
+        if k == TR__ID:
+            new = start[rep] + within
+        else:
+            sums = torch.zeros(ncell_m, dtype=torch.float64, device=dev).index_add_(0, slot, col[idx])
+            new = (sums / cnt)[rep]                      # 0/0 = NaN for empty cells, like the reference
+        key = col.data_ptr()
+        if key in seen and k != TR__ID:                  # aliased (shared) columns stay aliased
+            new_cols.append(seen[key])
+            continue
+        out = torch.cat([col, new])
+        seen[key] = out
+        new_cols.append(out)
+    gz = torch.as_tensor(np.asarray(s.grid[IZ], dtype=np.float64)).to(dev)
+    gx = torch.as_tensor(np.asarray(s.grid[IX], dtype=np.float64)).to(dev)
+    im, jm = (kmiss // ncx)[rep], (kmiss % ncx)[rep]
+    u = torch.rand((total, 2), dtype=torch.float64, device=dev, generator=generator)
+    xt = torch.empty((total, 2), dtype=torch.float64, device=dev)
+    xt[:, IX] = u[:, IX] * (gx[jm + 1] - gx[jm]) + gx[jm]
+    xt[:, IZ] = u[:, IZ] * (gz[im + 1] - gz[im]) + gz[im]
+    s.tr_x = torch.cat([s.tr_x, xt])
+    s.cols = new_cols
+    return total

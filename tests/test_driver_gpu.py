@@ -110,3 +110,36 @@ def test_convection_257_bench_solver_settings():
                              stokes_params={"warm_start": 2, "gcr_m": 30, "nu": 2, "lmax_every": 8})
     for e in errs:
         assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
+
+
+def test_injection_matches_reference_counts_and_properties(tmp_path):
+    """C1 as shipped (tracdens 45, tracdens_min 25): one step, then marker injection on the device
+    versus the oracle's restatement of pylamp2.py:594-633 (which reproduces the reference's golden run
+    bit for bit): same number of injected markers, same cells, same (cell-mean) properties, same ids;
+    positions are random inside the same cells.  Also the .npz writer keeps the reference's keys."""
+    from pylamp_b200 import driver, markers
+    nx, L, tr_x, tr_f, opts = setups.c1_shipped(1234)
+    so, oo = O.State(nx, L, tr_x.copy(), tr_f.copy()), O.Options(solve=O.solve_refined, **opts)
+    sg, og = driver.State(nx, L, tr_x, tr_f), driver.Options(**opts)
+    O.timestep(so, oo)
+    driver.timestep(sg, og)
+    # make the comparison independent of the 1e-6 solver noise of this setup: inject on the oracle's markers
+    sg.tr_x = torch.as_tensor(so.tr_x).cuda()
+    sg.kelem, sg.count = markers.cell_index_count(sg.tr_x, nx, L)
+    M0 = so.tr_x.shape[0]
+    np.random.seed(7)
+    n_ref = O.inject_markers(so, 45, 25)
+    n_gpu = markers.inject_markers(sg, 45, 25)
+    assert n_gpu == n_ref > 0 and sg.tr_x.shape[0] == so.tr_x.shape[0]
+    new_f = np.stack([c.cpu().numpy()[M0:] for c in sg.cols], axis=1)
+    assert np.allclose(new_f, so.tr_f[M0:], rtol=1e-12, atol=0, equal_nan=True)
+    k_ref, c_ref = O.cell_index_count(so.tr_x, nx, L)
+    k_gpu, c_gpu = markers.cell_index_count(sg.tr_x, nx, L)
+    assert np.array_equal(c_gpu.cpu().numpy(), c_ref)
+    assert np.array_equal(k_gpu.cpu().numpy()[M0:], k_ref[M0:])
+    assert c_ref.min() >= 25
+    driver.save_npz(sg, str(tmp_path) + "/")
+    g = np.load(str(tmp_path) + "/griddata.1.npz")
+    t = np.load(str(tmp_path) + "/tracs.1.npz")
+    assert set(g.files) == {"gridz", "gridx", "velz", "velx", "pres", "rho", "temp", "tstep", "time"}
+    assert set(t.files) == {"tr_x", "tr_f", "tr_v"} and t["tr_f"].shape[1] == 13

@@ -76,3 +76,32 @@ def test_spsolve_dispatch_rejects_foreign_matrices():
         def solve(self, rhs, **kw):
             return rhs * 2
     assert np.array_equal(solve.spsolve(solve.csc_matrix(Fake()), np.ones(3)), 2 * np.ones(3))
+
+
+def test_inject_markers_logic_on_cpu_tensors():
+    """markers.inject_markers is pure tensor logic: run it on CPU tensors against the oracle's
+    restatement of pylamp2.py:594-633 (counts, cells, ids and cell-mean properties must agree)."""
+    import types
+    import torch
+    from pylamp_b200 import markers
+    rng = np.random.default_rng(3)
+    nx, L = [9, 7], [1.0, 0.5]
+    M = 600
+    tr_x = rng.random((M, 2)) * L
+    tr_x[:, 0] = tr_x[:, 0] ** 2            # uneven density: some cells under-populated, some empty
+    tr_f = rng.random((M, O.NFTRAC))
+    tr_f[:, O.TR__ID] = np.arange(M)
+    so = O.State(nx, L, tr_x.copy(), tr_f.copy())
+    so.kelem, so.count = O.cell_index_count(so.tr_x, nx, L)
+    s = types.SimpleNamespace(nx=nx, L=L, grid=so.grid, tr_x=torch.as_tensor(tr_x.copy()),
+                              cols=[torch.as_tensor(np.ascontiguousarray(tr_f[:, k])) for k in range(O.NFTRAC)],
+                              kelem=torch.as_tensor(so.kelem), count=torch.as_tensor(so.count))
+    np.random.seed(0)
+    n_ref = O.inject_markers(so, 12, 6)
+    n_new = markers.inject_markers(s, 12, 6)
+    assert n_new == n_ref > 0
+    new_f = np.stack([c.numpy()[M:] for c in s.cols], axis=1)
+    assert np.allclose(new_f, so.tr_f[M:], rtol=1e-12, atol=0, equal_nan=True)
+    k_ref, c_ref = O.cell_index_count(so.tr_x, nx, L)
+    k_new, c_new = O.cell_index_count(s.tr_x.numpy(), nx, L)
+    assert np.array_equal(c_new, c_ref) and np.array_equal(k_new[M:], k_ref[M:])
