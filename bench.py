@@ -147,7 +147,7 @@ def run_b200(args):
     s = driver.State(nx, L, tr_x, cols, device=local)
     o = driver.Options(**opts)
     o.heat_rtol = args.heat_rtol
-    o.stokes_params = {"warm_start": 2, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu,
+    o.stokes_params = {"warm_start": args.warm_start, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu,
                        "graph_all": 0}     # keep the V-cycle's kernels individually event-timed (whole-cycle graph: no gain at 4096^2)
     M = s.ntrac
     if world > 1:
@@ -248,7 +248,7 @@ def run_b200(args):
                        "%d GPUs: z-slab Stokes solve (NCCL halo send/recv + all-reduced dots), marker-parallel "
                        "MIC with all-reduced node sums, replicated grids and heat solve" % world,
                        "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
-                       "stokes_rtol": o.stokes_rtol, "heat_rtol": o.heat_rtol, "smoother_steps": args.nu, "stokes_solver": "FGMRES(%d) + GMG V(nu,nu) Chebyshev-Jacobi (--nu), warm start by linear extrapolation of the last two solutions, eigenvalue estimates every 8 steps" % args.gmres_m},
+                       "stokes_rtol": o.stokes_rtol, "heat_rtol": o.heat_rtol, "smoother_steps": args.nu, "stokes_solver": "FGMRES(%d) + GMG V(nu,nu) Chebyshev-Jacobi (--nu), warm start by polynomial extrapolation of the last %d iterates, eigenvalue estimates every 8 steps" % (args.gmres_m, args.warm_start)},
             "stokes_dof_per_s": 3.0 * N / (ms_step * 1e-3),
             "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_stencil": roofline_stencil, "phases_ms_per_step": phase_ms,
@@ -311,6 +311,7 @@ def main():
     ap.add_argument("--per-side", type=int, default=4, help="markers per cell side (16/cell)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--heat-rtol", type=float, default=1e-11, help="tolerance of the energy solve")
+    ap.add_argument("--warm-start", type=int, default=5, help="Stokes initial guess: 0 zero, 1 previous iterate, p >= 2: polynomial extrapolation of the last p iterates")
     ap.add_argument("--nu", type=int, default=2, help="Chebyshev steps per pre-/post-smoothing")
     ap.add_argument("--gmres-m", type=int, default=30, help="FGMRES restart length of the Stokes solve")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")

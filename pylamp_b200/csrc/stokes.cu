@@ -86,8 +86,9 @@ struct plb_stokes {
     int graph_all = -1;           // capture the WHOLE V-cycle (-1: on a single GPU only; 1 also captures NCCL calls)
     double* zv = nullptr;         // fixed output buffer of the whole-cycle graph (2 local planes)
     cudaGraphExec_t graph_exec = nullptr;
-    bool have_prev = false, have_prev2 = false;
-    double* xprev = nullptr;
+    bool have_prev = false;
+    std::vector<double*> hist;    // previous converged iterates (warm_start >= 2), newest first
+    int nhist = 0;
     double floor_est = 0;         // attainable scaled residual learnt from a stalled solve
     int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
     double cheb_ratio = 8.0, kry_reorth = 1e-4;
@@ -938,13 +939,19 @@ k_sub_row_mean(LevelDev L, const double* __restrict__ m, double* __restrict__ bz
     if (is_vz_row(L, i, j)) bz[(long long)i * L.ld + j] -= m[i];
 }
 
-// warm start by linear extrapolation in time: a <- 2a - b (new initial guess), b <- a (old iterate)
-__global__ void __launch_bounds__(256) k_extrapolate(long long n, double* __restrict__ a, double* __restrict__ b) {
+// warm start by polynomial extrapolation in time of the last p converged iterates (equal step
+// lengths assumed): x0 = sum_j c_j h_j, c_j = (-1)^j C(p, j+1): (2,-1), (3,-3,1), (4,-6,4,-1), ...; h_0 = newest
+struct HistList {
+    const double* h[6];
+    double c[6];
+    int p;
+};
+__global__ void __launch_bounds__(256) k_extrapolate(long long n, HistList H, double* __restrict__ x) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
          t += (long long)gridDim.x * blockDim.x) {
-        const double x1 = a[t], x2 = b[t];
-        a[t] = 2 * x1 - x2;
-        b[t] = x1;
+        double v = 0;
+        for (int j = 0; j < H.p; j++) v += H.c[j] * H.h[j][t];
+        x[t] = v;
     }
 }
 
@@ -1399,8 +1406,9 @@ void plb_stokes_destroy(plb_stokes* op) {
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
     if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
-    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->xprev, op->zv};
+    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->zv};
     for (double* p : ptrs) if (p) cudaFree(p);
+    for (double* p : op->hist) if (p) cudaFree(p);
     plb_reduce_ws_free(&op->rws);
     delete op;
 }
@@ -1599,16 +1607,28 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     // warm starts are enabled, otherwise zero
     if (!(op->warm_start && op->have_prev)) {
         PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * 3 * P, ctx->stream));
-        op->have_prev2 = false;
+        op->nhist = 0;
     } else if (op->warm_start >= 2) {
-        // second-order start: extrapolate the last two converged iterates (equal step lengths assumed)
-        if (!op->xprev && zalloc(ctx, &op->xprev, 3 * P)) return 2;
-        if (op->have_prev2) {
-            k_extrapolate<<<plb_grid_for(ctx, (long long)(3 * P), 256, 8), 256, 0, ctx->stream>>>((long long)(3 * P), x, op->xprev);
+        // keep the last (warm_start - 1) iterates besides the live one; newest first
+        const int keep = std::min(op->warm_start, 6);
+        if ((int)op->hist.size() < keep) op->hist.resize(keep, nullptr);
+        double* recycled = op->hist[keep - 1];
+        for (int j = keep - 1; j > 0; j--) op->hist[j] = op->hist[j - 1];
+        op->hist[0] = recycled;
+        if (!op->hist[0] && zalloc(ctx, &op->hist[0], 3 * P)) return 2;
+        PLB_CUDA(ctx, cudaMemcpyAsync(op->hist[0], x, sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, ctx->stream));
+        op->nhist = std::min(op->nhist + 1, keep);
+        if (op->nhist >= 2) {
+            HistList H;
+            H.p = op->nhist;
+            double binom = 1;                                  // C(p, j+1), alternating sign
+            for (int j = 0; j < 6; j++) {
+                if (j < H.p) binom = binom * (H.p - j) / (j + 1);
+                H.h[j] = j < H.p ? op->hist[j] : nullptr;
+                H.c[j] = j < H.p ? ((j & 1) ? -binom : binom) : 0.0;
+            }
+            k_extrapolate<<<plb_grid_for(ctx, (long long)(3 * P), 256, 8), 256, 0, ctx->stream>>>((long long)(3 * P), H, x);
             PLB_LAUNCHED(ctx);
-        } else {
-            PLB_CUDA(ctx, cudaMemcpyAsync(op->xprev, x, sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, ctx->stream));
-            op->have_prev2 = true;
         }
     }
     int vcycles = 0;
