@@ -53,6 +53,10 @@ int plb_ctx_sync(plb_ctx* ctx);
 const char* plb_last_error(plb_ctx* ctx);
 /* number of CUDA kernels this library has launched on the context so far */
 long long plb_launch_count(plb_ctx* ctx);
+/* tuning knobs that never change results beyond summation order.  "t2g_variant": 1 (default) =
+ * plb_trac2grid uses the wide-load chunk kernel when every scheme is weighted and the arrays are
+ * 32-byte aligned; 0 = always the generic scatter kernel. */
+int plb_ctx_set_param(plb_ctx* ctx, const char* name, double value);
 const char* plb_version(void);
 /* per-kernel-class timing with CUDA event pairs recorded around the launches on the context's
  * stream (classes: 0 smoother sweep on the finest level, 1 coupled Stokes operator, 2 multi-dot,

@@ -26,6 +26,7 @@ _PROTOS = {
     "plb_ctx_sync": (I, [VP]),
     "plb_last_error": (C.c_char_p, [VP]),
     "plb_launch_count": (LL, [VP]),
+    "plb_ctx_set_param": (I, [VP, C.c_char_p, D]),
     "plb_profile_enable": (I, [VP, I]),
     "plb_profile_read": (I, [VP, C.POINTER(LL), DP, DP]),
     "plb_comm_unique_id": (I, [VP, C.c_char_p]),
@@ -164,6 +165,10 @@ class Context:
         """In-place all-reduce of a float64 CUDA tensor over the slab communicator (no-op for 1 rank)."""
         self.call("plb_allreduce", tensor.data_ptr(), tensor.numel(), {"sum": 0, "max": 1, "min": 2}[op])
         return tensor
+
+    def set_param(self, name, value):
+        """Tuning knob of the context (include/pylamp_b200.h: plb_ctx_set_param)."""
+        self.call("plb_ctx_set_param", name.encode(), float(value))
 
     def profile(self, on=True):
         self.call("plb_profile_enable", 1 if on else 0)

@@ -28,6 +28,8 @@ struct plb_ctx {
     int prof_cap, prof_used;
     long long prof_skipped[16];
     double* prof_bytes;    // algorithmic bytes per recorded pair
+    // tuning knobs (plb_ctx_set_param)
+    int t2g_variant;       // 1: wide-load chunk kernel for weighted schemes (default), 0: generic kernel only
 };
 
 // kernel classes for plb_profile_* (bench.py's roofline block)

@@ -19,6 +19,7 @@ int plb_ctx_create(int device, plb_ctx** out) {
         return 3;
     }
     c->own_stream = true;
+    c->t2g_variant = 1;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->num_sms = prop.multiProcessorCount;
@@ -71,6 +72,15 @@ int plb_ctx_sync(plb_ctx* ctx) {
 const char* plb_last_error(plb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
 long long plb_launch_count(plb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int plb_ctx_set_param(plb_ctx* ctx, const char* name, double value) {
+    if (!ctx || !name) return 1;
+    if (!strcmp(name, "t2g_variant")) {
+        ctx->t2g_variant = (int)value;
+        return 0;
+    }
+    PLB_FAIL(ctx, "plb_ctx_set_param: unknown parameter '%s'", name);
+}
 
 int plb_profile_enable(plb_ctx* ctx, int on) {
     if (!ctx) return 1;

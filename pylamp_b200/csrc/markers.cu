@@ -67,16 +67,21 @@ struct T2GArgs {
     const double* axx;
     const double* riz;             // 1/(axz[i+1]-axz[i])
     const double* rix;
+    const double2* tz;             // {axz[i], riz[i]} (one 16-byte load per marker and axis)
+    const double2* tx;
     int nze, nxe;
     double z0, zlen, x0, xlen;
     double sz, sx;                 // (nze-1)/zlen, (nxe-1)/xlen
     int k;
 };
 
-__global__ void k_axis_recip(int n, const double* __restrict__ ax, double* __restrict__ r) {
+__global__ void k_axis_recip(int n, const double* __restrict__ ax, double* __restrict__ r,
+                             double2* __restrict__ tab) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n - 1) r[i] = 1.0 / (ax[i + 1] - ax[i]);
-    else if (i == n - 1) r[i] = 0.0;
+    if (i >= n) return;
+    const double v = (i < n - 1) ? 1.0 / (ax[i + 1] - ax[i]) : 0.0;
+    r[i] = v;
+    tab[i] = make_double2(ax[i], v);
 }
 
 // (A shared-memory transpose variant of this reduction was measured slower: 50 vs 37 ms per 4096^2
@@ -256,6 +261,179 @@ k_t2g_scatter(long long M, const double2* __restrict__ trx, T2GArgs a) {
                     for (int c = 0; c < 4; c++) atomicAdd(a.acc[f] + idx[c], s);
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chunk kernel for the weighted schemes (every trac2grid call of the time loop).  Same algorithm as
+// k_t2g_scatter -- 4 consecutive markers per thread, cell runs combined across lanes, one atomic
+// per (run, node, quantity) -- restructured around what ncu showed to bound that kernel (the L1
+// load/store pipe at 67 % with 8-byte loads at a 32-byte lane stride, and ~200 issued instructions
+// per marker):
+//  * a thread's 4 positions arrive as two 256-bit loads, its 4 values of a field as one;
+//  * the four corner weights of the 4 markers are computed once and kept; the fields are then
+//    processed one after the other (load, sum, reduce, add to the plane), so no accumulator lives
+//    across fields and the register count does not grow with K;
+//  * 32-bit cell indices; axis coordinate and reciprocal spacing share one 16-byte table entry;
+//  * a chunk that straddles cells keeps two aggregates (its first and its last run of equal cells,
+//    selected by masking the values, no branches); markers between those runs (three or more cells
+//    in one chunk) and chunks with a marker outside the grid take the one-marker path.
+// Summation order differs from the generic kernel, results agree to rounding.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+    // volatile: never hoisted above the guard of a lane whose chunk lies beyond the arrays
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// one marker straight to the planes (weighted schemes; rare paths only)
+__device__ __forceinline__ void t2g_single(const T2GArgs& a, const double2* __restrict__ trx, long long m) {
+    const T2GMarker<1> r = t2g_load<1>(a, trx, m);     // cell and weights; field 0 is reloaded below
+    if (r.cell < 0) return;
+    const long long idx[4] = {r.cell, r.cell + a.nxe, r.cell + 1, r.cell + a.nxe + 1};
+#pragma unroll
+    for (int c = 0; c < 4; c++) atomicAdd(a.wsum + idx[c], r.w[c]);
+#pragma unroll 1
+    for (int f = 0; f < a.k; f++) {
+        double val = a.f[f][m];
+        if (!(a.scheme[f] & PLB_AVG_ARITHMETIC)) val = log(val);
+#pragma unroll
+        for (int c = 0; c < 4; c++) atomicAdd(a.acc[f] + idx[c], val * r.w[c]);
+    }
+}
+
+// sums of one quantity over the chunk's last run (u >= s) and first run (u < e), warp-level
+// combination of the last runs, atomics
+__device__ __forceinline__ void t2g_chunk_quantity(double* __restrict__ plane, const double (&v)[4],
+                                                   const double (&wu)[4][4], int s, int e, int lane,
+                                                   int run_end, int span, bool emit, bool any_first,
+                                                   int cell_last, int cell_first, int nxe) {
+    double L[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const double vl = (u >= s) ? v[u] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) L[c] = fma(vl, wu[u][c], L[c]);
+    }
+    const int off[4] = {0, nxe, 1, nxe + 1};
+    for (int o = 1; o <= span; o <<= 1) {          // segmented reduction of the four corners together
+        const bool take = lane + o <= run_end;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double t = __shfl_down_sync(0xffffffffu, L[c], o);
+            if (take) L[c] += t;
+        }
+    }
+    if (emit) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) atomicAdd(plane + (cell_last + off[c]), L[c]);
+    }
+    if (any_first) {
+        double F[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const double vf = (u < e) ? v[u] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) F[c] = fma(vf, wu[u][c], F[c]);
+        }
+        if (e > 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) atomicAdd(plane + (cell_first + off[c]), F[c]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_t2g_chunk(long long nchunk, const double2* __restrict__ trx, T2GArgs a) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double zlast = a.axz[a.nze - 1], xlast = a.axx[a.nxe - 1];
+    long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; base < nchunk; base += stride) {
+        const long long ch = base + lane;
+        const bool live = ch < nchunk;
+        int cell[4] = {0, 0, 0, 0};
+        double wu[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) wu[u][c] = 0;
+        bool ok = live;
+        if (live) {
+            double pz[4], px[4];
+            const double* xp = (const double*)(trx + 4 * ch);
+            ld256(xp, pz[0], px[0], pz[1], px[1]);
+            ld256(xp + 4, pz[2], px[2], pz[3], px[3]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int ie = __double2int_rd((pz[u] - a.z0) * a.sz);
+                int je = __double2int_rd((px[u] - a.x0) * a.sx);
+                // a marker on the upper edge of the (extended) axis belongs to the last cell
+                if (ie == a.nze - 1 && pz[u] <= zlast) ie = a.nze - 2;
+                if (je == a.nxe - 1 && px[u] <= xlast) je = a.nxe - 2;
+                const bool in = (unsigned)ie <= (unsigned)(a.nze - 2) && (unsigned)je <= (unsigned)(a.nxe - 2);
+                ok = ok && in;
+                ie = in ? ie : 0, je = in ? je : 0;
+                const double2 tz = __ldg(a.tz + ie), tx = __ldg(a.tx + je);
+                const double az = (pz[u] - tz.x) * tz.y;          // pylamp_trac.py:247
+                const double ax = (px[u] - tx.x) * tx.y;
+                const double bz = 1 - az, bx = 1 - ax;            // :249
+                wu[u][0] = (1 - ax) * (1 - az);                   // node (i  , j  )   :252-255
+                wu[u][1] = (1 - ax) * (1 - bz);                   // node (i+1, j  )
+                wu[u][2] = (1 - bx) * (1 - az);                   // node (i  , j+1)
+                wu[u][3] = (1 - bx) * (1 - bz);                   // node (i+1, j+1)
+                cell[u] = ie * a.nxe + je;
+            }
+        }
+        // last run = markers [s, 4), first run = markers [0, e) (only if it is not the last run too),
+        // markers [e, s) in between take the one-marker path; a chunk with a marker outside: all four do
+        int s = 4, e = live ? 0 : 4;
+        if (ok) {
+            s = 3;
+            if (cell[2] == cell[3]) s = 2;
+            if (s == 2 && cell[1] == cell[2]) s = 1;
+            if (s == 1 && cell[0] == cell[1]) s = 0;
+            if (s > 0) {
+                e = 1;
+                if (s > 1 && cell[1] == cell[0]) e = 2;
+                if (e == 2 && s > 2 && cell[2] == cell[0]) e = 3;
+            }
+        }
+        const int cell_last = ok ? cell[3] : -1 - lane;   // lanes without a last run form runs of their own
+        const bool any_first = __any_sync(full, ok && e > 0);
+        const bool any_mid = __any_sync(full, live && s > e);
+        const int ef = ok ? e : 0;                        // first run only exists for clean chunks
+        const int prev = __shfl_up_sync(full, cell_last, 1);
+        const bool head = (lane == 0) || (prev != cell_last);
+        const unsigned heads = __ballot_sync(full, head);
+        const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
+        const int run_end = after ? lane + __ffs(after) - 1 : 31;
+        const int span = __reduce_max_sync(full, run_end - lane);
+        const bool emit = head && ok;
+        // the fields one after the other (rolled: one copy of the code), the next field's values in flight
+        double vn[4] = {0, 0, 0, 0};
+        if (ok) ld256(a.f[0] + 4 * ch, vn[0], vn[1], vn[2], vn[3]);
+        {
+            const double one[4] = {1, 1, 1, 1};
+            t2g_chunk_quantity(a.wsum, one, wu, s, ef, lane, run_end, span, emit, any_first, cell_last, cell[0],
+                               a.nxe);
+        }
+#pragma unroll 1
+        for (int f = 0; f < a.k; f++) {
+            double v[4] = {vn[0], vn[1], vn[2], vn[3]};
+            if (ok && f + 1 < a.k) ld256(a.f[f + 1] + 4 * ch, vn[0], vn[1], vn[2], vn[3]);
+            if (!(a.scheme[f] & PLB_AVG_ARITHMETIC)) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = log(v[u]);
+            }
+            t2g_chunk_quantity(a.acc[f], v, wu, s, ef, lane, run_end, span, emit, any_first, cell_last, cell[0],
+                               a.nxe);
+        }
+        if (any_mid) {
+#pragma unroll 1
+            for (int u = 0; u < 4; u++)
+                if (live && u >= e && u < s) t2g_single(a, trx, 4 * ch + u);
         }
     }
 }
@@ -578,6 +756,27 @@ void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& 
     k_t2g_scatter<K><<<grid, threads, 0, ctx->stream>>>(M, x, a);
 }
 
+void launch_chunk(plb_ctx* ctx, long long nchunk, const double2* x, const T2GArgs& a) {
+    int grid = plb_grid_for(ctx, nchunk, 256, 6);     // 80 registers: 3 resident CTAs per SM, two full waves
+    k_t2g_chunk<<<grid, 256, 0, ctx->stream>>>(nchunk, x, a);
+}
+
+template <int K>
+void scatter_k(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& a, bool chunked) {
+    if (!chunked) {
+        launch_scatter<K>(ctx, M, x, a);
+        return;
+    }
+    const long long nchunk = M / 4, rest = M - 4 * nchunk;
+    launch_chunk(ctx, nchunk, x, a);
+    if (rest) {       // the < 4 markers after the last whole chunk: generic kernel on the tail
+        ctx->launches++;
+        T2GArgs t = a;
+        for (int f = 0; f < K; f++) t.f[f] = a.f[f] + 4 * nchunk;
+        launch_scatter<K>(ctx, rest, x + 4 * nchunk, t);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -632,14 +831,22 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
     }
     size_t plane = (size_t)nze * nxe;
     size_t nplanes = k + (any_w ? 1 : 0) + (any_c ? 1 : 0);
-    if (plb_ws_reserve(ctx, (nplanes * plane + nze + nxe) * sizeof(double))) return 2;
+    // scratch: accumulation planes | {coordinate, reciprocal spacing} tables (16-byte aligned) | reciprocals
+    const size_t tab_off = (nplanes * plane + 1) & ~(size_t)1;
+    if (plb_ws_reserve(ctx, (tab_off + 3 * (size_t)(nze + nxe)) * sizeof(double))) return 2;
     double* w = (double*)ctx->ws;
-    double* recip = w + nplanes * plane;
-    k_axis_recip<<<plb_blocks(nze, 256), 256, 0, ctx->stream>>>(nze, d_axis_z, recip);
+    double2* tab = (double2*)(w + tab_off);
+    double* recip = w + tab_off + 2 * (size_t)(nze + nxe);
+    k_axis_recip<<<plb_blocks(nze, 256), 256, 0, ctx->stream>>>(nze, d_axis_z, recip, tab);
     PLB_LAUNCHED(ctx);
-    k_axis_recip<<<plb_blocks(nxe, 256), 256, 0, ctx->stream>>>(nxe, d_axis_x, recip + nze);
+    k_axis_recip<<<plb_blocks(nxe, 256), 256, 0, ctx->stream>>>(nxe, d_axis_x, recip + nze, tab + nze);
     PLB_LAUNCHED(ctx);
     a.riz = recip, a.rix = recip + nze;
+    a.tz = tab, a.tx = tab + nze;
+    // the chunk kernel needs weighted schemes only, 32-bit plane indices and 32-byte aligned arrays
+    bool chunked = ctx->t2g_variant == 1 && !any_c && M >= 4 && plane < ((size_t)1 << 31) &&
+                   ((uintptr_t)d_tr_x & 31) == 0;
+    for (int f = 0; f < k; f++) chunked = chunked && ((uintptr_t)h_fields[f] & 31) == 0;
     a.sz = (double)(nze - 1) / zlen, a.sx = (double)(nxe - 1) / xlen;
     for (int f = 0; f < k; f++) a.acc[f] = w + (size_t)f * plane;
     size_t nxt = k;
@@ -652,14 +859,14 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
         plb_prof_scope prof_(ctx, PLB_K_T2G, (16.0 + 8.0 * k) * (double)M);
         const double2* x = (const double2*)d_tr_x;
         switch (k) {
-            case 1: launch_scatter<1>(ctx, M, x, a); break;
-            case 2: launch_scatter<2>(ctx, M, x, a); break;
-            case 3: launch_scatter<3>(ctx, M, x, a); break;
-            case 4: launch_scatter<4>(ctx, M, x, a); break;
-            case 5: launch_scatter<5>(ctx, M, x, a); break;
-            case 6: launch_scatter<6>(ctx, M, x, a); break;
-            case 7: launch_scatter<7>(ctx, M, x, a); break;
-            default: launch_scatter<8>(ctx, M, x, a); break;
+            case 1: scatter_k<1>(ctx, M, x, a, chunked); break;
+            case 2: scatter_k<2>(ctx, M, x, a, chunked); break;
+            case 3: scatter_k<3>(ctx, M, x, a, chunked); break;
+            case 4: scatter_k<4>(ctx, M, x, a, chunked); break;
+            case 5: scatter_k<5>(ctx, M, x, a, chunked); break;
+            case 6: scatter_k<6>(ctx, M, x, a, chunked); break;
+            case 7: scatter_k<7>(ctx, M, x, a, chunked); break;
+            default: scatter_k<8>(ctx, M, x, a, chunked); break;
         }
         PLB_LAUNCHED(ctx);
     }

@@ -189,3 +189,98 @@ def test_sort_by_cell_keeps_results(T):
     ref = [np.zeros(nx)]
     O.trac2grid(x, f[:, None], None, grid, ref, nx, avgscheme=[5])
     assert np.allclose(out_a[0], ref[0], rtol=1e-12) and np.allclose(out_b[0], ref[0], rtol=1e-12)
+
+
+def _t2g_dev(T, x, cols, schemes, grid, nx, variant, view_offset=0):
+    """trac2grid_device on CUDA tensors with the given scatter-kernel variant; `view_offset` > 0
+    passes views that start `view_offset` markers into larger allocations (not 32-byte aligned)."""
+    from pylamp_b200 import _lib
+    ctx = _lib.default_context()
+    ctx.set_param("t2g_variant", variant)
+    try:
+        pad = np.zeros((view_offset, 2))
+        xd = torch.as_tensor(np.concatenate([pad, x])).cuda()[view_offset:]
+        cd = [torch.as_tensor(np.concatenate([np.ones(view_offset), c])).cuda()[view_offset:] for c in cols]
+        out = [torch.zeros(tuple(nx), dtype=torch.float64, device="cuda") for _ in cols]
+        T.trac2grid_device(ctx, xd, cd, schemes, grid, out)
+        return [o.cpu().numpy() for o in out]
+    finally:
+        ctx.set_param("t2g_variant", 1)
+
+
+@pytest.mark.parametrize("cloud", ["random", "sorted", "drifted", "outside"])
+@pytest.mark.parametrize("ragged", [0, 1, 2, 3])
+def test_trac2grid_chunk_kernel_matches_generic_and_oracle(T, cloud, ragged):
+    """The wide-load chunk kernel (t2g_variant 1: two aggregates per 4-marker chunk, one-marker path
+    for the rest) against the generic scatter kernel and the oracle, on clouds that exercise every
+    path: unordered (mostly one-marker path), cell-ordered (single runs), cell-ordered then displaced
+    (two runs per chunk), markers beyond the grid (ghost extension), marker counts not divisible by
+    4 (tail launch), all four staggered targets, arithmetic and geometric weighted means."""
+    from pylamp_b200 import setups
+    rng = np.random.default_rng(11)
+    ncz, ncx, L = 48, 40, [1.0, 0.75]
+    nx = [ncz + 1, ncx + 1]
+    grid, mesh, gridmp, meshmp = O.make_grids(nx, L)
+    if cloud == "random":
+        x = rng.random((60000, 2)) * L
+    else:
+        x = setups.lattice_markers(ncz, ncx, L, 4, seed=3)[0]
+        if cloud == "drifted":
+            x = x + np.array([0.37 * L[0] / ncz, 0.61 * L[1] / ncx])
+            x = np.minimum(np.maximum(x, 1e-9), np.array(L) - 1e-9)
+        if cloud == "outside":
+            x = x + np.array([-0.4 * L[0] / ncz, 0.3 * L[1] / ncx])      # beyond z=0 and x=L
+    if ragged:
+        x = x[:x.shape[0] - 4 + ragged]
+    M = x.shape[0]
+    cols = [rng.uniform(1, 2, M), 10 ** rng.uniform(18, 24, M), rng.uniform(-1, 1, M)]
+    schemes = [5, 6, 5]
+    f = np.stack(cols, axis=1)
+    for gr in ([grid[0], grid[1]], [gridmp[0], gridmp[1]], [gridmp[0], grid[1]], [grid[0], gridmp[1]]):
+        ref = [np.zeros(nx) for _ in cols]
+        O.trac2grid(x, f, None, gr, ref, nx, avgscheme=schemes)
+        chunk = _t2g_dev(T, x, cols, schemes, gr, nx, 1)
+        generic = _t2g_dev(T, x, cols, schemes, gr, nx, 0)
+        for a, b, r in zip(chunk, generic, ref):
+            assert np.array_equal(np.isnan(a), np.isnan(r)) and np.array_equal(np.isnan(b), np.isnan(r))
+            # the arithmetic mean of values in (-1,1) can cancel: absolute floor of a few ulps of 1
+            assert np.allclose(a, r, rtol=1e-12, atol=1e-14, equal_nan=True)
+            assert np.allclose(b, r, rtol=1e-12, atol=1e-14, equal_nan=True)
+
+
+def test_trac2grid_chunk_kernel_falls_back_on_unaligned_views_and_counts(T):
+    """Views that do not start on a 32-byte boundary and unweighted schemes (per-node marker
+    counts) must take the generic kernel whatever the variant: same results either way."""
+    rng = np.random.default_rng(12)
+    nx, L = [33, 25], [1.0, 0.75]
+    grid = O.make_grids(nx, L)[0]
+    M = 30001
+    x = rng.random((M, 2)) * L
+    cols = [rng.uniform(1, 2, M), 10 ** rng.uniform(18, 24, M)]
+    f = np.stack(cols, axis=1)
+    for schemes, off in (([5, 6], 1), ([5, 6], 3), ([1, 2], 0), ([5, 2], 0)):
+        ref = [np.zeros(nx) for _ in cols]
+        O.trac2grid(x, f, None, grid, ref, nx, avgscheme=schemes)
+        for variant in (0, 1):
+            out = _t2g_dev(T, x, cols, schemes, grid, nx, variant, view_offset=off)
+            for a, r in zip(out, ref):
+                assert np.allclose(a, r, rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_trac2grid_chunk_kernel_log_of_zero(T):
+    """A marker with eta = 0 gives ln = -inf: its nodes' sums are zeroed before exp (pylamp_trac.py:301)
+    and no other node is affected (the run masks select values, they never multiply by them)."""
+    from pylamp_b200 import setups
+    ncz, ncx, L = 16, 12, [1.0, 0.75]
+    nx = [ncz + 1, ncx + 1]
+    grid = O.make_grids(nx, L)[0]
+    x = setups.lattice_markers(ncz, ncx, L, 4, seed=5)[0]
+    M = x.shape[0]
+    eta = np.full(M, 1e20)
+    eta[[5, 1234, M - 2]] = 0.0
+    ref = [np.zeros(nx)]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        O.trac2grid(x, eta[:, None], None, grid, ref, nx, avgscheme=[6])
+    for variant in (0, 1):
+        out = _t2g_dev(T, x, [eta], [6], grid, nx, variant)
+        assert np.allclose(out[0], ref[0], rtol=1e-12, atol=0, equal_nan=True)
