@@ -147,6 +147,7 @@ def run_b200(args):
     s = driver.State(nx, L, tr_x, cols, device=local)
     o = driver.Options(**opts)
     o.heat_rtol = args.heat_rtol
+    o.marker_ownership = args.marker_ownership
     o.stokes_params = {"warm_start": args.warm_start, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu,
                        "graph_all": 0}     # keep the V-cycle's kernels individually event-timed (whole-cycle graph: no gain at 4096^2)
     M = s.ntrac
@@ -200,7 +201,7 @@ def run_b200(args):
 
     # ---- e2e: the same step through host buffers (rank-local) ----
     e2e = None
-    if args.e2e_steps > 0:
+    if args.e2e_steps > 0 and not (world > 1 and args.marker_ownership == "slab"):   # slab clouds change size
         e2e = run_e2e(torch, driver, s, o, args.e2e_steps)
         if world > 1:
             t = torch.tensor([e2e["ms"]], dtype=torch.float64, device="cuda")
@@ -248,8 +249,10 @@ def run_b200(args):
                                    "%d^2 cells, %d markers/cell, Stokes+energy+MIC advection" % (ncell, args.per_side ** 2),
                        "grid_nodes": nx, "markers": M, "stokes_dof": 3 * N,
                        "parallelism": "1 GPU" if world == 1 else
-                       "%d GPUs: z-slab Stokes solve (NCCL halo send/recv + all-reduced dots), marker-parallel "
-                       "MIC with all-reduced node sums, replicated grids and heat solve" % world,
+                       "%d GPUs: z-slab Stokes and heat solves (NCCL halo send/recv + all-reduced dots), markers "
+                       "%s, node sums all-reduced, replicated grid fields" %
+                       (world, "owned by z-slab with migration after every step" if args.marker_ownership == "slab"
+                        else "shared by index (no migration needed)"),
                        "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
                        "spinup_steps": args.spinup, "stokes_rtol": o.stokes_rtol, "heat_rtol": o.heat_rtol, "smoother_steps": args.nu, "stokes_solver": "FGMRES(%d) + GMG V(nu,nu) Chebyshev-Jacobi (--nu), warm start by polynomial extrapolation of the last %d iterates, eigenvalue estimates every 8 steps" % (args.gmres_m, args.warm_start)},
             "stokes_dof_per_s": 3.0 * N / (ms_step * 1e-3),
@@ -318,6 +321,8 @@ def main():
     ap.add_argument("--warm-start", type=int, default=5, help="Stokes initial guess: 0 zero, 1 previous iterate, p >= 2: polynomial extrapolation of the last p iterates")
     ap.add_argument("--nu", type=int, default=2, help="Chebyshev steps per pre-/post-smoothing")
     ap.add_argument("--gmres-m", type=int, default=30, help="FGMRES restart length of the Stokes solve")
+    ap.add_argument("--marker-ownership", default="index", choices=["index", "slab"],
+                    help="several GPUs: markers stay with their rank (index) or are owned by z-slab and migrate (slab)")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
     ap.add_argument("--ref-ncell", type=int, default=256, help="--impl reference sample size")
     args = ap.parse_args()

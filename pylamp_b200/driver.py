@@ -15,7 +15,7 @@ both sides.  No injection / output here (SURVEY.md §8f "next" rows); NPROC = 1 
 import numpy as np
 import torch
 
-from . import _lib, markers, pylamp_diff, pylamp_stokes, pylamp_trac
+from . import _lib, markers, migrate, pylamp_diff, pylamp_stokes, pylamp_trac
 from .pylamp_const import *  # noqa: F401,F403
 from .pylamp_const import (DIM, EPS, IX, IZ, NFTRAC, SECINYR, TR_ACE, TR_ALP, TR_ET0, TR_ETA, TR_HCD,
                            TR_HCP, TR_IHT, TR_MAT, TR_RH0, TR_RHO, TR_TMP)
@@ -55,6 +55,10 @@ class Options:
         self.heat_extrapolate = True  # heat solve starts from T + the previous step's increment
         self.resort_every = 0         # > 0: re-order the markers by cell every n-th step
         self.tracdens, self.tracdens_min = 45, 0   # marker injection (pylamp2.py:594-633); 0 = off
+        # several ranks: "index" = every rank keeps the markers it started with (any marker may be
+        # processed by any rank); "slab" = rank r owns the markers in its cell rows, markers that
+        # cross a slab boundary migrate to the new owner after the fence (migrate.py)
+        self.marker_ownership = "index"
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -236,19 +240,32 @@ def timestep(s, o, want_kelem=True, phases=False):
     vzc, vxc = markers.centre_velocities(s.newvel[IZ], s.newvel[IX], o.bcstokes)
     pre = [gridmp[d][0] - (gridmp[d][1] - gridmp[d][0]) for d in range(DIM)]
     newgrid = [np.insert(gridmp[IZ], 0, pre[IZ]), np.insert(gridmp[IX], 0, pre[IX])]
-    s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep)
+    world = ctx.comm_info()[1]
+    slab = world > 1 and o.marker_ownership == "slab"
+    s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep,
+                                                spare=slab)
     ph.mark("advect_rk4")
     # fence + per-cell count, pylamp2.py:558-593
     if not o.tracs_fence_enabled:
         raise NotImplementedError("marker deletion (fence disabled / FLOWTHRU): SURVEY.md §8f-1")
     markers.fence(s.tr_x, s.L, EPS)
+    if slab:
+        # markers that crossed a slab boundary move to their new owner (positions are final here)
+        s.stats["migrated"] = migrate.migrate(s)
+        ph.mark("migrate")
     s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=want_kelem or o.tracdens_min > 0)
     if o.tracdens_min > 0:                                                          # :594-633
-        if ctx.comm_info()[1] > 1:
-            raise NotImplementedError("marker injection with marker-parallel ranks")
-        s.stats["injected"] = markers.inject_markers(s, o.tracdens, o.tracdens_min)
-    if ctx.comm_info()[1] > 1:
-        # marker-parallel ranks: per-cell counts of the whole cloud
+        if world > 1 and not slab:
+            raise NotImplementedError("marker injection needs marker_ownership='slab' on several ranks "
+                                      "(a cell's markers must live on one rank)")
+        rows = None
+        if slab:
+            # a slab owns every marker of its cell rows: the local counts of those rows are complete
+            b = migrate.slab_bounds(nx[IZ] - 1, world)
+            rows = (b[ctx.comm_info()[0]], b[ctx.comm_info()[0] + 1])
+        s.stats["injected"] = markers.inject_markers(s, o.tracdens, o.tracdens_min, cell_rows=rows)
+    if world > 1:
+        # per-cell counts of the whole cloud
         import torch.distributed as dist
         dist.all_reduce(s.count)
     ph.mark("fence_count")

@@ -126,7 +126,7 @@ def subgrid_fused(stage, tr_x, grid, field, T, dt=0.0, dz=1.0, dx=1.0, cp=None, 
     return Tsg, dT
 
 
-def inject_markers(s, tracdens, tracdens_min, generator=None):
+def inject_markers(s, tracdens, tracdens_min, generator=None, cell_rows=None, group=None):
     """Marker injection into under-populated cells on the device -- pylamp2.py:594-633.
 
     Every cell with fewer than `tracdens_min` markers receives `tracdens - count` new markers at
@@ -136,18 +136,39 @@ def inject_markers(s, tracdens, tracdens_min, generator=None):
     the running maximum, :614-615).  `s.kelem` / `s.count` must be current (end of `driver.timestep`).
     The reference draws positions from NumPy's global Mersenne-Twister stream, so positions (not
     counts, cells or properties) differ: parity is at the count/property level.
-    Implemented with torch tensor operations (device-side plumbing; no new kernel).  Returns the
-    number of injected markers."""
+    Implemented with torch tensor operations (device-side plumbing; no new kernel).
+
+    Several ranks with slab-owned markers (migrate.py): `cell_rows` = (first, last+1) cell row of
+    this rank's slab -- only those cells are served (their local counts are complete), and the ids
+    continue over the ranks in cell order like the reference's single loop (collective: every rank
+    must call).  Returns the number of markers injected on this rank."""
+    from .migrate import resize_rows
     from .pylamp_const import NFTRAC, TR__ID
     nz, nxx = int(s.nx[IZ]), int(s.nx[IX])
     ncx = nxx - 1
     dev = s.tr_x.device
     count, kelem = s.count, s.kelem
     few = count < tracdens_min
+    if cell_rows is not None:
+        own = torch.zeros_like(few)
+        own[cell_rows[0] * ncx:cell_rows[1] * ncx] = True
+        few &= own
     kmiss = torch.nonzero(few).flatten()
+    nmiss = (tracdens - count[kmiss]).to(torch.int64)
+    M0 = s.tr_x.shape[0]
+    max0 = s.cols[TR__ID].max() if M0 else torch.tensor(-1.0, dtype=torch.float64, device=dev)
+    id_offset = 0.0
+    if cell_rows is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        max0 = max0.clone()
+        dist.all_reduce(max0, op=dist.ReduceOp.MAX, group=group)
+        sums = torch.zeros(world, dtype=torch.float64, device=dev)
+        sums[rank] = (nmiss - 1).sum().to(torch.float64)
+        dist.all_reduce(sums, group=group)
+        id_offset = float(sums[:rank].sum().item())
     if kmiss.numel() == 0:
         return 0
-    nmiss = (tracdens - count[kmiss]).to(torch.int64)
     total = int(nmiss.sum().item())
     ncell_m = kmiss.numel()
     # existing markers of the deficient cells -> per-cell property means
@@ -159,23 +180,30 @@ def inject_markers(s, tracdens, tracdens_min, generator=None):
     cnt = count[kmiss].to(torch.float64)
     rep = torch.repeat_interleave(torch.arange(ncell_m, device=dev), nmiss)
     # ids: cell c starts at the running maximum: max0 + sum_{c'<c} (n_c' - 1)
-    max0 = s.cols[TR__ID].max()
-    start = max0 + torch.cumsum(nmiss - 1, 0).to(torch.float64) - (nmiss - 1).to(torch.float64)
+    start = max0 + id_offset + torch.cumsum(nmiss - 1, 0).to(torch.float64) - (nmiss - 1).to(torch.float64)
     within = torch.arange(total, device=dev, dtype=torch.float64) - \
         torch.repeat_interleave((torch.cumsum(nmiss, 0) - nmiss).to(torch.float64), nmiss)
     new_cols, seen = [], {}
+    id_aliased = any(k != TR__ID and s.cols[k].data_ptr() == s.cols[TR__ID].data_ptr() for k in range(NFTRAC))
     for k in range(NFTRAC):
         col = s.cols[k]
         if k == TR__ID:
             new = start[rep] + within
-        else:
-            sums = torch.zeros(ncell_m, dtype=torch.float64, device=dev).index_add_(0, slot, col[idx])
-            new = (sums / cnt)[rep]                      # 0/0 = NaN for empty cells, like the reference
+            if id_aliased:                               # the id column shares storage with another one: un-alias
+                new_cols.append(torch.cat([col, new]))
+            else:
+                out = resize_rows(col, M0 + total)
+                out[M0:] = new
+                new_cols.append(out)
+            continue
         key = col.data_ptr()
-        if key in seen and k != TR__ID:                  # aliased (shared) columns stay aliased
+        if key in seen:                                  # aliased (shared) columns stay aliased
             new_cols.append(seen[key])
             continue
-        out = torch.cat([col, new])
+        sums = torch.zeros(ncell_m, dtype=torch.float64, device=dev).index_add_(0, slot, col[idx])
+        new = (sums / cnt)[rep]                          # 0/0 = NaN for empty cells, like the reference
+        out = resize_rows(col, M0 + total)               # appended in place while the spare capacity lasts
+        out[M0:] = new
         seen[key] = out
         new_cols.append(out)
     gz = torch.as_tensor(np.asarray(s.grid[IZ], dtype=np.float64)).to(dev)
@@ -185,6 +213,7 @@ def inject_markers(s, tracdens, tracdens_min, generator=None):
     xt = torch.empty((total, 2), dtype=torch.float64, device=dev)
     xt[:, IX] = u[:, IX] * (gx[jm + 1] - gx[jm]) + gx[jm]
     xt[:, IZ] = u[:, IZ] * (gz[im + 1] - gz[im]) + gz[im]
-    s.tr_x = torch.cat([s.tr_x, xt])
+    s.tr_x = resize_rows(s.tr_x, M0 + total)
+    s.tr_x[M0:] = xt
     s.cols = new_cols
     return total

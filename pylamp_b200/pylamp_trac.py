@@ -180,12 +180,19 @@ def grid2trac(tr_x, tr_f, grid, gridfield, nx, defval=np.nan, method=INTERP_METH
     return
 
 
-def rk4_device(ctx, tr_x_d, grids, vz_d, vx_d, nx1, tstep, want_vel=True):
+def rk4_device(ctx, tr_x_d, grids, vz_d, vx_d, nx1, tstep, want_vel=True, spare=False):
+    """Device-resident RK4 (plb_rk4).  `spare`: allocate the outputs with a little spare capacity
+    (slab-owned marker clouds grow and shrink by migration, see migrate.py)."""
     gz, gx = _axis_np(grids[IZ]), _axis_np(grids[IX])
     gz_d, gx_d = _to_dev(gz, ctx), _to_dev(gx, ctx)
     M = tr_x_d.shape[0]
-    x_out = torch.empty_like(tr_x_d)
-    v_out = torch.empty_like(tr_x_d) if want_vel else None
+    if spare:
+        from .migrate import empty_rows
+        new = lambda: empty_rows(M, (2,), torch.float64, tr_x_d.device)
+    else:
+        new = lambda: torch.empty_like(tr_x_d)
+    x_out = new()
+    v_out = new() if want_vel else None
     ctx.call("plb_rk4", M, tr_x_d.data_ptr(), vz_d.data_ptr(), vx_d.data_ptr(), gz_d.data_ptr(),
              int(nx1[IZ]), gx_d.data_ptr(), int(nx1[IX]), int(vz_d.shape[1]), float(gz[0]),
              float(gz[-1] - gz[0]), float(gx[0]), float(gx[-1] - gx[0]), float(tstep),

@@ -1,6 +1,8 @@
 """Multi-GPU parity (torchrun, one process per GPU): the distributed timestep -- marker-parallel
 ranks, all-reduced node sums, z-slab Stokes solve -- versus the oracle's single-process loop body.
-  torchrun --nproc-per-node 2 scripts/multi_gpu_driver_check.py [ncell] [nsteps]"""
+  torchrun --nproc-per-node 2 scripts/multi_gpu_driver_check.py [ncell] [nsteps] [index|slab]
+With "slab" every rank starts with the markers of its own cell rows and markers migrate between the
+slabs after every step (pylamp_b200/migrate.py); markers are then matched with the oracle's by id."""
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import pylamp_oracle as O
@@ -11,29 +13,49 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+ownership = sys.argv[3] if len(sys.argv) > 3 else "index"
+host_group = dist.new_group(backend="gloo")          # object gathers of the id-matched comparison
 ctx = _lib.default_context(local)
 ctx.init_comm()
 nx, L, tr_x, tr_f, opts = setups.convection(ncell=ncell)
 M = tr_x.shape[0]
-lo, hi = (rank * M) // world, ((rank + 1) * M) // world          # contiguous share of the markers
-sg = driver.State(nx, L, tr_x[lo:hi], tr_f[lo:hi], device=local)
-og = driver.Options(**opts)
+if ownership == "slab":
+    from pylamp_b200 import migrate
+    b = migrate.slab_bounds(ncell, world)
+    ie = np.clip(np.floor(ncell * tr_x[:, 0] / L[0]).astype(int), 0, ncell - 1)
+    sel = np.nonzero(np.searchsorted(b[1:-1], ie, side="right") == rank)[0]
+else:
+    sel = np.arange((rank * M) // world, ((rank + 1) * M) // world)   # contiguous share of the markers
+sg = driver.State(nx, L, tr_x[sel], tr_f[sel], device=local)
+og = driver.Options(marker_ownership=ownership, **opts)
 if rank == 0:
     so, oo = O.State(nx, L, tr_x.copy(), tr_f.copy()), O.Options(solve=O.solve_refined, **opts)
 ok = True
 for it in range(nsteps):
     driver.timestep(sg, og)
+    # this rank's markers matched with the oracle's by id (they change slot and rank when they migrate)
+    ids = sg.cols[O.TR__ID].cpu().numpy().astype(np.int64)
+    mine = [None] * world
+    dist.gather_object((ids, sg.tr_x.cpu().numpy(), sg.cols[O.TR_TMP].cpu().numpy()), mine if rank == 0 else None,
+                       dst=0, group=host_group)
+    if ownership == "slab":
+        ok = ok and migrate.check_ownership(sg) == 0
     if rank == 0:
         O.timestep(so, oo)
+        all_ids = np.concatenate([m[0] for m in mine])
+        ok = ok and np.array_equal(np.sort(all_ids), np.arange(M))          # nobody lost, nobody duplicated
+        gx, gT = np.concatenate([m[1] for m in mine]), np.concatenate([m[2] for m in mine])
         rel = lambda a, b: float(np.linalg.norm(a.cpu().numpy() - b) / np.linalg.norm(b))
         e = {"vz": rel(sg.newvel[0], so.newvel[0]), "vx": rel(sg.newvel[1], so.newvel[1]),
              "P": rel(sg.newpres, so.newpres), "T": rel(sg.newtemp, so.newtemp), "rho": rel(sg.f_rho, so.f_rho),
-             "x": rel(sg.tr_x, so.tr_x[lo:hi]), "Tm": rel(sg.cols[O.TR_TMP], so.tr_f[lo:hi, O.TR_TMP]),
+             "x": float(np.linalg.norm(gx - so.tr_x[all_ids]) / np.linalg.norm(so.tr_x)),
+             "Tm": float(np.linalg.norm(gT - so.tr_f[all_ids, O.TR_TMP]) / np.linalg.norm(so.tr_f[:, O.TR_TMP])),
              "count": int(np.abs(sg.count.cpu().numpy() - so.count).max())}
-        print("step", it + 1, "world", world, sg.stats, {k: ("%.1e" % v if k != "count" else v) for k, v in e.items()}, flush=True)
+        print("step", it + 1, "world", world, ownership, sg.stats, {k: ("%.1e" % v if k != "count" else v) for k, v in e.items()}, flush=True)
         ok = ok and all(e[k] < 1e-8 for k in ("vz", "vx", "P", "T")) and e["x"] < 1e-10 and e["rho"] < 1e-10
 flag = torch.tensor([1 if ok else 0], device="cuda")
-dist.broadcast(flag, 0)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)        # rank 0 holds the parity verdict, every rank its ownership check
+ok = bool(flag.item())
 dist.destroy_process_group()
 if rank == 0:
     print("MULTI_GPU_PARITY", "OK" if ok else "FAILED")

@@ -14,13 +14,14 @@ from conftest import ROOT
 
 
 @pytest.mark.gpu
-def test_two_gpu_timestep_matches_oracle():
+@pytest.mark.parametrize("ownership,port", [("index", 29533), ("slab", 29535)])
+def test_two_gpu_timestep_matches_oracle(ownership, port):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533",
-           os.path.join(ROOT, "scripts", "multi_gpu_driver_check.py"), "64", "3"]
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "scripts", "multi_gpu_driver_check.py"), "64", "3", ownership]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0 and "MULTI_GPU_PARITY OK" in r.stdout
