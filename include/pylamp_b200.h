@@ -121,6 +121,10 @@ int plb_fence(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, d
  * d_count[(nz-1)*(nxx-1)] int64.  d_kelem may be NULL. */
 int plb_cell_index_count(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, int nxx,
                          double Lz, double Lx, long long* d_kelem, long long* d_count);
+/* plb_fence followed by plb_cell_index_count in one pass over d_tr_x (pylamp2.py:558-572 then
+ * :588-593; identical results, the coordinates are read once). */
+int plb_fence_count(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps, int nz,
+                    int nxx, long long* d_kelem, long long* d_count);
 /* marker property update, pylamp2.py:291-303 (columns of tr_f) */
 int plb_update_properties(plb_ctx* ctx, long long M, int tdep_rho, int tdep_eta, double Tref,
                           double etamin, double etamax, double gasr, const double* d_T,

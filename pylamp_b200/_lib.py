@@ -41,6 +41,7 @@ _PROTOS = {
     "plb_rk4": (I, [VP, LL, VP, VP, VP, VP, I, VP, I, I, D, D, D, D, D, VP, VP]),
     "plb_fence": (I, [VP, LL, VP, D, D, D]),
     "plb_cell_index_count": (I, [VP, LL, VP, I, I, D, D, VP, VP]),
+    "plb_fence_count": (I, [VP, LL, VP, D, D, D, I, I, VP, VP]),
     "plb_update_properties": (I, [VP, LL, I, I, D, D, D, D, VP, VP, VP, VP, VP, VP, VP]),
     "plb_centre_velocities": (I, [VP, I, I, I, VP, VP, IP, I, VP, VP]),
     "plb_subgrid_stage1": (I, [VP, LL, D, D, D, VP, VP, VP, VP, VP, VP, VP]),

@@ -81,7 +81,7 @@ __global__ void k_axis_recip(int n, const double* __restrict__ ax, double* __res
     if (i >= n) return;
     const double v = (i < n - 1) ? 1.0 / (ax[i + 1] - ax[i]) : 0.0;
     r[i] = v;
-    tab[i] = make_double2(ax[i], v);
+    if (tab) tab[i] = make_double2(ax[i], v);
 }
 
 // (A shared-memory transpose variant of this reduction was measured slower: 50 vs 37 ms per 4096^2
@@ -568,9 +568,11 @@ k_grid2trac(long long M, const double2* __restrict__ trx, int method, G2TGrid g,
 // reciprocal cell sizes serve the local coordinates and both Meyer-Jenny coefficients, and the cell
 // lookup multiplies by (n-1)/len instead of dividing (a marker sitting exactly on a cell face may
 // then be assigned to the neighbouring cell, where the continuous interpolant has the same value).
-// fp64 division is what bounds this kernel: 2 per stage instead of 6.
+// fp64 division is what bounds this kernel: the two reciprocals come from per-axis tables filled
+// by k_axis_recip with the same IEEE division (bit-identical results, no division per stage).
 __device__ __forceinline__ void vel_at(const double* __restrict__ fz, const double* __restrict__ fx,
-                                       const G2TGrid& g, double sz, double sx, double z, double x,
+                                       const G2TGrid& g, const double* __restrict__ riz,
+                                       const double* __restrict__ rix, double sz, double sx, double z, double x,
                                        double& vz, double& vx) {
     long long ie = (long long)floor((z - g.z0) * sz), je = (long long)floor((x - g.x0) * sx);
     if (ie < 0 || ie > g.nz - 2 || je < 0 || je > g.nxx - 2) {
@@ -579,7 +581,7 @@ __device__ __forceinline__ void vel_at(const double* __restrict__ fz, const doub
     }
     const double gz0 = g.gz[ie], gz1 = g.gz[ie + 1], gx0 = g.gx[je], gx1 = g.gx[je + 1];
     const double hz = gz1 - gz0, hx = gx1 - gx0;
-    const double rz = 1.0 / hz, rx = 1.0 / hx;
+    const double rz = riz[ie], rx = rix[je];          // 1/hz, 1/hx
     const double dzn = (z - gz0) * rz, dxn = (x - gx0) * rx;
     const double* pz = fz + ie * g.ld + je;
     const double* px = fx + ie * g.ld + je;
@@ -594,8 +596,8 @@ __device__ __forceinline__ void vel_at(const double* __restrict__ fz, const doub
 
 __global__ void __launch_bounds__(256)
 k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ fz,
-      const double* __restrict__ fx, G2TGrid g, double dt, double2* __restrict__ xout,
-      double2* __restrict__ vout) {
+      const double* __restrict__ fx, G2TGrid g, const double* __restrict__ riz,
+      const double* __restrict__ rix, double dt, double2* __restrict__ xout, double2* __restrict__ vout) {
     const double hdt = 0.5 * dt;
     const double sixth_dt = (1.0 / 6.0) * dt;
     const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
@@ -604,10 +606,10 @@ k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ f
          m += (long long)gridDim.x * blockDim.x) {
         double2 p = trx[m];
         double k1z, k1x, k2z, k2x, k3z, k3x, k4z, k4x;
-        vel_at(fz, fx, g, sz, sx, p.x, p.y, k1z, k1x);
-        vel_at(fz, fx, g, sz, sx, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
-        vel_at(fz, fx, g, sz, sx, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
-        vel_at(fz, fx, g, sz, sx, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
+        vel_at(fz, fx, g, riz, rix, sz, sx, p.x, p.y, k1z, k1x);
+        vel_at(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
+        vel_at(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
+        vel_at(fz, fx, g, riz, rix, sz, sx, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
         double2 q;
         q.x = p.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // :385 (unweighted sum)
         q.y = p.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
@@ -646,6 +648,29 @@ k_cell_index_count(long long M, const double2* __restrict__ trx, int nz, int nxx
          m += (long long)gridDim.x * blockDim.x) {
         double2 p = trx[m];
         // pylamp2.py:588-589: floor((n-1)*x/L) -- multiply, then divide
+        long long ie = (long long)floor(__ddiv_rn(__dmul_rn((double)(nz - 1), p.x), Lz));
+        long long je = (long long)floor(__ddiv_rn(__dmul_rn((double)(nxx - 1), p.y), Lx));
+        long long k = ie * (nxx - 1) + je;
+        if (kelem) kelem[m] = k;
+        if (count && k >= 0 && k < ncell) atomicAdd(count + k, 1ull);
+    }
+}
+
+// fence + cell index + per-cell count in one pass over the coordinates (same operations as k_fence
+// followed by k_cell_index_count: bit-identical results, one read of tr_x instead of two)
+__global__ void __launch_bounds__(256)
+k_fence_count(long long M, double2* __restrict__ trx, double Lz, double Lx, double eps, int nz, int nxx,
+              long long* __restrict__ kelem, unsigned long long* __restrict__ count) {
+    const long long ncell = (long long)(nz - 1) * (nxx - 1);
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
+         m += (long long)gridDim.x * blockDim.x) {
+        double2 p = trx[m];
+        bool ch = false;
+        if (p.x <= 0) p.x = eps, ch = true;
+        if (p.x >= Lz) p.x = Lz - eps, ch = true;
+        if (p.y <= 0) p.y = eps, ch = true;
+        if (p.y >= Lx) p.y = Lx - eps, ch = true;
+        if (ch) trx[m] = p;
         long long ie = (long long)floor(__ddiv_rn(__dmul_rn((double)(nz - 1), p.x), Lz));
         long long je = (long long)floor(__ddiv_rn(__dmul_rn((double)(nxx - 1), p.y), Lx));
         long long k = ie * (nxx - 1) + je;
@@ -922,9 +947,17 @@ int plb_rk4(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_vz_
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     G2TGrid g = {d_gc_z, d_gc_x, nzc, nxc, ld, z0, zlen, x0, xlen};
     if (M > 0) {
+        // reciprocal cell sizes of both axes, once per call instead of twice per marker and stage
+        if (plb_ws_reserve(ctx, (size_t)(nzc + nxc) * sizeof(double))) return 2;
+        double* recip = (double*)ctx->ws;
+        k_axis_recip<<<plb_blocks(nzc, 256), 256, 0, ctx->stream>>>(nzc, d_gc_z, recip, nullptr);
+        PLB_LAUNCHED(ctx);
+        k_axis_recip<<<plb_blocks(nxc, 256), 256, 0, ctx->stream>>>(nxc, d_gc_x, recip + nzc, nullptr);
+        PLB_LAUNCHED(ctx);
         plb_prof_scope prof_(ctx, PLB_K_RK4, (d_v_out ? 48.0 : 32.0) * (double)M);
         k_rk4<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
-            M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, dt, (double2*)d_x_out, (double2*)d_v_out);
+            M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, recip, recip + nzc, dt, (double2*)d_x_out,
+            (double2*)d_v_out);
         PLB_LAUNCHED(ctx);
     }
     return 0;
@@ -950,6 +983,21 @@ int plb_cell_index_count(plb_ctx* ctx, long long M, const double* d_tr_x, int nz
     if (M > 0) {
         k_cell_index_count<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
             M, (const double2*)d_tr_x, nz, nxx, Lz, Lx, d_kelem, (unsigned long long*)d_count);
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+int plb_fence_count(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps, int nz,
+                    int nxx, long long* d_kelem, long long* d_count) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d_count)
+        PLB_CUDA(ctx, cudaMemsetAsync(d_count, 0, (size_t)(nz - 1) * (nxx - 1) * sizeof(long long),
+                                      ctx->stream));
+    if (M > 0) {
+        k_fence_count<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(
+            M, (double2*)d_tr_x, Lz, Lx, eps, nz, nxx, d_kelem, (unsigned long long*)d_count);
         PLB_LAUNCHED(ctx);
     }
     return 0;

@@ -248,12 +248,15 @@ def timestep(s, o, want_kelem=True, phases=False):
     # fence + per-cell count, pylamp2.py:558-593
     if not o.tracs_fence_enabled:
         raise NotImplementedError("marker deletion (fence disabled / FLOWTHRU): SURVEY.md §8f-1")
-    markers.fence(s.tr_x, s.L, EPS)
+    need_kelem = want_kelem or o.tracdens_min > 0
     if slab:
+        markers.fence(s.tr_x, s.L, EPS)
         # markers that crossed a slab boundary move to their new owner (positions are final here)
         s.stats["migrated"] = migrate.migrate(s)
         ph.mark("migrate")
-    s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=want_kelem or o.tracdens_min > 0)
+        s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=need_kelem)
+    else:
+        s.kelem, s.count = markers.fence_count(s.tr_x, nx, s.L, EPS, want_kelem=need_kelem)
     if o.tracdens_min > 0:                                                          # :594-633
         if world > 1 and not slab:
             raise NotImplementedError("marker injection needs marker_ownership='slab' on several ranks "

@@ -31,6 +31,18 @@ def fence(tr_x, L, eps=EPS):
     _ctx(tr_x).call("plb_fence", tr_x.shape[0], tr_x.data_ptr(), float(L[IZ]), float(L[IX]), float(eps))
 
 
+def fence_count(tr_x, nx, L, eps=EPS, want_kelem=True):
+    """`fence` then `cell_index_count` in one pass over the coordinates (pylamp2.py:558-572, :588-593)."""
+    ctx = _ctx(tr_x)
+    M = tr_x.shape[0]
+    nz, nxx = int(nx[IZ]), int(nx[IX])
+    kelem = torch.empty(M, dtype=torch.int64, device=tr_x.device) if want_kelem else None
+    count = torch.empty((nz - 1) * (nxx - 1), dtype=torch.int64, device=tr_x.device)
+    ctx.call("plb_fence_count", M, tr_x.data_ptr(), float(L[IZ]), float(L[IX]), float(eps), nz, nxx,
+             kelem.data_ptr() if want_kelem else None, count.data_ptr())
+    return kelem, count
+
+
 def update_properties(T, rho0, alpha, Ea, eta0, tdep_rho, tdep_eta, Tref, etamin, etamax,
                       rho_out=None, eta_out=None):
     """rho(T), eta(T) on markers -- pylamp2.py:291-303."""

@@ -284,3 +284,23 @@ def test_trac2grid_chunk_kernel_log_of_zero(T):
     for variant in (0, 1):
         out = _t2g_dev(T, x, [eta], [6], grid, nx, variant)
         assert np.allclose(out[0], ref[0], rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_fence_count_fused_bit_exact():
+    """plb_fence_count == plb_fence followed by plb_cell_index_count == the oracle, bit for bit."""
+    from pylamp_b200 import markers
+    rng = np.random.default_rng(21)
+    nx, L = [201, 41], [1.0, 0.2]
+    x = (rng.random((400000, 2)) * 1.1 - 0.05) * L          # some markers beyond every wall
+    x[:5] = 0.0
+    x[5:10] = L
+    ref = x.copy()
+    O.fence(ref, np.zeros((x.shape[0], O.NFTRAC)), L, [1, 1, 1, 1])
+    kelem, count = O.cell_index_count(ref, nx, L)
+    xd = torch.as_tensor(x).cuda()
+    kd, cd = markers.fence_count(xd, nx, L)
+    assert np.array_equal(xd.cpu().numpy(), ref)
+    assert np.array_equal(kd.cpu().numpy(), kelem) and np.array_equal(cd.cpu().numpy(), count)
+    xd2 = torch.as_tensor(x).cuda()
+    _, cd2 = markers.fence_count(xd2, nx, L, want_kelem=False)
+    assert np.array_equal(cd2.cpu().numpy(), count)
