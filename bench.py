@@ -222,7 +222,7 @@ def run_b200(args):
         traffic = None
         try:        # DRAM bytes per launch from the committed ncu --set full capture (same kernel, same grid)
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = "k_cheb" if dom == 0 else None
+            key = {0: "k_cheb", 4: "k_t2g"}.get(dom)
             if key and tr[key]["grid_nodes"] == list(nx) and world == 1:
                 traffic = tr[key]["dram_bytes_per_launch"]
         except Exception:
