@@ -55,7 +55,9 @@ const char* plb_last_error(plb_ctx* ctx);
 long long plb_launch_count(plb_ctx* ctx);
 /* tuning knobs that never change results beyond summation order.  "t2g_variant": 1 (default) =
  * plb_trac2grid uses the wide-load chunk kernel when every scheme is weighted and the arrays are
- * 32-byte aligned; 0 = always the generic scatter kernel. */
+ * 32-byte aligned; 2 = the same kernel, additionally combining the chunks' first runs across the
+ * lanes of a warp (fewer atomics on staggered targets and displaced clouds); 0 = always the generic
+ * scatter kernel. */
 int plb_ctx_set_param(plb_ctx* ctx, const char* name, double value);
 const char* plb_version(void);
 /* per-kernel-class timing with CUDA event pairs recorded around the launches on the context's

@@ -69,6 +69,7 @@ struct T2GArgs {
     const double* rix;
     const double2* tz;             // {axz[i], riz[i]} (one 16-byte load per marker and axis)
     const double2* tx;
+    int merge_first;               // chunk kernel: combine the first runs across lanes too (t2g_variant 2)
     int nze, nxe;
     double z0, zlen, x0, xlen;
     double sz, sx;                 // (nze-1)/zlen, (nxe-1)/xlen
@@ -302,11 +303,50 @@ __device__ __forceinline__ void t2g_single(const T2GArgs& a, const double2* __re
     }
 }
 
-// sums of one quantity over the chunk's last run (u >= s) and first run (u < e), warp-level
-// combination of the last runs, atomics
+// the first / last run of a lane's chunk as seen by the warp-level segmented reduction: head of a run
+// of lanes with the same cell, last lane of that run, longest remaining run in the warp
+struct RunInfo {
+    int run_end, span;
+    bool emit;
+};
+
+__device__ __forceinline__ RunInfo t2g_runs(int cell, bool has, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int prev = __shfl_up_sync(full, cell, 1);
+    const bool head = (lane == 0) || (prev != cell);
+    const unsigned heads = __ballot_sync(full, head);
+    const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
+    RunInfo r;
+    r.run_end = after ? lane + __ffs(after) - 1 : 31;
+    r.span = __reduce_max_sync(full, r.run_end - lane);
+    r.emit = head && has;
+    return r;
+}
+
+// segmented reduction of the four corner sums over runs of lanes, then one atomic per corner by the head
+__device__ __forceinline__ void t2g_reduce_emit(double* __restrict__ plane, double (&S)[4], const RunInfo& r,
+                                                int lane, int cell, int nxe) {
+    for (int o = 1; o <= r.span; o <<= 1) {
+        const bool take = lane + o <= r.run_end;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double t = __shfl_down_sync(0xffffffffu, S[c], o);
+            if (take) S[c] += t;
+        }
+    }
+    if (r.emit) {
+        const int off[4] = {0, nxe, 1, nxe + 1};
+#pragma unroll
+        for (int c = 0; c < 4; c++) atomicAdd(plane + (cell + off[c]), S[c]);
+    }
+}
+
+// sums of one quantity over the chunk's last run (u >= s) and first run (u < e); the last runs are
+// combined across the lanes of the warp, the first runs too when `merge` is set (otherwise every
+// lane adds its own first run)
 __device__ __forceinline__ void t2g_chunk_quantity(double* __restrict__ plane, const double (&v)[4],
                                                    const double (&wu)[4][4], int s, int e, int lane,
-                                                   int run_end, int span, bool emit, bool any_first,
+                                                   const RunInfo& rl, const RunInfo& rf, bool any_first, bool merge,
                                                    int cell_last, int cell_first, int nxe) {
     double L[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -315,19 +355,7 @@ __device__ __forceinline__ void t2g_chunk_quantity(double* __restrict__ plane, c
 #pragma unroll
         for (int c = 0; c < 4; c++) L[c] = fma(vl, wu[u][c], L[c]);
     }
-    const int off[4] = {0, nxe, 1, nxe + 1};
-    for (int o = 1; o <= span; o <<= 1) {          // segmented reduction of the four corners together
-        const bool take = lane + o <= run_end;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const double t = __shfl_down_sync(0xffffffffu, L[c], o);
-            if (take) L[c] += t;
-        }
-    }
-    if (emit) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) atomicAdd(plane + (cell_last + off[c]), L[c]);
-    }
+    t2g_reduce_emit(plane, L, rl, lane, cell_last, nxe);
     if (any_first) {
         double F[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -336,14 +364,18 @@ __device__ __forceinline__ void t2g_chunk_quantity(double* __restrict__ plane, c
 #pragma unroll
             for (int c = 0; c < 4; c++) F[c] = fma(vf, wu[u][c], F[c]);
         }
-        if (e > 0) {
+        if (merge) {
+            t2g_reduce_emit(plane, F, rf, lane, cell_first, nxe);
+        } else if (e > 0) {
+            const int off[4] = {0, nxe, 1, nxe + 1};
 #pragma unroll
             for (int c = 0; c < 4; c++) atomicAdd(plane + (cell_first + off[c]), F[c]);
         }
     }
 }
 
-__global__ void __launch_bounds__(256)
+template <bool MERGE>
+__global__ void __launch_bounds__(256, 3)
 k_t2g_chunk(long long nchunk, const double2* __restrict__ trx, T2GArgs a) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -404,20 +436,17 @@ k_t2g_chunk(long long nchunk, const double2* __restrict__ trx, T2GArgs a) {
         const bool any_first = __any_sync(full, ok && e > 0);
         const bool any_mid = __any_sync(full, live && s > e);
         const int ef = ok ? e : 0;                        // first run only exists for clean chunks
-        const int prev = __shfl_up_sync(full, cell_last, 1);
-        const bool head = (lane == 0) || (prev != cell_last);
-        const unsigned heads = __ballot_sync(full, head);
-        const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
-        const int run_end = after ? lane + __ffs(after) - 1 : 31;
-        const int span = __reduce_max_sync(full, run_end - lane);
-        const bool emit = head && ok;
+        const int cell_first = ef > 0 ? cell[0] : -1 - lane;
+        constexpr bool merge = MERGE;
+        const RunInfo rl = t2g_runs(cell_last, ok, lane);
+        RunInfo rf = {lane, 0, false};
+        if (any_first && merge) rf = t2g_runs(cell_first, ef > 0, lane);
         // the fields one after the other (rolled: one copy of the code), the next field's values in flight
         double vn[4] = {0, 0, 0, 0};
         if (ok) ld256(a.f[0] + 4 * ch, vn[0], vn[1], vn[2], vn[3]);
         {
             const double one[4] = {1, 1, 1, 1};
-            t2g_chunk_quantity(a.wsum, one, wu, s, ef, lane, run_end, span, emit, any_first, cell_last, cell[0],
-                               a.nxe);
+            t2g_chunk_quantity(a.wsum, one, wu, s, ef, lane, rl, rf, any_first, merge, cell_last, cell_first, a.nxe);
         }
 #pragma unroll 1
         for (int f = 0; f < a.k; f++) {
@@ -427,8 +456,7 @@ k_t2g_chunk(long long nchunk, const double2* __restrict__ trx, T2GArgs a) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) v[u] = log(v[u]);
             }
-            t2g_chunk_quantity(a.acc[f], v, wu, s, ef, lane, run_end, span, emit, any_first, cell_last, cell[0],
-                               a.nxe);
+            t2g_chunk_quantity(a.acc[f], v, wu, s, ef, lane, rl, rf, any_first, merge, cell_last, cell_first, a.nxe);
         }
         if (any_mid) {
 #pragma unroll 1
@@ -783,7 +811,8 @@ void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& 
 
 void launch_chunk(plb_ctx* ctx, long long nchunk, const double2* x, const T2GArgs& a) {
     int grid = plb_grid_for(ctx, nchunk, 256, 6);     // 80 registers: 3 resident CTAs per SM, two full waves
-    k_t2g_chunk<<<grid, 256, 0, ctx->stream>>>(nchunk, x, a);
+    if (a.merge_first) k_t2g_chunk<true><<<grid, 256, 0, ctx->stream>>>(nchunk, x, a);
+    else k_t2g_chunk<false><<<grid, 256, 0, ctx->stream>>>(nchunk, x, a);
 }
 
 template <int K>
@@ -869,7 +898,8 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
     a.riz = recip, a.rix = recip + nze;
     a.tz = tab, a.tx = tab + nze;
     // the chunk kernel needs weighted schemes only, 32-bit plane indices and 32-byte aligned arrays
-    bool chunked = ctx->t2g_variant == 1 && !any_c && M >= 4 && plane < ((size_t)1 << 31) &&
+    a.merge_first = ctx->t2g_variant == 2;
+    bool chunked = ctx->t2g_variant >= 1 && !any_c && M >= 4 && plane < ((size_t)1 << 31) &&
                    ((uintptr_t)d_tr_x & 31) == 0;
     for (int f = 0; f < k; f++) chunked = chunked && ((uintptr_t)h_fields[f] & 31) == 0;
     a.sz = (double)(nze - 1) / zlen, a.sx = (double)(nxe - 1) / xlen;

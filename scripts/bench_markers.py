@@ -46,7 +46,7 @@ moved = (tr_x + 3.3 * dz * disp).clamp_(2.0 ** -10, L[0] - 2.0 ** -10).contiguou
 del disp, zn, xn
 for name, x in (("ordered", tr_x), ("displaced", moved)):
     mm = T.marker_minmax(x, ctx)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.set_param("t2g_variant", variant)
         nodes = lambda: T.trac2grid_device(ctx, x, [cols[k] for k in (TR_RHO, TR_ETA, TR_HCP, TR_TMP, TR_IHT, TR_MAT)],
                                            [5, 6, 5, 5, 5, 5], grid, out6, mm)

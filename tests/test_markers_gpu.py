@@ -212,7 +212,8 @@ def _t2g_dev(T, x, cols, schemes, grid, nx, variant, view_offset=0):
 @pytest.mark.parametrize("ragged", [0, 1, 2, 3])
 def test_trac2grid_chunk_kernel_matches_generic_and_oracle(T, cloud, ragged):
     """The wide-load chunk kernel (t2g_variant 1: two aggregates per 4-marker chunk, one-marker path
-    for the rest) against the generic scatter kernel and the oracle, on clouds that exercise every
+    for the rest; t2g_variant 2: the first runs are combined across lanes as well) and the generic
+    scatter kernel against the oracle, on clouds that exercise every
     path: unordered (mostly one-marker path), cell-ordered (single runs), cell-ordered then displaced
     (two runs per chunk), markers beyond the grid (ghost extension), marker counts not divisible by
     4 (tail launch), all four staggered targets, arithmetic and geometric weighted means."""
@@ -239,13 +240,11 @@ def test_trac2grid_chunk_kernel_matches_generic_and_oracle(T, cloud, ragged):
     for gr in ([grid[0], grid[1]], [gridmp[0], gridmp[1]], [gridmp[0], grid[1]], [grid[0], gridmp[1]]):
         ref = [np.zeros(nx) for _ in cols]
         O.trac2grid(x, f, None, gr, ref, nx, avgscheme=schemes)
-        chunk = _t2g_dev(T, x, cols, schemes, gr, nx, 1)
-        generic = _t2g_dev(T, x, cols, schemes, gr, nx, 0)
-        for a, b, r in zip(chunk, generic, ref):
-            assert np.array_equal(np.isnan(a), np.isnan(r)) and np.array_equal(np.isnan(b), np.isnan(r))
-            # the arithmetic mean of values in (-1,1) can cancel: absolute floor of a few ulps of 1
-            assert np.allclose(a, r, rtol=1e-12, atol=1e-14, equal_nan=True)
-            assert np.allclose(b, r, rtol=1e-12, atol=1e-14, equal_nan=True)
+        for variant in (1, 2, 0):          # chunk kernel, chunk kernel with merged first runs, generic kernel
+            for a, r in zip(_t2g_dev(T, x, cols, schemes, gr, nx, variant), ref):
+                assert np.array_equal(np.isnan(a), np.isnan(r)), variant
+                # the arithmetic mean of values in (-1,1) can cancel: absolute floor of a few ulps of 1
+                assert np.allclose(a, r, rtol=1e-12, atol=1e-14, equal_nan=True), variant
 
 
 def test_trac2grid_chunk_kernel_falls_back_on_unaligned_views_and_counts(T):
@@ -261,7 +260,7 @@ def test_trac2grid_chunk_kernel_falls_back_on_unaligned_views_and_counts(T):
     for schemes, off in (([5, 6], 1), ([5, 6], 3), ([1, 2], 0), ([5, 2], 0)):
         ref = [np.zeros(nx) for _ in cols]
         O.trac2grid(x, f, None, grid, ref, nx, avgscheme=schemes)
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             out = _t2g_dev(T, x, cols, schemes, grid, nx, variant, view_offset=off)
             for a, r in zip(out, ref):
                 assert np.allclose(a, r, rtol=1e-12, atol=0, equal_nan=True)
@@ -281,7 +280,7 @@ def test_trac2grid_chunk_kernel_log_of_zero(T):
     ref = [np.zeros(nx)]
     with np.errstate(divide="ignore", invalid="ignore"):
         O.trac2grid(x, eta[:, None], None, grid, ref, nx, avgscheme=[6])
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         out = _t2g_dev(T, x, [eta], [6], grid, nx, variant)
         assert np.allclose(out[0], ref[0], rtol=1e-12, atol=0, equal_nan=True)
 

@@ -12,7 +12,7 @@ from oracle import pylamp_oracle as O
 from pylamp_b200 import setups
 
 
-def emulate_chunk_kernel(x, f, axz, axx):
+def emulate_chunk_kernel(x, f, axz, axx, merge_first=False):
     """Raw sums (wsum, fsum) over the extended axes axz/axx, computed the way the kernel does."""
     nze, nxe = len(axz), len(axx)
     z0, x0 = axz[0], axx[0]
@@ -73,40 +73,50 @@ def emulate_chunk_kernel(x, f, axz, axx):
                         e = 2
                     if e == 2 and s > 2 and cell[2] == cell[0]:
                         e = 3
-            lanes.append(dict(ch=ch, live=live, ok=ok, cell=cell, wu=wu, s=s, e=e, ef=e if ok else 0,
-                              cell_last=cell[3] if ok else -1 - lane))
-        cl = [d["cell_last"] for d in lanes]
-        head = [lane == 0 or cl[lane - 1] != cl[lane] for lane in range(32)]
-        run_end = []
-        for lane in range(32):
-            nxt = [j for j in range(lane + 1, 32) if head[j]]
-            run_end.append(nxt[0] - 1 if nxt else 31)
-        span = max(run_end[lane] - lane for lane in range(32))
+            ef = e if ok else 0
+            lanes.append(dict(ch=ch, live=live, ok=ok, cell=cell, wu=wu, s=s, e=e, ef=ef,
+                              cell_last=cell[3] if ok else -1 - lane, cell_first=cell[0] if ef > 0 else -1 - lane))
+
+        def runs(cells):
+            head = [lane == 0 or cells[lane - 1] != cells[lane] for lane in range(32)]
+            run_end = []
+            for lane in range(32):
+                nxt = [j for j in range(lane + 1, 32) if head[j]]
+                run_end.append(nxt[0] - 1 if nxt else 31)
+            return head, run_end, max(run_end[lane] - lane for lane in range(32))
+
+        def seg_reduce(S, run_end, span):
+            o = 1
+            while o <= span:                       # __shfl_down_sync reads the pre-step values of all lanes
+                t = np.vstack([S[o:], np.zeros((o, 4))])
+                for lane in range(32):
+                    if lane + o <= run_end[lane]:
+                        S[lane] += t[lane]
+                o <<= 1
+
+        head, run_end, span = runs([d["cell_last"] for d in lanes])
+        head_f, run_end_f, span_f = runs([d["cell_first"] for d in lanes])
         for plane, vals in ((wsum, None), (fsum, f)):
-            L = np.zeros((32, 4))
+            L, F = np.zeros((32, 4)), np.zeros((32, 4))
             for lane, d in enumerate(lanes):
                 v = np.ones(4) if vals is None else (vals[4 * d["ch"]:4 * d["ch"] + 4] if d["ok"] else np.zeros(4))
                 for u in range(4):
                     if u >= d["s"]:
                         L[lane] += v[u] * d["wu"][u]
-                F = np.zeros(4)
                 for u in range(3):
                     if u < d["ef"]:
-                        F += v[u] * d["wu"][u]
-                if d["ef"] > 0:
-                    plane[d["cell"][0] + off] += F
-                    stats["first"] += plane is wsum
-            o = 1
-            while o <= span:                       # __shfl_down_sync reads the pre-step values of all lanes
-                t = np.vstack([L[o:], np.zeros((o, 4))])
-                for lane in range(32):
-                    if lane + o <= run_end[lane]:
-                        L[lane] += t[lane]
-                o <<= 1
+                        F[lane] += v[u] * d["wu"][u]
+            seg_reduce(L, run_end, span)
             for lane, d in enumerate(lanes):
                 if head[lane] and d["ok"]:
                     plane[d["cell_last"] + off] += L[lane]
                     stats["merged_lanes"] += (plane is wsum) * (run_end[lane] - lane)
+            if merge_first:
+                seg_reduce(F, run_end_f, span_f)
+            for lane, d in enumerate(lanes):
+                if d["ef"] > 0 and (head_f[lane] or not merge_first):
+                    plane[d["cell_first"] + off] += F[lane]
+                    stats["first"] += plane is wsum
         for d in lanes:
             for u in range(4):
                 if d["live"] and d["e"] <= u < d["s"]:
@@ -116,8 +126,9 @@ def emulate_chunk_kernel(x, f, axz, axx):
     return wsum.reshape(nze, nxe), fsum.reshape(nze, nxe), stats
 
 
+@pytest.mark.parametrize("merge_first", [False, True])
 @pytest.mark.parametrize("cloud", ["random", "sorted", "drifted", "outside", "ragged"])
-def test_chunk_aggregation_adds_every_marker_once(cloud):
+def test_chunk_aggregation_adds_every_marker_once(cloud, merge_first):
     rng = np.random.default_rng(4)
     ncz, ncx, L = 10, 9, [1.0, 0.75]
     nx = [ncz + 1, ncx + 1]
@@ -139,7 +150,7 @@ def test_chunk_aggregation_adds_every_marker_once(cloud):
         if cloud == "outside":
             xs = xs + np.array([-0.4 * L[0] / ncz, 0.3 * L[1] / ncx])
             xs[7] = [-5.0, 0.1]          # outside even the extended axes: skipped, its chunk takes the one-marker path
-        wsum, fsum, stats = emulate_chunk_kernel(xs, f, axz, axx)
+        wsum, fsum, stats = emulate_chunk_kernel(xs, f, axz, axx, merge_first)
         # brute force: every marker added once
         nze, nxe = len(axz), len(axx)
         wref, fref = np.zeros((nze, nxe)), np.zeros((nze, nxe))
