@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 CLASS_NAMES = {0: "k_cheb (Chebyshev-Jacobi smoother sweep, finest level)",
                1: "k_stokes_op (coupled Stokes residual/apply)", 2: "k_multi_dot", 3: "k_multi_axpy2",
-               4: "k_t2g_scatter (trac2grid)", 5: "k_rk4", 6: "k_grid2trac",
+               4: "k_t2g_chunk (trac2grid scatter)", 5: "k_rk4", 6: "k_grid2trac",
                7: "coarse part of the V-cycle (levels >= 1, many launches)",
                8: "finest-level residual+restrict+prolong", 9: "k_precond_rhs", 10: "k_diff", 11: "marker misc"}
 SINGLE_KERNEL_CLASSES = (0, 1, 2, 3, 4, 5, 6, 9)

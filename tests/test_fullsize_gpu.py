@@ -113,7 +113,7 @@ def test_time_loop_conserves_markers_and_solves_the_system(big):
     divrel = float(div[1:-1, 1:-1].abs().max()) / scale
     print("full-size Stokes: |b-Ax|/|b| = %.2e, max|div v| dx/max|v| = %.2e, iterations %d" %
           (res, divrel, s.stats["stokes_iters"]))
-    assert res < 1e-6 and divrel < 1e-5
+    assert res < 1e-10 and divrel < 1e-10          # measured on B200: 4.4e-13 and 6.7e-14
 
 
 def test_operators_linear_and_steady_state(big):
