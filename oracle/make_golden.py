@@ -149,6 +149,36 @@ def kernel_vectors():
     print("kernels.npz:", len(out), "arrays")
 
 
+def fence_delete_vectors():
+    """The driver-inline fence / delete block (pylamp2.py:557-581) executed as it stands: the lines
+    are read from the reference checkout at generation time, dedented and run on crafted markers
+    (some beyond every wall), with the fence enabled and disabled."""
+    import textwrap
+    rt, rs, rd, rc = ref_shims.load()
+    lines = open(os.path.join(ref_shims.REFERENCE_DIR, "pylamp2.py")).read().split("\n")
+    assert "do not allow tracers to advect outside the domain" in lines[556] and "ntrac = ntrac - dntrac" in lines[580]
+    block = compile(textwrap.dedent("\n".join(lines[556:581])), "pylamp2.py:557-581", "exec")
+    rng = np.random.default_rng(17)
+    L = [1.0, 0.5]
+    M = 400
+    tr_x0 = (rng.random((M, 2)) * 1.3 - 0.15) * L
+    tr_x0[:4] = [[0.0, 0.1], [1.0, 0.2], [0.3, 0.0], [0.4, 0.5]]        # exactly on the walls
+    tr_f0 = rng.random((M, rc.NFTRAC))
+    tr_f0[:, rc.TR__ID] = np.arange(M)
+    vel0 = rng.random((M, 2))
+    out = {"fd_L": np.array(L), "fd_tr_x": tr_x0, "fd_tr_f": tr_f0, "fd_vel": vel0}
+    for tag, enabled in (("on", True), ("off", False)):
+        ns = {"np": np, "DIM": rc.DIM, "IX": rc.IX, "IZ": rc.IZ, "EPS": rc.EPS, "TR__ID": rc.TR__ID, "L": L,
+              "pylamp_stokes": rs, "bcstokes": [1, 1, 1, 1], "tracs_fence_enabled": enabled,
+              "tr_x": tr_x0.copy(), "tr_f": tr_f0.copy(), "trac_vel": vel0.copy(), "ntrac": M,
+              "pprint": lambda *a: None}
+        exec(block, ns)
+        out["fd_%s_tr_x" % tag], out["fd_%s_tr_f" % tag] = ns["tr_x"], ns["tr_f"]
+        out["fd_%s_vel" % tag], out["fd_%s_ntrac" % tag] = ns["trac_vel"], ns["ntrac"]
+    np.savez_compressed(os.path.join(OUT, "fence_delete.npz"), **out)
+    print("fence_delete.npz: kept", int(out["fd_on_ntrac"]), "(fence on),", int(out["fd_off_ntrac"]), "(fence off) of", M)
+
+
 def driver_run(name, nsteps, seed, subs, stride):
     cap = ref_shims.run_driver(nsteps, seed, substitutions=subs)
     out = {"seed": seed, "nsteps": nsteps, "stride": stride}
@@ -167,7 +197,11 @@ def driver_run(name, nsteps, seed, subs, stride):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--only-fence-delete" in sys.argv:
+        fence_delete_vectors()
+        sys.exit(0)
     kernel_vectors()
+    fence_delete_vectors()
     driver_run("c1_shipped", 3, SEED_C1, [], 997)
     driver_run("c1_noinject", 3, SEED_C1, C1_NOINJECT_SUBS, 997)
     driver_run("thermo_variant", 4, SEED_THERMO, THERMO_SUBS, 53)

@@ -611,6 +611,16 @@ def fence(tr_x, tr_f, L, bcstokes, enabled=True):
                 tr_f[idx, TR__ID] = -1
 
 
+def delete_outside(tr_x, tr_f, trac_vel):
+    """pylamp2.py:573-581: markers that `fence` flagged (TR__ID = -1: beyond a wall with the fence
+    disabled, or beyond a FLOWTHRU wall) are removed from tr_x, tr_f and trac_vel.
+    Returns (tr_x, tr_f, trac_vel, number removed)."""
+    outside = tr_f[:, TR__ID] < 0
+    idx = np.where(outside)[0]
+    return (np.delete(tr_x, idx, axis=0), np.delete(tr_f, idx, axis=0),
+            np.delete(trac_vel, idx, axis=0) if trac_vel is not None else None, int(np.sum(outside)))
+
+
 def cell_index_count(tr_x, nx, L):
     """Marker cell index and per-cell count, pylamp2.py:588-593.  BIT-EXACT parity item."""
     ielem = np.floor((nx[IZ] - 1) * tr_x[:, IZ] / L[IZ]).astype(np.int64)
@@ -757,6 +767,7 @@ def timestep(s, o, timers=None):
     s.trac_vel, s.tr_x = RK(tr_x, newgrid, vels, nx, tstep)                         # :550
     lap("advect")
     fence(s.tr_x, tr_f, s.L, o.bcstokes, o.tracs_fence_enabled)                      # :558-572
+    s.tr_x, s.tr_f, s.trac_vel, s.removed = delete_outside(s.tr_x, tr_f, s.trac_vel)  # :573-581
     s.kelem, s.count = cell_index_count(s.tr_x, nx, s.L)                            # :588-593
     lap("fence_count")
     return s

@@ -10,7 +10,8 @@ its inline NumPy steps then bounce every marker through host memory each call; t
 markers (SoA columns) and grid fields on the GPU and is what `bench.py` times.
 
 Mirrors oracle/pylamp_oracle.py's State/Options/timestep so that the parity tests read the same on
-both sides.  No injection / output here (SURVEY.md §8f "next" rows); NPROC = 1 per slab.
+both sides.  Marker injection (`tracdens_min > 0`), marker removal (`tracs_fence_enabled=False`) and the
+`.npz` output (`save_npz`) are the SURVEY.md §8f rows built so far.
 """
 import numpy as np
 import torch
@@ -245,11 +246,14 @@ def timestep(s, o, want_kelem=True, phases=False):
     s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep,
                                                 spare=slab)
     ph.mark("advect_rk4")
-    # fence + per-cell count, pylamp2.py:558-593
-    if not o.tracs_fence_enabled:
-        raise NotImplementedError("marker deletion (fence disabled / FLOWTHRU): SURVEY.md §8f-1")
+    # fence (or removal of the markers that left the box) + per-cell count, pylamp2.py:558-593
     need_kelem = want_kelem or o.tracdens_min > 0
-    if slab:
+    if not o.tracs_fence_enabled:
+        s.stats["removed"] = markers.delete_outside(s)                              # :563-581
+        if slab:
+            s.stats["migrated"] = migrate.migrate(s)
+        s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=need_kelem)
+    elif slab:
         markers.fence(s.tr_x, s.L, EPS)
         # markers that crossed a slab boundary move to their new owner (positions are final here)
         s.stats["migrated"] = migrate.migrate(s)

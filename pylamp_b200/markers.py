@@ -43,6 +43,40 @@ def fence_count(tr_x, nx, L, eps=EPS, want_kelem=True):
     return kelem, count
 
 
+def delete_outside(s):
+    """With the fence disabled the reference removes every marker that left the box
+    (pylamp2.py:563-581: x <= 0 or x >= L in either direction -> TR__ID = -1 -> np.delete on tr_x,
+    tr_f and trac_vel).  Same set of survivors here; the survivors of the tail are moved into the
+    holes instead of shifting every array (marker order is free: every kernel is order-independent).
+    Device-side torch plumbing (one pass over the coordinates, O(removed) entries moved).
+    Returns the number of markers removed."""
+    from .migrate import compaction_plan
+    x, L = s.tr_x, s.L
+    outside = (x[:, 0] <= 0) | (x[:, 0] >= L[IZ]) | (x[:, 1] <= 0) | (x[:, 1] >= L[IX])
+    holes = torch.nonzero(outside).flatten()
+    n = int(holes.numel())
+    if n == 0:
+        return 0
+    M_new, _, src, dst = compaction_plan(int(x.shape[0]), holes, outside, 0)
+
+    def cut(t):
+        if src.numel():
+            t.index_copy_(0, dst, t.index_select(0, src))
+        return t[:M_new]
+
+    s.tr_x = cut(s.tr_x)
+    seen, cols = {}, []
+    for c in s.cols:                      # columns may alias each other
+        key = c.data_ptr()
+        if key not in seen:
+            seen[key] = cut(c)
+        cols.append(seen[key])
+    s.cols = cols
+    if getattr(s, "trac_vel", None) is not None:
+        s.trac_vel = cut(s.trac_vel)
+    return n
+
+
 def update_properties(T, rho0, alpha, Ea, eta0, tdep_rho, tdep_eta, Tref, etamin, etamax,
                       rho_out=None, eta_out=None):
     """rho(T), eta(T) on markers -- pylamp2.py:291-303."""

@@ -105,3 +105,30 @@ def test_inject_markers_logic_on_cpu_tensors():
     k_ref, c_ref = O.cell_index_count(so.tr_x, nx, L)
     k_new, c_new = O.cell_index_count(s.tr_x.numpy(), nx, L)
     assert np.array_equal(c_new, c_ref) and np.array_equal(k_new[M:], k_ref[M:])
+
+
+def test_delete_outside_logic_on_cpu_tensors():
+    """markers.delete_outside (fence disabled: markers beyond a wall are removed, pylamp2.py:563-581) is
+    tensor logic: on CPU tensors it must keep exactly the markers the reference's block keeps (golden
+    vectors of that block), whatever their order, with aliased columns still aliased."""
+    import os
+    import types
+    import torch
+    from conftest import GOLDEN
+    from pylamp_b200 import markers
+    g = np.load(os.path.join(GOLDEN, "fence_delete.npz"))
+    x0, f0, v0 = g["fd_tr_x"], g["fd_tr_f"], g["fd_vel"]
+    cols = [torch.as_tensor(np.ascontiguousarray(f0[:, k])) for k in range(O.NFTRAC)]
+    cols[O.TR_MRK] = cols[O.TR_IHT]                                   # aliased pair
+    s = types.SimpleNamespace(L=list(g["fd_L"]), tr_x=torch.as_tensor(x0.copy()), cols=cols,
+                              trac_vel=torch.as_tensor(v0.copy()))
+    n = markers.delete_outside(s)
+    want_x, want_f, want_v = g["fd_off_tr_x"], g["fd_off_tr_f"].copy(), g["fd_off_vel"]
+    want_f[:, O.TR_MRK] = want_f[:, O.TR_IHT]
+    assert n == x0.shape[0] - want_x.shape[0] and s.tr_x.shape[0] == want_x.shape[0]
+    got_f = np.stack([c.numpy() for c in s.cols], axis=1)
+    order = np.argsort(got_f[:, O.TR__ID])
+    assert np.array_equal(got_f[order], want_f) and np.array_equal(s.tr_x.numpy()[order], want_x)
+    assert np.array_equal(s.trac_vel.numpy()[order], want_v)
+    assert s.cols[O.TR_MRK].data_ptr() == s.cols[O.TR_IHT].data_ptr()
+    assert markers.delete_outside(s) == 0                             # idempotent
