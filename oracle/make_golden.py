@@ -31,6 +31,8 @@ THERMO_SUBS = [
     ("bcstokes = [[]] * 4", "bcstokes = [1, 1, 1, 1]"),
 ]
 C1_NOINJECT_SUBS = [("tracdens_min = 25 ", "tracdens_min = 0 ")]
+# free-surface stabilisation with the dynamic time step (re-solve loop pylamp2.py:387-405)
+C1_SURFSTAB_SUBS = C1_NOINJECT_SUBS + [("surface_stabilization = False ", "surface_stabilization = True ")]
 
 
 def grids(nx, L):
@@ -200,8 +202,12 @@ if __name__ == "__main__":
     if "--only-fence-delete" in sys.argv:
         fence_delete_vectors()
         sys.exit(0)
+    if "--only-surfstab" in sys.argv:
+        driver_run("c1_surfstab", 3, SEED_C1, C1_SURFSTAB_SUBS, 997)
+        sys.exit(0)
     kernel_vectors()
     fence_delete_vectors()
     driver_run("c1_shipped", 3, SEED_C1, [], 997)
     driver_run("c1_noinject", 3, SEED_C1, C1_NOINJECT_SUBS, 997)
     driver_run("thermo_variant", 4, SEED_THERMO, THERMO_SUBS, 53)
+    driver_run("c1_surfstab", 3, SEED_C1, C1_SURFSTAB_SUBS, 997)

@@ -663,6 +663,9 @@ class Options:
         self.etamax = 1e23
         self.Tref = 1623
         self.tracs_fence_enabled = True
+        self.surface_stabilization = False      # pylamp2.py:71-73
+        self.surfstab_theta = 0.5
+        self.surfstab_tstep = -1                # negative: the dynamic time step is used (re-solve loop)
         self.bcstokes = [BC_TYPE_FREESLIP] * 4
         self.bcheat = [BC_TYPE_FIXTEMP, BC_TYPE_FIXFLOW, BC_TYPE_FIXTEMP, BC_TYPE_FIXFLOW]
         self.bcheatvals = [273, 0, 1623, 0]
@@ -691,8 +694,7 @@ class State:
 
 
 def timestep(s, o, timers=None):
-    """One pass of the loop body pylamp2.py:273-594 (no injection, no output, NPROC=1,
-    surface stabilisation off).  ``timers`` (dict) accumulates per-phase seconds."""
+    """One pass of the loop body pylamp2.py:273-594 (no injection, no output, NPROC=1).  ``timers`` (dict) accumulates per-phase seconds."""
     import time as _time
     t0 = [_time.perf_counter()]
 
@@ -730,17 +732,37 @@ def timestep(s, o, timers=None):
     if o.do_heatdiff:
         tstep_temp = heat_timestep(s.f_k[IZ], s.f_rho, s.f_Cp, s.dx, o.tstep_modifier,
                                    o.tstep_dif_min, o.tstep_dif_max)
-    A, rhs = makeStokesMatrix(nx, grid, s.f_etas, s.f_etan, s.f_rho, o.bcstokes)      # :353
+    if not o.surface_stabilization or o.surfstab_tstep < 0:                         # :352-355
+        A, rhs = makeStokesMatrix(nx, grid, s.f_etas, s.f_etan, s.f_rho, o.bcstokes)
+    else:
+        A, rhs = makeStokesMatrix(nx, grid, s.f_etas, s.f_etan, s.f_rho, o.bcstokes, surfstab=True,
+                                  tstep=o.surfstab_tstep, surfstab_theta=o.surfstab_theta)
     lap("stokes_assembly")
     x = o.solve(A, rhs)                                                             # :360
     lap("stokes_solve")
     s.newvel, s.newpres = x2vp(x, nx)
     tstep_stokes = stokes_timestep(s.newvel, s.dx, o.tstep_modifier, o.tstep_adv_min, o.tstep_adv_max)
+    if o.surfstab_tstep > 0:                                                        # :368-372
+        tstep_stokes = o.surfstab_tstep
     if o.do_heatdiff:
         s.limiter = "H" if tstep_temp < tstep_stokes else "S"                      # :374-379
         tstep = min(tstep_temp, tstep_stokes)
     else:
         tstep, s.limiter = tstep_stokes, "S"
+    s.stab_solves = 0
+    if o.surface_stabilization and o.surfstab_tstep < 0:                            # :387-405
+        while True:      # redo the solve with the stabilisation terms of the step actually taken
+            A, rhs = makeStokesMatrix(nx, grid, s.f_etas, s.f_etan, s.f_rho, o.bcstokes, surfstab=True,
+                                      tstep=tstep, surfstab_theta=o.surfstab_theta)
+            x = o.solve(A, rhs)
+            s.stab_solves += 1
+            s.newvel, s.newpres = x2vp(x, nx)
+            check = o.tstep_modifier * np.min(s.dx) / np.max(s.newvel)               # :399 (not clamped)
+            if check < tstep:
+                tstep, s.limiter = check, "Ss"
+            else:
+                break
+        lap("stokes_solve")
     s.tstep = tstep
     s.totaltime += tstep
     lap("dt")
