@@ -303,3 +303,27 @@ def test_fence_count_fused_bit_exact():
     xd2 = torch.as_tensor(x).cuda()
     _, cd2 = markers.fence_count(xd2, nx, L, want_kelem=False)
     assert np.array_equal(cd2.cpu().numpy(), count)
+
+
+def test_delete_outside_on_device_matches_reference_block():
+    """markers.delete_outside on CUDA tensors keeps exactly the markers the reference's own block keeps
+    (tests/golden/fence_delete.npz, fence disabled), and the driver's cell count then sees them all."""
+    import os
+    import types
+    from conftest import GOLDEN
+    from pylamp_b200 import markers
+    g = np.load(os.path.join(GOLDEN, "fence_delete.npz"))
+    x0, f0, v0 = g["fd_tr_x"], g["fd_tr_f"], g["fd_vel"]
+    cols = [torch.as_tensor(np.ascontiguousarray(f0[:, k])).cuda() for k in range(O.NFTRAC)]
+    s = types.SimpleNamespace(L=list(g["fd_L"]), tr_x=torch.as_tensor(x0.copy()).cuda(), cols=cols,
+                              trac_vel=torch.as_tensor(v0.copy()).cuda())
+    n = markers.delete_outside(s)
+    want_x, want_f, want_v = g["fd_off_tr_x"], g["fd_off_tr_f"], g["fd_off_vel"]
+    assert n == x0.shape[0] - want_x.shape[0]
+    got_f = np.stack([c.cpu().numpy() for c in s.cols], axis=1)
+    order = np.argsort(got_f[:, O.TR__ID])
+    assert np.array_equal(got_f[order], want_f) and np.array_equal(s.tr_x.cpu().numpy()[order], want_x)
+    assert np.array_equal(s.trac_vel.cpu().numpy()[order], want_v)
+    nx = [9, 7]
+    _, count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=False)
+    assert int(count.sum().item()) == want_x.shape[0]
