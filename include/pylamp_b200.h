@@ -193,6 +193,10 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
  * (0: zero start, 1: start from the previous solve's iterate, 2: linear extrapolation of the last two), "reorth_thresh" (1e-4), "lmax_every" (1: the
  * smoother's eigenvalue estimates are recomputed on every n-th coefficient update) */
 int plb_stokes_set_param(plb_stokes* op, const char* name, double value);
+/* free-surface stabilisation terms of makeStokesMatrix(surfstab=True, tstep, surfstab_theta),
+ * pylamp_stokes.py:422-426 and :483-487: theta_dt = surfstab_theta * tstep (<= 0: off).  Uses the
+ * density field of the last plb_stokes_set_coeffs, which also switches the terms off again. */
+int plb_stokes_set_surfstab(plb_stokes* op, double theta_dt);
 /* test hook: one multigrid V-cycle x = V(b) on the velocity block; b, x are two planes
  * [vz | vx] of nz*nxx doubles each */
 int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2);

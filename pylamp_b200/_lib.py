@@ -58,6 +58,7 @@ _PROTOS = {
     "plb_stokes_apply": (I, [VP, VP, VP]),
     "plb_stokes_solve": (I, [VP, VP, D, I, VP, IP, DP]),
     "plb_stokes_set_param": (I, [VP, C.c_char_p, D]),
+    "plb_stokes_set_surfstab": (I, [VP, D]),
     "plb_stokes_vcycle": (I, [VP, VP, VP]),
     "plb_stokes_last_stats": (I, [VP, DP]),
     "plb_x2vp": (I, [VP, I, I, I, VP, VP, VP, VP]),

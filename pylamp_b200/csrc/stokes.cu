@@ -67,6 +67,10 @@ struct plb_stokes {
     std::vector<Level> lv;
     const double* rho = nullptr;
     double g_z = 9.81, g_x = 0;
+    // free-surface stabilisation (pylamp_stokes.py:422-426, :483-487): theta*dt (0 = off) and the two
+    // full-size planes of centred density gradients Dz | Dx the extra momentum-row terms are built from
+    double surf = 0;
+    double* surf_d = nullptr;
     double Kc = 0, Kb = 0;
     bool coeffs = false, hierarchy = false;
     plb_reduce_ws rws{};
@@ -130,8 +134,34 @@ struct FullArgs {
     double Kc, Kb;
 };
 
+// Free-surface stabilisation terms (SURF): with q = Dz*vz(i,j) + Dx*vx(i,j), the interior z-momentum row
+// gains theta*dt*g_z*q and the interior x-momentum row theta*dt*g_x*q, where
+//   Dz(i,j) = (rho[i+1,j]+rho[i+1,j+1]-rho[i-1,j]-rho[i-1,j+1]) / 2 / (z[i+1]-z[i-1]),
+//   Dx(i,j) = (rho[i,j+1]+rho[i+1,j+1]-rho[i,j-1]-rho[i+1,j-1]) / 2 / (x[j+1]-x[j-1])
+// (pylamp_stokes.py:422-426, :483-487).  sd = [Dz | Dx], two full-size planes indexed with global rows.
+struct SurfArgs {
+    const double* dz;
+    const double* dx;
+    double cz, cx;        // theta*dt*g_z, theta*dt*g_x
+};
+
 __global__ void __launch_bounds__(BX* BY)
-k_stokes_full(LevelDev L, FullArgs a, const double* __restrict__ vz, const double* __restrict__ vx,
+k_surfstab_planes(LevelDev L, const double* __restrict__ rho, double* __restrict__ dzp, double* __restrict__ dxp) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (i >= L.nz || j >= L.nxx) return;
+    const int ld = L.ld;
+    const long long o = (long long)i * ld + j;
+    double a = 0, b = 0;
+    if (i >= 1 && i <= L.nz - 2 && j >= 1 && j <= L.nxx - 2) {
+        a = 0.5 * (rho[o + ld] + rho[o + ld + 1] - rho[o - ld] - rho[o - ld + 1]) * L.idzc[i];
+        b = 0.5 * (rho[o + 1] + rho[o + ld + 1] - rho[o - 1] - rho[o + ld - 1]) * L.idxc[j];
+    }
+    dzp[o] = a, dxp[o] = b;
+}
+
+template <bool SURF>
+__global__ void __launch_bounds__(BX* BY)
+k_stokes_full(LevelDev L, FullArgs a, SurfArgs sf, const double* __restrict__ vz, const double* __restrict__ vx,
               const double* __restrict__ p, double* __restrict__ yz, double* __restrict__ yx,
               double* __restrict__ yp) {
     const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
@@ -150,6 +180,7 @@ k_stokes_full(LevelDev L, FullArgs a, const double* __restrict__ vz, const doubl
     } else {
         VzCoef c = vz_coef(L, i, j);
         r = kvz_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idzc[i] * (p[o] - p[o - ld]);
+        if (SURF) r += sf.cz * (sf.dz[o] * vz[o] + sf.dx[o] * vx[o]);
     }
     yz[o] = r;
     // ---- vx row
@@ -172,6 +203,7 @@ k_stokes_full(LevelDev L, FullArgs a, const double* __restrict__ vz, const doubl
     } else {
         VxCoef c = vx_coef(L, i, j);
         r = kvx_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idxc[j] * (p[o] - p[o - 1]);
+        if (SURF) r += sf.cx * (sf.dz[o] * vz[o] + sf.dx[o] * vx[o]);
     }
     yx[o] = r;
     // ---- pressure row
@@ -231,9 +263,9 @@ k_deinterleave_rows(LevelDev L, const double* __restrict__ x, double* __restrict
 //   RESID: out = W (b - A x)   else   out = W (A x);   W_v = 1/sqrt|diag K|, W_p = sqrt(eta_n)/Kc
 // x must satisfy the homogeneous BC rows (slaves filled); out is zero on non-rows.
 // -------------------------------------------------------------------------------------------
-template <bool RESID>
+template <bool RESID, bool SURF>
 __global__ void __launch_bounds__(BX* BY)
-k_stokes_op(LevelDev L, double Kc, const double* __restrict__ vz, const double* __restrict__ vx,
+k_stokes_op(LevelDev L, SurfArgs sf, double Kc, const double* __restrict__ vz, const double* __restrict__ vx,
             const double* __restrict__ p, const double* __restrict__ bz, const double* __restrict__ bx,
             const double* __restrict__ bp, double* __restrict__ oz, double* __restrict__ ox,
             double* __restrict__ op) {
@@ -249,9 +281,13 @@ k_stokes_op(LevelDev L, double Kc, const double* __restrict__ vz, const double* 
         if (RESID) bzv = bz[o], bxv = bx[o], bpv = bp[o];
         const double vz00 = vz[o], vzP0 = vz[o + ld], vx00 = vx[o], vx0P = vx[o + 1];
         const Rows2 q = rows_interior<true>(L, vz, vx, i, j);
+        double sq = 0;
+        if (SURF) sq = sf.dz[o] * vz00 + sf.dx[o] * vx00;
         double a = q.kz - 2 * Kc * L.idzc[i] * (p00 - pM0);
+        if (SURF) a += sf.cz * sq;
         oz[o] = is_vz_row(L, i, j) ? (RESID ? bzv - a : a) * rsqrt(-q.dz) : 0.0;
         a = q.kx - 2 * Kc * L.idxc[j] * (p00 - p0M);
+        if (SURF) a += sf.cx * sq;
         ox[o] = is_vx_row(L, i, j) ? (RESID ? bxv - a : a) * rsqrt(-q.dx) : 0.0;
         a = Kc * (L.idx[j] * (vx0P - vx00) + L.idz[i] * (vzP0 - vz00));
         op[o] = is_p_row(L, i, j) ? (RESID ? bpv - a : a) * (sqrt(en) / Kc) : 0.0;
@@ -261,6 +297,7 @@ k_stokes_op(LevelDev L, double Kc, const double* __restrict__ vz, const double* 
     if (is_vz_row(L, i, j)) {
         VzCoef c = vz_coef(L, i, j);
         double a = kvz_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idzc[i] * (p[o] - p[o - ld]);
+        if (SURF) a += sf.cz * (sf.dz[o] * vz[o] + sf.dx[o] * vx[o]);
         r = (RESID ? bz[o] - a : a) * rsqrt(-c.diag);
     }
     oz[o] = r;
@@ -268,6 +305,7 @@ k_stokes_op(LevelDev L, double Kc, const double* __restrict__ vz, const double* 
     if (is_vx_row(L, i, j)) {
         VxCoef c = vx_coef(L, i, j);
         double a = kvx_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idxc[j] * (p[o] - p[o - 1]);
+        if (SURF) a += sf.cx * (sf.dz[o] * vz[o] + sf.dx[o] * vx[o]);
         r = (RESID ? bx[o] - a : a) * rsqrt(-c.diag);
     }
     ox[o] = r;
@@ -530,9 +568,9 @@ k_cheb_tile(LevelDev L, int row_lo, int row_hi, const double* __restrict__ xz, c
 }
 
 // shared-memory-staged variant of k_stokes_op (pressure staged as a fifth tile)
-template <bool RESID>
+template <bool RESID, bool SURF>
 __global__ void __launch_bounds__(256)
-k_stokes_op_tile(LevelDev L, int row_lo, int row_hi, double Kc, const double* __restrict__ vz,
+k_stokes_op_tile(LevelDev L, SurfArgs sf, int row_lo, int row_hi, double Kc, const double* __restrict__ vz,
                  const double* __restrict__ vx, const double* __restrict__ p, const double* __restrict__ bz,
                  const double* __restrict__ bx, const double* __restrict__ bp, double* __restrict__ oz,
                  double* __restrict__ ox, double* __restrict__ op) {
@@ -568,6 +606,7 @@ k_stokes_op_tile(LevelDev L, int row_lo, int row_hi, double Kc, const double* __
             if (is_vz_row(L, i, j)) {
                 VzCoef c = vz_coef(L, i, j);
                 double a = kvz_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idzc[i] * (p[o] - p[o - ld]);
+                if (SURF) a += sf.cz * (sf.dz[o] * vz[o] + sf.dx[o] * vx[o]);
                 q = (RESID ? vbz - a : a) * rsqrt(-c.diag);
             }
             oz[o] = q;
@@ -575,6 +614,7 @@ k_stokes_op_tile(LevelDev L, int row_lo, int row_hi, double Kc, const double* __
             if (is_vx_row(L, i, j)) {
                 VxCoef c = vx_coef(L, i, j);
                 double a = kvx_apply(L, c, vz, vx, i, j) - 2 * Kc * L.idxc[j] * (p[o] - p[o - 1]);
+                if (SURF) a += sf.cx * (sf.dz[o] * vz[o] + sf.dx[o] * vx[o]);
                 q = (RESID ? vbx - a : a) * rsqrt(-c.diag);
             }
             ox[o] = q;
@@ -590,9 +630,13 @@ k_stokes_op_tile(LevelDev L, int row_lo, int row_hi, double Kc, const double* __
         const double* pp = &sp[(r + 1) * TLE + tx + 1];
         const double p00 = pp[0], pM0 = pp[-TLE], p0M = pp[-1];
         const double en = sen[(r + 1) * TLE + tx + 1];
+        double sq = 0;
+        if (SURF) sq = sf.dz[o] * t.z00 + sf.dx[o] * t.x00;
         double a = t.kz - 2 * Kc * L.idzc[i] * (p00 - pM0);
+        if (SURF) a += sf.cz * sq;
         oz[o] = is_vz_row(L, i, j) ? (RESID ? vbz - a : a) * rsqrt(-t.dgz) : 0.0;
         a = t.kx - 2 * Kc * idxc_j * (p00 - p0M);
+        if (SURF) a += sf.cx * sq;
         ox[o] = is_vx_row(L, i, j) ? (RESID ? vbx - a : a) * rsqrt(-t.dgx) : 0.0;
         a = Kc * (idx_j * (t.x0P - t.x00) + L.idz[i] * (t.zP0 - t.z00));
         op[o] = is_p_row(L, i, j) ? (RESID ? vbp - a : a) * (sqrt(en) / Kc) : 0.0;
@@ -990,6 +1034,14 @@ int zalloc(plb_ctx* ctx, double** d, size_t n) {
     PLB_CUDA(ctx, cudaMalloc(d, sizeof(double) * n));
     PLB_CUDA(ctx, cudaMemsetAsync(*d, 0, sizeof(double) * n, ctx->stream));
     return 0;
+}
+
+SurfArgs surf_args(const plb_stokes* op) {
+    SurfArgs s;
+    s.dz = op->surf_d;
+    s.dx = op->surf_d ? op->surf_d + op->lv[0].full : nullptr;
+    s.cz = op->surf * op->g_z, s.cx = op->surf * op->g_x;
+    return s;
 }
 
 int level_metrics(plb_ctx* ctx, Level& L) {
@@ -1406,7 +1458,7 @@ void plb_stokes_destroy(plb_stokes* op) {
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
     if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
-    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->zv};
+    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->zv, op->surf_d};
     for (double* p : ptrs) if (p) cudaFree(p);
     for (double* p : op->hist) if (p) cudaFree(p);
     plb_reduce_ws_free(&op->rws);
@@ -1447,6 +1499,7 @@ int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_
     Level& L = op->lv[0];
     L.etas = d_etas, L.etan = d_etan;
     op->rho = d_rho, op->g_z = gz, op->g_x = gx;
+    op->surf = 0;      // the stabilisation planes belong to the previous density field: off until set again
     // mineta over both fields INCLUDING the ghost row/column of etan, like np.min (:116)
     double* d = op->d_scal + 920;
     k_set1<<<1, 1, 0, ctx->stream>>>(d, INFINITY);
@@ -1461,6 +1514,24 @@ int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_
     op->Kc = 2 * mineta / (avgdx + avgdz);
     op->Kb = 4 * mineta / ((avgdx + avgdz) * (avgdx + avgdz));
     op->coeffs = true, op->hierarchy = false;
+    return 0;
+}
+
+int plb_stokes_set_surfstab(plb_stokes* op, double theta_dt) {
+    if (!op) return 1;
+    plb_ctx* ctx = op->ctx;
+    if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_set_surfstab: coefficients not set");
+    if (!(theta_dt > 0)) {
+        op->surf = 0;
+        return 0;
+    }
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    Level& L = op->lv[0];
+    if (!op->surf_d && zalloc(ctx, &op->surf_d, 2 * L.full)) return 2;
+    k_surfstab_planes<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(L.dev(), op->rho, op->surf_d,
+                                                                        op->surf_d + L.full);
+    PLB_LAUNCHED(ctx);
+    op->surf = theta_dt;
     return 0;
 }
 
@@ -1501,8 +1572,13 @@ int plb_stokes_apply(plb_stokes* op, const double* d_x, double* d_y) {
     k_deinterleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, d_x, in, in + P, in + 2 * P);
     PLB_LAUNCHED(ctx);
     FullArgs a = {op->gz_d, op->gx_d, op->bc[0], op->bc[2], op->Kc, op->Kb};
-    k_stokes_full<<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(L.dev(), a, in, in + P, in + 2 * P, outp,
-                                                                    outp + P, outp + 2 * P);
+    const SurfArgs sf = surf_args(op);
+    if (op->surf > 0)
+        k_stokes_full<true><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(L.dev(), a, sf, in, in + P, in + 2 * P,
+                                                                              outp, outp + P, outp + 2 * P);
+    else
+        k_stokes_full<false><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(L.dev(), a, sf, in, in + P, in + 2 * P,
+                                                                               outp, outp + P, outp + 2 * P);
     PLB_LAUNCHED(ctx);
     k_interleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, outp, outp + P,
                                                                                 outp + 2 * P, d_y);
@@ -1554,6 +1630,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     const LevelDev D = L.dev();
     const size_t P = L.plane;
     const double Kc = op->Kc;
+    const SurfArgs sf = surf_args(op);
     double *x = op->xs, *r = op->r3, *b = op->b3;
     const dim3 g = L.grid(), blk = block2d();
     const dim3 tg((L.nxx + TLX - 1) / TLX, (L.i1 - L.i0 + TLZ - 1) / TLZ);     // tile-staged kernels
@@ -1584,13 +1661,21 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     auto stokes_resid = [&](double* xx, double* out) -> int {
         if (halo(op, L, xx, 3)) return 2;
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 88.0 * (double)P);
-        if (op->tile_smoother && L.nxx >= 1024)
-            k_stokes_op_tile<true><<<tg, 256, 0, ctx->stream>>>(D, L.lo, L.hi, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2),
-                                                                C3(b, 0), C3(b, 1), C3(b, 2), V3(out, 0), V3(out, 1),
-                                                                V3(out, 2));
+        if (op->surf > 0) {      // free-surface stabilisation terms in the outer operator
+            if (op->tile_smoother && L.nxx >= 1024)
+                k_stokes_op_tile<true, true><<<tg, 256, 0, ctx->stream>>>(D, sf, L.lo, L.hi, Kc, C3(xx, 0), C3(xx, 1),
+                                                                          C3(xx, 2), C3(b, 0), C3(b, 1), C3(b, 2),
+                                                                          V3(out, 0), V3(out, 1), V3(out, 2));
+            else
+                k_stokes_op<true, true><<<g, blk, 0, ctx->stream>>>(D, sf, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2), C3(b, 0),
+                                                                    C3(b, 1), C3(b, 2), V3(out, 0), V3(out, 1), V3(out, 2));
+        } else if (op->tile_smoother && L.nxx >= 1024)
+            k_stokes_op_tile<true, false><<<tg, 256, 0, ctx->stream>>>(D, sf, L.lo, L.hi, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2),
+                                                                       C3(b, 0), C3(b, 1), C3(b, 2), V3(out, 0), V3(out, 1),
+                                                                       V3(out, 2));
         else
-            k_stokes_op<true><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2), C3(b, 0), C3(b, 1),
-                                                          C3(b, 2), V3(out, 0), V3(out, 1), V3(out, 2));
+            k_stokes_op<true, false><<<g, blk, 0, ctx->stream>>>(D, sf, Kc, C3(xx, 0), C3(xx, 1), C3(xx, 2), C3(b, 0), C3(b, 1),
+                                                                 C3(b, 2), V3(out, 0), V3(out, 1), V3(out, 2));
         PLB_LAUNCHED(ctx);
         return 0;
     };
@@ -1636,12 +1721,20 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         // z comes out of `precond` with valid halo rows
         if (op->debug_halo && halo(op, L, const_cast<double*>(z), 3)) return 2;
         plb_prof_scope prof_(ctx, PLB_K_STOKES_OP, 64.0 * (double)P);
-        if (op->tile_smoother && L.nxx >= 1024)
-            k_stokes_op_tile<false><<<tg, 256, 0, ctx->stream>>>(D, L.lo, L.hi, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr,
-                                                                 nullptr, nullptr, V3(c, 0), V3(c, 1), V3(c, 2));
+        if (op->surf > 0) {
+            if (op->tile_smoother && L.nxx >= 1024)
+                k_stokes_op_tile<false, true><<<tg, 256, 0, ctx->stream>>>(D, sf, L.lo, L.hi, Kc, C3(z, 0), C3(z, 1), C3(z, 2),
+                                                                           nullptr, nullptr, nullptr, V3(c, 0), V3(c, 1),
+                                                                           V3(c, 2));
+            else
+                k_stokes_op<false, true><<<g, blk, 0, ctx->stream>>>(D, sf, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr, nullptr,
+                                                                     nullptr, V3(c, 0), V3(c, 1), V3(c, 2));
+        } else if (op->tile_smoother && L.nxx >= 1024)
+            k_stokes_op_tile<false, false><<<tg, 256, 0, ctx->stream>>>(D, sf, L.lo, L.hi, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr,
+                                                                        nullptr, nullptr, V3(c, 0), V3(c, 1), V3(c, 2));
         else
-            k_stokes_op<false><<<g, blk, 0, ctx->stream>>>(D, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr, nullptr,
-                                                           nullptr, V3(c, 0), V3(c, 1), V3(c, 2));
+            k_stokes_op<false, false><<<g, blk, 0, ctx->stream>>>(D, sf, Kc, C3(z, 0), C3(z, 1), C3(z, 2), nullptr, nullptr,
+                                                                  nullptr, V3(c, 0), V3(c, 1), V3(c, 2));
         PLB_LAUNCHED(ctx);
         return 0;
     };

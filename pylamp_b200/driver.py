@@ -44,6 +44,9 @@ class Options:
         self.etamax = 1e23
         self.Tref = 1623
         self.tracs_fence_enabled = True
+        self.surface_stabilization = False      # pylamp2.py:71-73
+        self.surfstab_theta = 0.5
+        self.surfstab_tstep = -1                # negative: the dynamic time step is used (re-solve loop)
         self.bcstokes = [pylamp_stokes.BC_TYPE_FREESLIP] * 4
         self.bcheat = [pylamp_diff.BC_TYPE_FIXTEMP, pylamp_diff.BC_TYPE_FIXFLOW,
                        pylamp_diff.BC_TYPE_FIXTEMP, pylamp_diff.BC_TYPE_FIXFLOW]
@@ -184,6 +187,8 @@ def timestep(s, o, want_kelem=True, phases=False):
             s.stokes_op.set_param(k, v)
     else:
         s.stokes_op.set_coeffs(s.f_etas, s.f_etan, s.f_rho)
+    if o.surface_stabilization and o.surfstab_tstep >= 0:                           # :354-355
+        s.stokes_op.set_surfstab(o.surfstab_tstep, o.surfstab_theta)
     x = s.stokes_op.solve(None, rtol=o.stokes_rtol, maxit=o.stokes_maxit)
     s.stats["stokes_iters"] = s.stokes_op.iterations
     s.stats["stokes_relres"] = s.stokes_op.relres
@@ -191,11 +196,28 @@ def timestep(s, o, want_kelem=True, phases=False):
     s.newvel, s.newpres = pylamp_stokes.x2vp(x, nx)
     vmax = max(markers.field_max(s.newvel[IZ]), markers.field_max(s.newvel[IX]))   # :364 (signed)
     tstep_stokes = _clamp(o.tstep_modifier * min(s.dx) / vmax, o.tstep_adv_min, o.tstep_adv_max)
+    if o.surfstab_tstep > 0:                                                        # :368-372
+        tstep_stokes = o.surfstab_tstep
     if o.do_heatdiff:                                                               # :374-385
         s.limiter = "H" if tstep_temp < tstep_stokes else "S"
         tstep = min(tstep_temp, tstep_stokes)
     else:
         tstep, s.limiter = tstep_stokes, "S"
+    if o.surface_stabilization and o.surfstab_tstep < 0:                            # :387-405
+        s.stats["stab_solves"] = 0
+        while True:      # solve again with the stabilisation terms of the step actually taken
+            s.stokes_op.set_surfstab(tstep, o.surfstab_theta)
+            x = s.stokes_op.solve(None, rtol=o.stokes_rtol, maxit=o.stokes_maxit)
+            s.stats["stab_solves"] += 1
+            s.stats["stokes_iters"] += s.stokes_op.iterations
+            s.newvel, s.newpres = pylamp_stokes.x2vp(x, nx)
+            vmax = max(markers.field_max(s.newvel[IZ]), markers.field_max(s.newvel[IX]))
+            check = o.tstep_modifier * min(s.dx) / vmax                            # :399 (not clamped)
+            if check < tstep:
+                tstep, s.limiter = check, "Ss"
+            else:
+                break
+        ph.mark("stokes_solve")
     s.tstep = tstep
     s.totaltime += tstep
     ph.mark("x2vp_dt")

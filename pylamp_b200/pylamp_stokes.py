@@ -86,6 +86,13 @@ class StokesOperator:
     def set_param(self, name, value):
         self.ctx.check(self.ctx.lib.plb_stokes_set_param(self.h, name.encode(), float(value)))
 
+    def set_surfstab(self, tstep=None, surfstab_theta=0.5):
+        """Free-surface stabilisation terms of ``makeStokesMatrix(surfstab=True, tstep, surfstab_theta)``
+        (pylamp_stokes.py:422-426, :483-487) for the current density field; ``tstep=None`` switches
+        them off.  `set_coeffs` switches them off as well (they belong to a density field)."""
+        theta_dt = 0.0 if tstep is None else float(surfstab_theta) * float(tstep)
+        self.ctx.check(self.ctx.lib.plb_stokes_set_surfstab(self.h, theta_dt))
+
     @property
     def scaling(self):
         """(Kcont, Kbond) of pylamp_stokes.py:116-122."""
@@ -168,9 +175,9 @@ def makeStokesMatrix(nx, grid, f_etas, f_etan, f_rho, bc, surfstab=False, tstep=
     :class:`StokesOperator` (see the module docstring), ``rhs`` the (3N,) right-hand side."""
     if surfstab and tstep is None:
         raise Exception("surface stabilization needs predetermined tstep")       # :423-424
-    if surfstab:
-        raise NotImplementedError("free-surface stabilisation terms: SURVEY.md §8f-3 (next)")
     if (bc[DIM * 0 + IZ] & BC_TYPE_FLOWTHRU) or (bc[DIM * 1 + IZ] & BC_TYPE_FLOWTHRU):
         raise Exception("BC_TYPE_FLOWTHRU not implemented for z-direction")      # :546
     A = StokesOperator(nx, grid, f_etas, f_etan, f_rho, bc)
+    if surfstab:
+        A.set_surfstab(tstep, surfstab_theta)                                    # :422-426, :483-487
     return A, A.rhs(device=not A.host)
