@@ -148,6 +148,7 @@ def run_b200(args):
     o = driver.Options(**opts)
     o.heat_rtol = args.heat_rtol
     o.marker_ownership = args.marker_ownership
+    o.slab_reduce = bool(args.slab_reduce)
     o.stokes_params = {"warm_start": args.warm_start, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu,
                        "graph_all": 0}     # keep the V-cycle's kernels individually event-timed (whole-cycle graph: no gain at 4096^2)
     M = s.ntrac
@@ -323,6 +324,8 @@ def main():
     ap.add_argument("--gmres-m", type=int, default=30, help="FGMRES restart length of the Stokes solve")
     ap.add_argument("--marker-ownership", default="index", choices=["index", "slab"],
                     help="several GPUs: markers stay with their rank (index) or are owned by z-slab and migrate (slab)")
+    ap.add_argument("--slab-reduce", type=int, default=0,
+                    help="with --marker-ownership slab: boundary-row exchange + all-gather instead of the all-reduce of node sums")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
     ap.add_argument("--ref-ncell", type=int, default=256, help="--impl reference sample size")
     args = ap.parse_args()

@@ -99,6 +99,20 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
                   int crop_z0, int crop_x0, int nz, int nxx, int ld, double* const* h_out);
 
 /* ---- grid -> markers: pylamp_trac.grid2trac, pylamp_trac.py:30-158 ---------------------- */
+/* plb_trac2grid in two halves, for slab-owned markers (pylamp_b200/slabgrid.py; SURVEY.md 8e "halo-row
+ * accumulate"): `scatter` zeroes d_planes and leaves the raw sums of this rank's markers in it --
+ * planes [field 0..k-1 | sum of weights (if a weighted scheme is present) | marker count (if an
+ * unweighted one is)], each nze*nxe over the extended axes, *h_nplanes of them -- without any
+ * all-reduce; after the caller has combined the rows shared with the neighbouring slabs, `finalise`
+ * divides / exponentiates rows [row0,row1) of the cropped (nz x nxx) target (pylamp_trac.py:276-316). */
+int plb_trac2grid_scatter(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
+                          const double* const* h_fields, const int* h_scheme, const double* d_axis_z,
+                          int nze, const double* d_axis_x, int nxe, double z0, double zlen, double x0,
+                          double xlen, double* d_planes, int* h_nplanes);
+int plb_trac2grid_finalise(plb_ctx* ctx, int k, const int* h_scheme, const double* d_planes, int nze, int nxe,
+                           int crop_z0, int crop_x0, int nz, int nxx, int ld, int row0, int row1,
+                           double* const* h_out);
+
 /* method = PLB_METHOD_{NEAREST,LINEAR,VELDIV}.  Writes k output columns (SoA, length M).
  * Markers outside the grid get `defval` and are counted into *h_n_outside (synchronises). */
 int plb_grid2trac(plb_ctx* ctx, long long M, const double* d_tr_x, int method, int k,

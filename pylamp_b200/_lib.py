@@ -36,6 +36,8 @@ _PROTOS = {
     "plb_comm_destroy": (None, [VP]),
     "plb_marker_minmax": (I, [VP, LL, VP, DP]),
     "plb_trac2grid": (I, [VP, LL, VP, I, PP, IP, VP, I, VP, I, D, D, D, D, I, I, I, I, I, PP]),
+    "plb_trac2grid_scatter": (I, [VP, LL, VP, I, PP, IP, VP, I, VP, I, D, D, D, D, VP, IP]),
+    "plb_trac2grid_finalise": (I, [VP, I, IP, VP, I, I, I, I, I, I, I, I, I, PP]),
     "plb_grid2trac": (I, [VP, LL, VP, I, I, PP, VP, I, VP, I, I, D, D, D, D, D, PP,
                           C.POINTER(LL)]),
     "plb_rk4": (I, [VP, LL, VP, VP, VP, VP, I, VP, I, I, D, D, D, D, D, VP, VP]),

@@ -934,6 +934,101 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
     return 0;
 }
 
+// plb_trac2grid in two halves for slab-owned markers (pylamp_b200/slabgrid.py): the raw sums land in
+// caller-owned planes [field 0 .. k-1 | sum of weights | marker count] (the last two only if a
+// weighted / an unweighted scheme is present), nothing is all-reduced and nothing divided; the
+// caller combines the boundary rows of neighbouring slabs and then finalises a row range.
+int plb_trac2grid_scatter(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
+                          const double* const* h_fields, const int* h_scheme, const double* d_axis_z,
+                          int nze, const double* d_axis_x, int nxe, double z0, double zlen, double x0,
+                          double xlen, double* d_planes, int* h_nplanes) {
+    if (!ctx || !d_planes) return 1;
+    if (k < 1 || k > PLB_MAX_FIELDS) PLB_FAIL(ctx, "plb_trac2grid_scatter: k=%d out of range 1..%d", k, PLB_MAX_FIELDS);
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    T2GArgs a;
+    memset(&a, 0, sizeof(a));
+    bool any_w = false, any_c = false;
+    for (int f = 0; f < k; f++) {
+        int sc = h_scheme[f];
+        if (!(sc & (PLB_AVG_ARITHMETIC | PLB_AVG_GEOMETRIC)))
+            PLB_FAIL(ctx, "plb_trac2grid_scatter: invalid averaging scheme %d", sc);
+        (sc & PLB_AVG_WEIGHTED) ? any_w = true : any_c = true;
+        a.f[f] = h_fields[f];
+        a.scheme[f] = sc;
+    }
+    const size_t plane = (size_t)nze * nxe;
+    const size_t nplanes = k + (any_w ? 1 : 0) + (any_c ? 1 : 0);
+    if (h_nplanes) *h_nplanes = (int)nplanes;
+    if (plb_ws_reserve(ctx, 3 * (size_t)(nze + nxe) * sizeof(double))) return 2;
+    double2* tab = (double2*)ctx->ws;
+    double* recip = (double*)ctx->ws + 2 * (size_t)(nze + nxe);
+    k_axis_recip<<<plb_blocks(nze, 256), 256, 0, ctx->stream>>>(nze, d_axis_z, recip, tab);
+    PLB_LAUNCHED(ctx);
+    k_axis_recip<<<plb_blocks(nxe, 256), 256, 0, ctx->stream>>>(nxe, d_axis_x, recip + nze, tab + nze);
+    PLB_LAUNCHED(ctx);
+    a.riz = recip, a.rix = recip + nze, a.tz = tab, a.tx = tab + nze;
+    a.sz = (double)(nze - 1) / zlen, a.sx = (double)(nxe - 1) / xlen;
+    for (int f = 0; f < k; f++) a.acc[f] = d_planes + (size_t)f * plane;
+    size_t nxt = k;
+    if (any_w) a.wsum = d_planes + (nxt++) * plane;
+    if (any_c) a.cnt = d_planes + (nxt++) * plane;
+    a.axz = d_axis_z, a.axx = d_axis_x, a.nze = nze, a.nxe = nxe;
+    a.z0 = z0, a.zlen = zlen, a.x0 = x0, a.xlen = xlen, a.k = k;
+    a.merge_first = ctx->t2g_variant == 2;
+    bool chunked = ctx->t2g_variant >= 1 && !any_c && M >= 4 && plane < ((size_t)1 << 31) &&
+                   ((uintptr_t)d_tr_x & 31) == 0;
+    for (int f = 0; f < k; f++) chunked = chunked && ((uintptr_t)h_fields[f] & 31) == 0;
+    PLB_CUDA(ctx, cudaMemsetAsync(d_planes, 0, nplanes * plane * sizeof(double), ctx->stream));
+    if (M > 0) {
+        plb_prof_scope prof_(ctx, PLB_K_T2G, (16.0 + 8.0 * k) * (double)M);
+        const double2* x = (const double2*)d_tr_x;
+        switch (k) {
+            case 1: scatter_k<1>(ctx, M, x, a, chunked); break;
+            case 2: scatter_k<2>(ctx, M, x, a, chunked); break;
+            case 3: scatter_k<3>(ctx, M, x, a, chunked); break;
+            case 4: scatter_k<4>(ctx, M, x, a, chunked); break;
+            case 5: scatter_k<5>(ctx, M, x, a, chunked); break;
+            case 6: scatter_k<6>(ctx, M, x, a, chunked); break;
+            case 7: scatter_k<7>(ctx, M, x, a, chunked); break;
+            default: scatter_k<8>(ctx, M, x, a, chunked); break;
+        }
+        PLB_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+// rows [row0, row1) of the (nz x nxx) target from raw planes laid out as by plb_trac2grid_scatter
+int plb_trac2grid_finalise(plb_ctx* ctx, int k, const int* h_scheme, const double* d_planes, int nze, int nxe,
+                           int crop_z0, int crop_x0, int nz, int nxx, int ld, int row0, int row1,
+                           double* const* h_out) {
+    if (!ctx || !d_planes) return 1;
+    if (k < 1 || k > PLB_MAX_FIELDS) PLB_FAIL(ctx, "plb_trac2grid_finalise: k=%d out of range", k);
+    if (row0 < 0 || row1 > nz || row0 > row1 || crop_z0 + nz > nze || crop_x0 + nxx > nxe)
+        PLB_FAIL(ctx, "plb_trac2grid_finalise: rows/crop outside the grids");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (row1 == row0) return 0;
+    T2GArgs a;
+    memset(&a, 0, sizeof(a));
+    bool any_w = false, any_c = false;
+    for (int f = 0; f < k; f++) (h_scheme[f] & PLB_AVG_WEIGHTED) ? any_w = true : any_c = true;
+    const size_t plane = (size_t)nze * nxe;
+    double* planes = const_cast<double*>(d_planes);
+    for (int f = 0; f < k; f++) {
+        a.scheme[f] = h_scheme[f];
+        a.acc[f] = planes + (size_t)f * plane;
+        a.out[f] = h_out[f] + (size_t)row0 * ld;
+    }
+    size_t nxt = k;
+    if (any_w) a.wsum = planes + (nxt++) * plane;
+    if (any_c) a.cnt = planes + (nxt++) * plane;
+    a.nze = nze, a.nxe = nxe, a.k = k;
+    const int rows = row1 - row0;
+    k_t2g_finalise<<<plb_grid_for(ctx, (long long)rows * nxx, 256, 8), 256, 0, ctx->stream>>>(
+        a, crop_z0 + row0, crop_x0, rows, nxx, ld);
+    PLB_LAUNCHED(ctx);
+    return 0;
+}
+
 int plb_grid2trac(plb_ctx* ctx, long long M, const double* d_tr_x, int method, int k,
                   const double* const* h_fields, const double* d_grid_z, int nz,
                   const double* d_grid_x, int nxx, int ld, double z0, double zlen, double x0,

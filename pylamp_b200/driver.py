@@ -63,6 +63,9 @@ class Options:
         # processed by any rank); "slab" = rank r owns the markers in its cell rows, markers that
         # cross a slab boundary migrate to the new owner after the fence (migrate.py)
         self.marker_ownership = "index"
+        # slab-owned markers only: combine the node sums by a boundary-row exchange with the neighbouring
+        # slabs + an all-gather of the finished rows instead of all-reducing every raw plane (slabgrid.py)
+        self.slab_reduce = False
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -157,6 +160,11 @@ def timestep(s, o, want_kelem=True, phases=False):
     # markers -> grids, pylamp2.py:307-319
     mm = pylamp_trac.marker_minmax(tr_x, ctx)
     t2g = pylamp_trac.trac2grid_device
+    if o.slab_reduce and o.marker_ownership == "slab" and ctx.comm_info()[1] > 1:
+        slab_bounds = migrate.slab_bounds(nx[IZ] - 1, ctx.comm_info()[1])
+
+        def t2g(ctx_, x_, cols_, schemes_, grid_, out_, mm_):
+            return pylamp_trac.trac2grid_slab(ctx_, x_, cols_, schemes_, grid_, out_, mm_, slab_bounds)
     if o.do_advect and o.do_heatdiff:
         t2g(ctx, tr_x, [cols[k] for k in (TR_RHO, TR_ETA, TR_HCP, TR_TMP, TR_IHT, TR_MAT)],
             [INTERP_AVG_ARITHW, INTERP_AVG_GEOMW] + [INTERP_AVG_ARITHW] * 4, grid,

@@ -92,6 +92,38 @@ def trac2grid_device(ctx, tr_x_d, cols_d, schemes, grid, out_d, minmax=None):
     return minmax
 
 
+def trac2grid_slab(ctx, tr_x_d, cols_d, schemes, grid, out_d, minmax, bounds, group=None, check=False):
+    """`trac2grid_device` for slab-owned markers on several ranks (migrate.py): raw sums of the own
+    markers (plb_trac2grid_scatter), boundary rows combined with the two neighbouring slabs, own rows
+    finalised (plb_trac2grid_finalise), finished rows all-gathered -- instead of the all-reduce of
+    every raw plane inside plb_trac2grid (slabgrid.py).  `minmax` must be the GLOBAL marker extent
+    (`marker_minmax` all-reduces it), `bounds` the cell-row bounds of the slabs."""
+    import torch.distributed as dist
+    from . import slabgrid
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    k = len(cols_d)
+    M = tr_x_d.shape[0]
+    gz, gx = _axis_np(grid[IZ]), _axis_np(grid[IX])
+    axz, lz, rz = _extended_axis(gz, minmax[0], minmax[1])
+    axx, lx, rx = _extended_axis(gx, minmax[2], minmax[3])
+    axz_d, axx_d = _to_dev(axz, ctx), _to_dev(axx, ctx)
+    nz, nxx = out_d[0].shape
+    assert nz == gz.shape[0] and nxx == gx.shape[0]
+    nze, nxe = axz.shape[0], axx.shape[0]
+    planes = torch.empty((k + 2, nze, nxe), dtype=torch.float64, device=tr_x_d.device)
+    npl = C.c_int(0)
+    ctx.call("plb_trac2grid_scatter", M, tr_x_d.data_ptr(), k, _lib.ptr_array(cols_d), _lib.int_array(schemes),
+             axz_d.data_ptr(), nze, axx_d.data_ptr(), nxe, float(axz[0]), float(axz[-1] - axz[0]), float(axx[0]),
+             float(axx[-1] - axx[0]), planes.data_ptr(), C.byref(npl))
+    p = slabgrid.row_partition(bounds, lz, nze)
+    slabgrid.exchange_boundary_rows(planes[:npl.value], p, rank, world, group, check=check)
+    q = [0] + [int(b) for b in bounds[1:-1]] + [int(nz)]
+    ctx.call("plb_trac2grid_finalise", k, _lib.int_array(schemes), planes.data_ptr(), nze, nxe, lz, lx, nz, nxx,
+             nxx, q[rank], q[rank + 1], _lib.ptr_array(out_d))
+    slabgrid.gather_rows(out_d, q, rank, world, group)
+    return minmax
+
+
 def trac2grid(tr_x, tr_f, mesh, grid, gridfield, nx, distweight=None, avgscheme=None,
               method=INTERP_METHOD_ELEM, debug=False):
     """Marker-to-node averaging; writes ``gridfield[k][:, :]`` in place and returns None.

@@ -1,6 +1,6 @@
 """Multi-GPU parity (torchrun, one process per GPU): the distributed timestep -- marker-parallel
 ranks, all-reduced node sums, z-slab Stokes solve -- versus the oracle's single-process loop body.
-  torchrun --nproc-per-node 2 scripts/multi_gpu_driver_check.py [ncell] [nsteps] [index|slab]
+  torchrun --nproc-per-node 2 scripts/multi_gpu_driver_check.py [ncell] [nsteps] [index|slab] [reduce]
 With "slab" every rank starts with the markers of its own cell rows and markers migrate between the
 slabs after every step (pylamp_b200/migrate.py); markers are then matched with the oracle's by id."""
 import os, sys, numpy as np, torch, torch.distributed as dist
@@ -14,6 +14,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ownership = sys.argv[3] if len(sys.argv) > 3 else "index"
+slab_reduce = len(sys.argv) > 4 and sys.argv[4] == "reduce"      # slab only: slabgrid.py instead of the all-reduce
 host_group = dist.new_group(backend="gloo")          # object gathers of the id-matched comparison
 ctx = _lib.default_context(local)
 ctx.init_comm()
@@ -27,7 +28,7 @@ if ownership == "slab":
 else:
     sel = np.arange((rank * M) // world, ((rank + 1) * M) // world)   # contiguous share of the markers
 sg = driver.State(nx, L, tr_x[sel], tr_f[sel], device=local)
-og = driver.Options(marker_ownership=ownership, **opts)
+og = driver.Options(marker_ownership=ownership, slab_reduce=slab_reduce, **opts)
 if rank == 0:
     so, oo = O.State(nx, L, tr_x.copy(), tr_f.copy()), O.Options(solve=O.solve_refined, **opts)
 ok = True
