@@ -214,8 +214,10 @@ int plb_stokes_set_surfstab(plb_stokes* op, double theta_dt);
 /* test hook: one multigrid V-cycle x = V(b) on the velocity block; b, x are two planes
  * [vz | vx] of nz*nxx doubles each */
 int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2);
-/* h_out[4] = {Krylov iterations, V-cycles, final scaled relative residual of the last solve,
- * residual floor learnt so far (0 = none met)} */
+/* h_out[6] = {Krylov iterations, V-cycles, final scaled relative residual of the last solve,
+ * fp64 residual floor met on the current coefficient fields (0 = none; reset by set_coeffs/set_surfstab),
+ * status (0 converged to rtol; 1 stopped above rtol at the fp64 floor or at stagnation but accepted,
+ * <= "rtol_accept"; 2 not converged), effective tolerance the solve iterated to} */
 int plb_stokes_last_stats(plb_stokes* op, double* h_out);
 /* x2vp, pylamp_stokes.py:86-101: de-interleave into three (nz x ld) planes */
 int plb_x2vp(plb_ctx* ctx, int nz, int nxx, int ld, const double* d_x, double* d_vz,

@@ -34,6 +34,7 @@ struct plb_fgmres_result {
     double relres = 0;         // Arnoldi estimate of || r || / bnorm at exit
     bool converged = false;
     double floor = 0;          // > 0: the true residual stopped following the Arnoldi estimate here
+    bool stagnated = false;    // restart cycles stopped reducing the true residual (NOT a floor: no status change)
 };
 
 inline int plb_fgmres_alloc(plb_ctx* ctx, plb_fgmres_ws* ws, int m, long long n, double* d_scal) {
@@ -77,7 +78,7 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
     res->iters = 0, res->converged = false, res->relres = 1;
     int total = 0, stalls = 0;
     double beta_prev = INFINITY, est_prev = -1;
-    res->floor = 0;
+    res->floor = 0, res->stagnated = false;
     while (total < maxit) {
         if (need(ws->V, 0)) return 2;
         if (residual(ws->V[0])) return 2;
@@ -92,17 +93,21 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
             res->converged = true;
             break;
         }
-        // fp64 floor of the residual evaluation (~ eps * n^2 for this operator): the TRUE residual no
-        // longer follows the Arnoldi estimate / restart cycles no longer reduce it
-        // (a mismatch alone can also come from orthogonality loss in a long cycle, which the restart
-        // repairs -- so require that the last cycle also failed to halve the true residual)
+        // fp64 floor of the residual evaluation: in exact arithmetic the TRUE residual at a restart equals
+        // the Arnoldi estimate at the end of the cycle before.  A true residual several times above that
+        // estimate is rounding -- either lost orthogonality in a long cycle (the restart repairs that: the
+        // next cycle makes progress again) or the accuracy of b^ - A^ x itself (no cycle can go below it).
+        // Only the second is a floor, so both are required: the gap AND a cycle that failed to halve the
+        // true residual.  Slow convergence alone (no gap) is never reported as a floor.
         if (est_prev >= 0 && beta > 5 * est_prev && beta > 0.5 * beta_prev) {
             res->floor = beta / bnorm;
             break;
         }
+        // stagnation without a gap: three cycles in a row that did not halve the residual -- give up
+        // (not converged; the caller sees relres and decides)
         stalls = (beta > 0.5 * beta_prev) ? stalls + 1 : 0;
-        if (stalls >= 2) {
-            res->floor = beta / bnorm;
+        if (stalls >= 3) {
+            res->stagnated = true;
             break;
         }
         beta_prev = beta;

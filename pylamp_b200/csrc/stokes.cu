@@ -78,7 +78,8 @@ struct plb_stokes {
     // dense coarse solve
     int nc = 0;
     double* cinv = nullptr;       // nc x nc inverse (row-major)
-    double* cwork = nullptr;
+    double *probes = nullptr, *gjM = nullptr;   // resident scratch of the dense inverse (n probes, [A | I])
+    int scratch_n = 0;
     // Krylov storage (3 planes per vector)
     plb_fgmres_ws kry;
     double *xs = nullptr, *r3 = nullptr, *b3 = nullptr, *t3 = nullptr, *gz_d = nullptr, *gx_d = nullptr;
@@ -90,16 +91,32 @@ struct plb_stokes {
     int graph_all = -1;           // capture the WHOLE V-cycle (-1: on a single GPU only; 1 also captures NCCL calls)
     double* zv = nullptr;         // fixed output buffer of the whole-cycle graph (2 local planes)
     cudaGraphExec_t graph_exec = nullptr;
+    // everything the captured cycle bakes in (kernel arguments): coefficient pointers of level 0, the dense
+    // inverse, smoothing parameters, eigenvalue estimates.  A replay is only valid while these are unchanged.
+    struct GraphSig {
+        const void *etas = nullptr, *etan = nullptr, *cinv = nullptr;
+        int nu = 0, nu_coarse = 0, nc = 0, tile = 0, all = 0, level = -1;
+        double cheb_ratio = 0;
+        std::vector<double> lmax;
+        bool operator==(const GraphSig& o) const {
+            return etas == o.etas && etan == o.etan && cinv == o.cinv && nu == o.nu && nu_coarse == o.nu_coarse &&
+                   nc == o.nc && tile == o.tile && all == o.all && level == o.level && cheb_ratio == o.cheb_ratio &&
+                   lmax == o.lmax;
+        }
+    } graph_sig;
     bool have_prev = false;
     std::vector<double*> hist;    // previous converged iterates (warm_start >= 2), newest first
     int nhist = 0;
-    double floor_est = 0;         // attainable scaled residual learnt from a stalled solve
+    // fp64 floor of the scaled residual met by the last solve on the CURRENT coefficient fields (0 = none):
+    // reset by plb_stokes_set_coeffs / plb_stokes_set_surfstab, so one solve never loosens a later system
+    double floor_est = 0;
     int nu = 3, gcr_m = 50, coarsen_wide = 1, dense_max = 640, nu_coarse = 60, reorth = 0;
     double cheb_ratio = 8.0, kry_reorth = 1e-4;
     double rtol_accept = 1e-8;    // a solve stalled at its fp64 floor is accepted below this true residual
     // statistics of the last solve
     int last_iters = 0, last_vcycles = 0;
-    double last_relres = 0;
+    double last_relres = 0, last_rtol_eff = 0;
+    int last_status = 0;          // 0 converged to rtol, 1 accepted at the fp64 floor (> rtol, <= rtol_accept), 2 not converged
 };
 
 namespace {
@@ -1329,11 +1346,19 @@ int setup_hierarchy(plb_stokes* op) {
     if (n <= op->dense_max) {
         const LevelDev D = Lc.dev();
         const size_t P = Lc.plane;
-        double *probes = nullptr, *M = nullptr;
-        int* fail = nullptr;
-        if (zalloc(ctx, &probes, (size_t)n * 2 * P) || zalloc(ctx, &M, (size_t)n * 2 * n)) return 2;
-        PLB_CUDA(ctx, cudaMalloc(&fail, sizeof(int)));
-        PLB_CUDA(ctx, cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
+        // scratch stays resident (one allocation per operator, not per coefficient update)
+        if (op->scratch_n != n) {
+            if (op->probes) cudaFree(op->probes), op->probes = nullptr;
+            if (op->gjM) cudaFree(op->gjM), op->gjM = nullptr;
+            PLB_CUDA(ctx, cudaMalloc(&op->probes, sizeof(double) * (size_t)n * 2 * P));
+            PLB_CUDA(ctx, cudaMalloc(&op->gjM, sizeof(double) * (size_t)n * 2 * n));
+            op->scratch_n = n;
+        }
+        double *probes = op->probes, *M = op->gjM;
+        int* fail = (int*)(op->d_scal + 940);        // read back with the right-hand-side norm of the next solve
+        PLB_CUDA(ctx, cudaMemsetAsync(probes, 0, sizeof(double) * (size_t)n * 2 * P, ctx->stream));
+        PLB_CUDA(ctx, cudaMemsetAsync(M, 0, sizeof(double) * (size_t)n * 2 * n, ctx->stream));
+        PLB_CUDA(ctx, cudaMemsetAsync(fail, 0, sizeof(double), ctx->stream));
         if (!op->cinv) PLB_CUDA(ctx, cudaMalloc(&op->cinv, sizeof(double) * (size_t)n * n));
         k_probe_set<<<grid2d(Lc.nz, Lc.nxx), block2d(), 0, ctx->stream>>>(D, n, P, probes);
         PLB_LAUNCHED(ctx);
@@ -1345,32 +1370,31 @@ int setup_hierarchy(plb_stokes* op) {
         PLB_LAUNCHED(ctx);
         k_extract_inverse<<<(int)(((size_t)n * n + 255) / 256), 256, 0, ctx->stream>>>(n, M, op->cinv);
         PLB_LAUNCHED(ctx);
-        int hfail = 0;
-        PLB_CUDA(ctx, cudaMemcpyAsync(&hfail, fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(probes), cudaFree(M), cudaFree(fail);
-        if (hfail) PLB_FAIL(ctx, "Stokes MG: singular coarse-level operator");
         op->nc = n;
     }
     // capture the V-cycle of the small levels (<= 1025 rows, replicated: no NCCL calls inside) into a
     // CUDA graph: those levels are launch-latency-bound (~10 launches of a few microseconds each)
     // (kernel arguments only change with the eigenvalue estimates: re-capture only then)
-    if (op->graph_exec && (fresh || !op->use_graph)) cudaGraphExecDestroy(op->graph_exec), op->graph_exec = nullptr;
+    int lg = -1;
+    for (int l = 1; l < nlev; l++)
+        if (!op->lv[l].dist && op->lv[l].nz <= 1025) { lg = l; break; }
+    const bool all = op->graph_all == 1 || (op->graph_all < 0 && !op->lv[0].dist);
+    if (all) lg = 0;
+    plb_stokes::GraphSig sig;
+    sig.etas = lg == 0 ? op->lv[0].etas : nullptr, sig.etan = lg == 0 ? op->lv[0].etan : nullptr;   // levels >= 1 own theirs
+    sig.cinv = op->cinv, sig.nu = op->nu, sig.nu_coarse = op->nu_coarse, sig.nc = op->nc;
+    sig.tile = op->tile_smoother, sig.all = all ? 1 : 0, sig.level = lg, sig.cheb_ratio = op->cheb_ratio;
+    for (int l = 0; l < nlev; l++) sig.lmax.push_back(op->lv[l].lmax);
+    if (op->graph_exec && (!op->use_graph || !(sig == op->graph_sig)))
+        cudaGraphExecDestroy(op->graph_exec), op->graph_exec = nullptr;
     if (!op->graph_exec) op->graph_level = -1;
     if (op->use_graph && !op->graph_exec) {
-        int lg = -1;
-        for (int l = 1; l < nlev; l++)
-            if (!op->lv[l].dist && op->lv[l].nz <= 1025) { lg = l; break; }
         // Default on one GPU: record the WHOLE cycle (~70 launches) -- small and medium grids are bound by
         // the host's enqueue rate (2049^2: 67 -> 53 ms per solve).  With slabs the cycle also contains
         // ~35 grouped NCCL send/recv calls; capturing them works ("graph_all" = 1, tested on 2/4/8 GPUs)
         // but brings nothing there (the NCCL kernels' own latency on the device timeline is the bound),
         // so slab solves keep the graph for the replicated small levels only.
-        const bool all = op->graph_all == 1 || (op->graph_all < 0 && !op->lv[0].dist);
-        if (all) {
-            lg = 0;
-            if (!op->zv && zalloc(ctx, &op->zv, 2 * op->lv[0].plane)) return 2;
-        }
+        if (all && !op->zv && zalloc(ctx, &op->zv, 2 * op->lv[0].plane)) return 2;
         if (lg >= 0 && lg < nlev) {
             Level& Lg = op->lv[lg];
             double* gout = lg == 0 ? op->zv : Lg.X;
@@ -1400,6 +1424,7 @@ int setup_hierarchy(plb_stokes* op) {
             PLB_CUDA(ctx, cudaGraphInstantiate(&op->graph_exec, graph, 0));
             cudaGraphDestroy(graph);
             op->graph_level = lg;
+            op->graph_sig = sig;
         }
     }
     op->hierarchy = true;
@@ -1458,7 +1483,7 @@ void plb_stokes_destroy(plb_stokes* op) {
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
     if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
-    double* ptrs[] = {op->d_scal, op->cinv, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->zv, op->surf_d};
+    double* ptrs[] = {op->d_scal, op->cinv, op->probes, op->gjM, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->zv, op->surf_d};
     for (double* p : ptrs) if (p) cudaFree(p);
     for (double* p : op->hist) if (p) cudaFree(p);
     plb_reduce_ws_free(&op->rws);
@@ -1468,15 +1493,15 @@ void plb_stokes_destroy(plb_stokes* op) {
 int plb_stokes_set_param(plb_stokes* op, const char* name, double value) {
     if (!op || !name) return 1;
     plb_ctx* ctx = op->ctx;
-    if (!strcmp(name, "nu")) op->nu = (int)value;
+    if (!strcmp(name, "nu")) op->nu = (int)value, op->hierarchy = false;
     else if (!strcmp(name, "gcr_m")) {
         if (value < 2 || value > 800) PLB_FAIL(ctx, "plb_stokes_set_param: gcr_m out of range 2..800");
         op->gcr_m = (int)value;
     }
     else if (!strcmp(name, "coarsen_wide")) op->coarsen_wide = (int)value, op->hierarchy = false;
-    else if (!strcmp(name, "cheb_ratio")) op->cheb_ratio = value;
+    else if (!strcmp(name, "cheb_ratio")) op->cheb_ratio = value, op->hierarchy = false;
     else if (!strcmp(name, "dense_max")) op->dense_max = (int)value, op->hierarchy = false;
-    else if (!strcmp(name, "nu_coarse")) op->nu_coarse = (int)value;
+    else if (!strcmp(name, "nu_coarse")) op->nu_coarse = (int)value, op->hierarchy = false;
     else if (!strcmp(name, "reorth")) op->reorth = (int)value;
     else if (!strcmp(name, "rtol_accept")) op->rtol_accept = value;
     else if (!strcmp(name, "hydrostatic")) op->hydrostatic = (int)value;
@@ -1500,6 +1525,7 @@ int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_
     L.etas = d_etas, L.etan = d_etan;
     op->rho = d_rho, op->g_z = gz, op->g_x = gx;
     op->surf = 0;      // the stabilisation planes belong to the previous density field: off until set again
+    op->floor_est = 0; // a residual floor belongs to the system it was met on
     // mineta over both fields INCLUDING the ghost row/column of etan, like np.min (:116)
     double* d = op->d_scal + 920;
     k_set1<<<1, 1, 0, ctx->stream>>>(d, INFINITY);
@@ -1521,6 +1547,7 @@ int plb_stokes_set_surfstab(plb_stokes* op, double theta_dt) {
     if (!op) return 1;
     plb_ctx* ctx = op->ctx;
     if (!op->coeffs) PLB_FAIL(ctx, "plb_stokes_set_surfstab: coefficients not set");
+    op->floor_est = 0;
     if (!(theta_dt > 0)) {
         op->surf = 0;
         return 0;
@@ -1615,6 +1642,7 @@ int plb_stokes_vcycle(plb_stokes* op, const double* d_b2, double* d_x2) {
 int plb_stokes_last_stats(plb_stokes* op, double* h_out) {
     if (!op) return 1;
     h_out[0] = op->last_iters, h_out[1] = op->last_vcycles, h_out[2] = op->last_relres, h_out[3] = op->floor_est;
+    h_out[4] = op->last_status, h_out[5] = op->last_rtol_eff;
     return 0;
 }
 
@@ -1686,7 +1714,15 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     if (stokes_resid(op->t3, r)) return 2;
     double bn2;
     if (plb_dot(ctx, &op->rws, 3 * P, r, r, op->d_scal + 910)) return 2;
-    if (plb_read_scalars(ctx, op->d_scal + 910, 1, &bn2)) return 2;
+    {
+        // one read-back: the norm and the failure flag of the coarse-level inverse built by setup_hierarchy
+        double h[31];
+        if (plb_read_scalars(ctx, op->d_scal + 910, 31, h)) return 2;
+        bn2 = h[0];
+        int hfail;
+        memcpy(&hfail, &h[30], sizeof(int));
+        if (hfail) PLB_FAIL(ctx, "Stokes MG: singular coarse-level operator");
+    }
     const double bnorm = sqrt(bn2);
     // initial guess: the previous solve's iterate (deviation from its hydrostatic pressure) when
     // warm starts are enabled, otherwise zero
@@ -1762,7 +1798,8 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     };
     plb_fgmres_result res;
     op->kry.reorth_thresh = op->kry_reorth;
-    // the residual floor met by an earlier solve on this grid bounds what any later one can reach
+    // a floor met by an earlier solve on these SAME coefficient fields (re-solves of the surfstab loop,
+    // repeated solves of one system) bounds what this one can reach; new coefficients reset it
     const double rtol_eff = std::max(rtol, 3 * op->floor_est);
     if (bnorm > 0) {
         if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol_eff, maxit, &res)) return 2;
@@ -1772,6 +1809,8 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     }
     const int total = res.iters;
     op->last_iters = total, op->last_vcycles = vcycles, op->last_relres = res.relres;
+    op->last_rtol_eff = rtol_eff;
+    op->last_status = (res.converged && res.relres <= 1.5 * rtol) ? 0 : (res.relres <= op->rtol_accept ? 1 : 2);
     op->have_prev = res.converged || res.relres <= op->rtol_accept;
     if (h_iters) *h_iters = total;
     if (h_relres) *h_relres = res.relres;

@@ -21,14 +21,12 @@ DEFAULT_RTOL = 1e-13
 DEFAULT_MAXIT = 400
 
 
-def gidx(idxs, nx, dim):
-    """Global DOF index (pylamp_diff.py:15-28)."""
-    if len(idxs) != dim:
-        raise Exception("num of idxs != dimensions")
+def gidx(idxs, nx):
+    """Global DOF index (pylamp_diff.py:15-28: two arguments, the dimension is len(nx))."""
+    dim = len(nx)
     if dim == 2:
         return idxs[IZ] * nx[IX] + idxs[IX]
-    elif dim == 3:
-        return idxs[IZ] * nx[IX] * nx[IY] + idxs[IX] * nx[IY] + idxs[IY]  # noqa: F405
+    print("!!! NOT IMPLEMENTED")                                             # :26
 
 
 def x2t(x, nx):

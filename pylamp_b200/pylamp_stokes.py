@@ -31,9 +31,8 @@ def gidx(idxs, nx, dim):
     if len(idxs) != dim:
         raise Exception("num of idxs != dimensions")
     if dim == 2:
-        return idxs[IZ] * nx[IX] * (DIM + 1) + idxs[IX] * (DIM + 1)
-    elif dim == 3:
-        return idxs[IZ] * nx[IX] * nx[IY] * (DIM + 1) + idxs[IX] * nx[IY] * (DIM + 1) + idxs[IY] * (DIM + 1)  # noqa: F405
+        return idxs[IZ] * nx[IX] * (dim + 1) + idxs[IX] * (dim + 1)
+    print("!!! NOT IMPLEMENTED")                                             # :32-33
 
 
 def x2vp(x, nx):
@@ -71,6 +70,8 @@ class StokesOperator:
                                             gz.ctypes.data_as(_lib.DP), gx.ctypes.data_as(_lib.DP),
                                             _lib.int_array(self.bc), C.byref(h)))
         self.h = h
+        self.warn_unconverged = True
+        self.converged = None
         self.set_coeffs(f_etas, f_etan, f_rho)
 
     def set_coeffs(self, f_etas, f_etan, f_rho):
@@ -135,15 +136,21 @@ class StokesOperator:
         self.iterations, self.relres = it.value, rr.value
         if rc != 0 and raise_on_fail:
             self.ctx.check(rc)
+        self.converged = rr.value <= 1.5 * float(rtol)
+        if rc == 0 and not self.converged and self.warn_unconverged:
+            import warnings
+            warnings.warn("Stokes solve stopped at relres %.2e > rtol %.1e (fp64 residual floor or stagnation; "
+                          "accepted below rtol_accept) -- see StokesOperator.stats" % (rr.value, rtol))
         if self.ctx.comm_info()[1] > 1:
             self.ctx.allreduce(x)       # every slab rank filled its own rows: sum the pieces
         return x.cpu().numpy() if host else x
 
     @property
     def stats(self):
-        out = (C.c_double * 4)()
+        out = (C.c_double * 6)()
         self.ctx.check(self.ctx.lib.plb_stokes_last_stats(self.h, out))
-        return {"iterations": int(out[0]), "vcycles": int(out[1]), "relres": out[2], "floor": out[3]}
+        return {"iterations": int(out[0]), "vcycles": int(out[1]), "relres": out[2], "floor": out[3],
+                "status": ("converged", "accepted_above_rtol", "not_converged")[int(out[4])], "rtol_eff": out[5]}
 
     def close(self):
         if getattr(self, "h", None):

@@ -21,8 +21,8 @@ INTERP_AVG_GEOMETRIC = 2
 INTERP_AVG_WEIGHTED = 4
 INTERP_AVG_ARITHW = 5
 INTERP_AVG_GEOMW = 6
-INTERP_METHOD_GRIDDATA = 1
-INTERP_METHOD_IDW = 2
+INTERP_METHOD_IDW = 1
+INTERP_METHOD_GRIDDATA = 2
 INTERP_METHOD_ELEM = 4
 INTERP_METHOD_NEAREST = 8
 INTERP_METHOD_LINEAR = 16

@@ -144,6 +144,38 @@ def solcx_fields(n, eta_right=1e6):
     return nx, L, grid, gridmp, etas, etan, rho
 
 
+def convection_fields(ncell, t=0.0, Ra=1e6, Lbox=1e6, shift_cells=0.3):
+    """C4-type coefficient fields given analytically on the node / centre grids (no markers), as a
+    function of a step counter `t`: the temperature field of `convection` with a 10 % lateral
+    perturbation plus a plume-like anomaly, translated by `shift_cells` cells per unit of t --
+    i.e. what consecutive time steps of the loop hand to the Stokes solve.  Used for solver parity at
+    sizes where only ONE direct solve is affordable (tests/golden/large_*.npz hold the reference's
+    solution at t = 0; the GPU solver is stepped through t = -n..0 with its time-loop settings).
+    Returns (nx, L, grid, gridmp, f_etas, f_etan, f_rho)."""
+    nx, L = [ncell + 1, ncell + 1], [Lbox, Lbox]
+    grid, gridmp = make_grids(nx, L)
+    rho0, alpha, k, cp, Ea, Tref = 3300.0, 3.5e-5, 4.0, 1250.0, 120e3, 1623.0
+    dT = 1623.0 - 273.0
+    eta0 = rho0 * G[IZ] * alpha * dT * Lbox ** 3 / ((k / (rho0 * cp)) * Ra)
+    s = shift_cells * t / ncell
+
+    def temp(z, x):
+        zn, xn = z / Lbox, x / Lbox - s
+        T = 273.0 + dT * zn + 0.10 * dT * np.sin(np.pi * zn) * np.cos(2 * np.pi * xn)
+        T = T + 0.25 * dT * np.exp(-((xn - 0.37) ** 2 + (zn - 0.55) ** 2) / 0.01) * np.sin(np.pi * zn)
+        return np.clip(T, 273.0, 1900.0)
+
+    def eta(T):
+        return np.clip(eta0 * np.exp(Ea / (GASR * T) - Ea / (GASR * Tref)), 1e17, 1e23)
+
+    zs, xs = np.meshgrid(grid[IZ], grid[IX], indexing="ij")
+    zc, xc = np.meshgrid(gridmp[IZ], gridmp[IX], indexing="ij")
+    Ts = temp(zs, xs)
+    f_etas, f_etan = eta(Ts), eta(temp(zc, xc))
+    f_rho = rho0 / (alpha * (Ts - Tref) + 1)
+    return nx, L, grid, gridmp, f_etas, f_etan, f_rho
+
+
 def convection_device(ncell=4096, per_side=4, seed=11, Ra=1e6, Lbox=1e6, device="cuda", rank=0, world=1):
     """`convection` generated directly in HBM with torch (the 4096^2 case has 2.7e8 markers: ~32 GB
     of host arrays otherwise).  Same lattice/ordering/physics; the jitter comes from torch's RNG,

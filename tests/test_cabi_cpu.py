@@ -63,4 +63,4 @@ def test_host_modules_keep_reference_names():
         assert hasattr(pylamp_diff, name)
     assert pylamp_const.EPS == 2 ** -10 and pylamp_const.NFTRAC == 13
     assert pylamp_stokes.gidx([2, 3], [10, 7], 2) == 2 * 7 * 3 + 3 * 3
-    assert pylamp_diff.gidx([2, 3], [10, 7], 2) == 2 * 7 + 3
+    assert pylamp_diff.gidx([2, 3], [10, 7]) == 2 * 7 + 3       # reference signature: gidx(idxs, nx)

@@ -2,10 +2,9 @@
 GPU: finalising all rows of the scattered planes must reproduce plb_trac2grid bit for bit (same
 kernels, same planes), and a row range must fill exactly that range.
 
-WRITTEN AFTER ROUND 1's GPU BUDGET WAS SPENT (host-side C++ around tested kernels; never run): opt-in with
-PLB_RUN_UNVERIFIED=1 until it has passed once on a B200.  The communication part (slabgrid.py) is
+First run on a B200 in round 2 (profiles/r02_gpu_unverified.log).  The communication part (slabgrid.py) is
 tested under gloo in tests/test_slabgrid_cpu.py; the 2-GPU run is
-`scripts/multi_gpu_driver_check.py 64 3 slab reduce`."""
+`scripts/multi_gpu_driver_check.py 64 3 slab reduce` (tests/test_multi_gpu.py)."""
 import ctypes as C
 import os
 
@@ -15,9 +14,7 @@ import torch
 
 from oracle import pylamp_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PLB_RUN_UNVERIFIED") != "1",
-                                 reason="not yet verified on a GPU (set PLB_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_scatter_finalise_equals_trac2grid():

@@ -2,10 +2,8 @@
 `surfstab=True` against the oracle (whose assembly and re-solve loop are pinned to the reference,
 tests/test_oracle_golden.py).
 
-WRITTEN AFTER ROUND 1's GPU BUDGET WAS SPENT: the CUDA side (stokes.cu: k_surfstab_planes, the SURF
-instantiations of k_stokes_op / k_stokes_op_tile / k_stokes_full) has compiled but never run.  These tests
-are therefore opt-in (PLB_RUN_UNVERIFIED=1) until they have passed once on a B200; the default
-instantiations of the touched kernels are instruction-for-instruction identical to the tested ones.
+First run on a B200 in round 2 (profiles/r02_gpu_unverified.log: all green); since then part of the
+default `-m gpu` suite.
 """
 import os
 
@@ -15,9 +13,7 @@ import pytest
 from oracle import pylamp_oracle as O
 from pylamp_b200 import setups
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PLB_RUN_UNVERIFIED") != "1",
-                                 reason="surfstab CUDA path not yet verified on a GPU (set PLB_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _comp_err(x, ref):
