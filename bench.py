@@ -33,6 +33,23 @@ CLASS_NAMES = {0: "k_cheb (Chebyshev-Jacobi smoother sweep, finest level)",
 SINGLE_KERNEL_CLASSES = (0, 1, 2, 3, 4, 5, 6, 9)
 
 
+# Solver settings of the timed loop.  stokes_rtol: the scaled TRUE residual (relative to the flow-driving load)
+# every timed solve must reach; measured on the B200 (profiles/r02_SUMMARY.md): the fp64 floor of that residual
+# at 4097^2 nodes is 2.0e-10 (3e-12 at 513^2), and a solve stopped at 9e-10 is 5e-12 / 1.4e-11 / 9e-15 away from
+# the reference's direct solve in vz / vx / P~ (513^2; north_star asks for 1e-8).  tests/test_stokes_large_gpu.py imports exactly these to hold the
+# time-loop solver (not a specially tightened one) to the 1e-8 parity bound against the reference's direct
+# solve at 513^2 and 1025^2 nodes.
+DEFAULTS = {"warm_start": 5, "nu": 2, "gmres_m": 30, "lmax_every": 8, "stokes_rtol": 1e-9, "heat_rtol": 1e-11}
+
+
+def stokes_params(warm_start=None, nu=None, gmres_m=None):
+    d = DEFAULTS
+    return {"warm_start": d["warm_start"] if warm_start is None else warm_start,
+            "gcr_m": d["gmres_m"] if gmres_m is None else gmres_m, "lmax_every": d["lmax_every"],
+            "nu": d["nu"] if nu is None else nu,
+            "graph_all": 0}     # keep the V-cycle's kernels individually event-timed (whole-cycle graph: no gain at 4096^2)
+
+
 def peaks():
     """HBM peak: MEASURED_PEAKS.json (driver-written) else the profiling guide's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -149,8 +166,8 @@ def run_b200(args):
     o.heat_rtol = args.heat_rtol
     o.marker_ownership = args.marker_ownership
     o.slab_reduce = bool(args.slab_reduce)
-    o.stokes_params = {"warm_start": args.warm_start, "gcr_m": args.gmres_m, "lmax_every": 8, "nu": args.nu,
-                       "graph_all": 0}     # keep the V-cycle's kernels individually event-timed (whole-cycle graph: no gain at 4096^2)
+    o.stokes_rtol = args.stokes_rtol
+    o.stokes_params = stokes_params(args.warm_start, args.nu, args.gmres_m)
     M = s.ntrac
     if world > 1:
         tm = torch.tensor([M], dtype=torch.int64, device="cuda")
@@ -255,7 +272,11 @@ def run_b200(args):
                        (world, "owned by z-slab with migration after every step" if args.marker_ownership == "slab"
                         else "shared by index (no migration needed)"),
                        "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
-                       "spinup_steps": args.spinup, "stokes_rtol": o.stokes_rtol, "heat_rtol": o.heat_rtol, "smoother_steps": args.nu, "stokes_solver": "FGMRES(%d) + GMG V(nu,nu) Chebyshev-Jacobi (--nu), warm start by polynomial extrapolation of the last %d iterates, eigenvalue estimates every 8 steps" % (args.gmres_m, args.warm_start)},
+                       "spinup_steps": args.spinup, "stokes_rtol": o.stokes_rtol,
+                       "stokes_rtol_eff_max": max(i.get("stokes_rtol_eff", 0.0) for i in iters),
+                       "stokes_relres_max": max(i.get("stokes_relres", 0.0) for i in iters),
+                       "stokes_floor_est_max": max(i.get("stokes_floor", 0.0) for i in iters),
+                       "stokes_all_converged_to_rtol": all(i.get("stokes_status") == "converged" for i in iters), "heat_rtol": o.heat_rtol, "smoother_steps": args.nu, "stokes_solver": "FGMRES(%d) + GMG V(nu,nu) Chebyshev-Jacobi (--nu), warm start by polynomial extrapolation of the last %d iterates, eigenvalue estimates every 8 steps" % (args.gmres_m, args.warm_start)},
             "stokes_dof_per_s": 3.0 * N / (ms_step * 1e-3),
             "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_stencil": roofline_stencil, "phases_ms_per_step": phase_ms,
@@ -318,10 +339,12 @@ def main():
     ap.add_argument("--ncell", type=int, default=4096, help="cells per side of the GPU workload")
     ap.add_argument("--per-side", type=int, default=4, help="markers per cell side (16/cell)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--heat-rtol", type=float, default=1e-11, help="tolerance of the energy solve")
-    ap.add_argument("--warm-start", type=int, default=5, help="Stokes initial guess: 0 zero, 1 previous iterate, p >= 2: polynomial extrapolation of the last p iterates")
-    ap.add_argument("--nu", type=int, default=2, help="Chebyshev steps per pre-/post-smoothing")
-    ap.add_argument("--gmres-m", type=int, default=30, help="FGMRES restart length of the Stokes solve")
+    ap.add_argument("--heat-rtol", type=float, default=DEFAULTS["heat_rtol"], help="tolerance of the energy solve")
+    ap.add_argument("--stokes-rtol", type=float, default=DEFAULTS["stokes_rtol"],
+                    help="tolerance of the Stokes solve (scaled true residual, relative to the flow-driving load)")
+    ap.add_argument("--warm-start", type=int, default=DEFAULTS["warm_start"], help="Stokes initial guess: 0 zero, 1 previous iterate, p >= 2: polynomial extrapolation of the last p iterates")
+    ap.add_argument("--nu", type=int, default=DEFAULTS["nu"], help="Chebyshev steps per pre-/post-smoothing")
+    ap.add_argument("--gmres-m", type=int, default=DEFAULTS["gmres_m"], help="FGMRES restart length of the Stokes solve")
     ap.add_argument("--marker-ownership", default="index", choices=["index", "slab"],
                     help="several GPUs: markers stay with their rank (index) or are owned by z-slab and migrate (slab)")
     ap.add_argument("--slab-reduce", type=int, default=0,

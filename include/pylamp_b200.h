@@ -82,6 +82,42 @@ int plb_comm_info(plb_ctx* ctx, int* h_rank, int* h_size);
 int plb_allreduce(plb_ctx* ctx, double* d_buf, long long count, int op);
 void plb_comm_destroy(plb_ctx* ctx);
 
+/* ---- the marker->grid targets of one time step in ONE pass over the markers -------------------
+ * (pylamp2.py:309-313 calls trac2grid four times -- nodes, cell centres, the two half-staggered grids --
+ * and once more at :478; each call re-reads the coordinates and recomputes the cell of every marker.)
+ * kind: 0 = (z-node, x-node), 1 = (z-mid, x-mid), 2 = (z-mid, x-node), 3 = (z-node, x-mid), where the
+ * "mid" axes hold the midpoints of the node axis plus one point beyond the end (pylamp2.py:92-95).
+ * axis_z/axis_x: the target's axes AFTER the ghost-node extension of pylamp_trac.py:207-217 (staggered
+ * axes must carry >= 1 ghost node on the low side), crop_*: number of ghost nodes prepended.  Weighted
+ * schemes only (PLB_AVG_ARITHMETIC|PLB_AVG_WEIGHTED, PLB_AVG_GEOMETRIC|PLB_AVG_WEIGHTED).  Every distinct
+ * marker column is read once.  Returns 3, leaving the outputs untouched, when the request does not fit
+ * (unweighted scheme, > 8 distinct columns, missing ghost node): use plb_trac2grid per target then. */
+typedef struct {
+    int kind;
+    int k;
+    const double* fields[PLB_MAX_FIELDS];
+    int scheme[PLB_MAX_FIELDS];
+    const double* axis_z;
+    int nze;
+    const double* axis_x;
+    int nxe;
+    int crop_z0, crop_x0;
+    double* out[PLB_MAX_FIELDS];
+} plb_t2g_target;
+int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, int nxx, int ld, double z0,
+                        double zlen, double x0, double xlen, int ntargets, const plb_t2g_target* h_targets);
+
+/* ---- marker-by-cell sort (device counting sort; no reference counterpart: NumPy's np.add.at at
+ * pylamp_trac.py:257-298 is order-blind, on the GPU the order decides how well the node sums aggregate
+ * and how local the gathers of grid2trac / RK are).  plb_sort_plan: d_dest[m] = slot of marker m in
+ * cell-major order, cells numbered ie*(nxx-1)+je with the exact floor((n-1)*x/L) of pylamp2.py:588-589
+ * (markers outside the box are clamped into the nearest cell); d_cell_start ((nz-1)*(nxx-1)+1 ints,
+ * may be NULL) receives the first slot of every cell.  plb_permute: d_out[d_dest[m]] = d_in[m] for rows
+ * of `width` (1 or 2) doubles; d_out must not alias d_in. */
+int plb_sort_plan(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, int nxx, double Lz, double Lx,
+                  unsigned* d_dest, int* d_cell_start);
+int plb_permute(plb_ctx* ctx, long long M, const unsigned* d_dest, const double* d_in, double* d_out, int width);
+
 /* ---- markers -> grid: pylamp_trac.trac2grid, pylamp_trac.py:161-318 -------------------- */
 /* h_out[4] = min z, max z, min x, max x over the markers (the ghost-node extension test of
  * pylamp_trac.py:207-217 is a global min/max).  Synchronises. */

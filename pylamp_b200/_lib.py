@@ -35,6 +35,8 @@ _PROTOS = {
     "plb_allreduce": (I, [VP, VP, LL, I]),
     "plb_comm_destroy": (None, [VP]),
     "plb_marker_minmax": (I, [VP, LL, VP, DP]),
+    "plb_sort_plan": (I, [VP, LL, VP, I, I, D, D, VP, VP]),
+    "plb_permute": (I, [VP, LL, VP, VP, VP, I]),
     "plb_trac2grid": (I, [VP, LL, VP, I, PP, IP, VP, I, VP, I, D, D, D, D, I, I, I, I, I, PP]),
     "plb_trac2grid_scatter": (I, [VP, LL, VP, I, PP, IP, VP, I, VP, I, D, D, D, D, VP, IP]),
     "plb_trac2grid_finalise": (I, [VP, I, IP, VP, I, I, I, I, I, I, I, I, I, PP]),
@@ -72,6 +74,17 @@ _PROTOS = {
     "plb_diff_apply": (I, [VP, VP, VP]),
     "plb_diff_solve": (I, [VP, VP, D, I, VP, IP, DP]),
 }
+
+
+
+class T2GTarget(C.Structure):
+    """plb_t2g_target of include/pylamp_b200.h"""
+    _fields_ = [("kind", C.c_int), ("k", C.c_int), ("fields", C.c_void_p * 8), ("scheme", C.c_int * 8),
+                ("axis_z", C.c_void_p), ("nze", C.c_int), ("axis_x", C.c_void_p), ("nxe", C.c_int),
+                ("crop_z0", C.c_int), ("crop_x0", C.c_int), ("out", C.c_void_p * 8)]
+
+
+_PROTOS["plb_trac2grid_fused"] = (I, [VP, LL, VP, I, I, I, D, D, D, D, I, C.POINTER(T2GTarget)])
 
 _lib = None
 _lock = threading.Lock()

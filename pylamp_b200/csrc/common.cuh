@@ -30,6 +30,7 @@ struct plb_ctx {
     double* prof_bytes;    // algorithmic bytes per recorded pair
     // tuning knobs (plb_ctx_set_param)
     int t2g_variant;       // 1: wide-load chunk kernel for weighted schemes (default), 0: generic kernel only
+    int t2g_parts;         // fused step kernel: lanes per run (0: automatic; 1, 2, 4)
 };
 
 // kernel classes for plb_profile_* (bench.py's roofline block)
@@ -46,6 +47,7 @@ enum {
     PLB_K_PRECRHS = 9,   // preconditioner right-hand side
     PLB_K_DIFF = 10,     // heat operator
     PLB_K_MARKER_MISC = 11,
+    PLB_K_SORT = 12,     // marker-by-cell sort: permutation of the marker arrays
     PLB_K_NCLASS = 16
 };
 

@@ -79,6 +79,10 @@ int plb_ctx_set_param(plb_ctx* ctx, const char* name, double value) {
         ctx->t2g_variant = (int)value;
         return 0;
     }
+    if (!strcmp(name, "t2g_parts")) {
+        ctx->t2g_parts = (int)value;
+        return 0;
+    }
     PLB_FAIL(ctx, "plb_ctx_set_param: unknown parameter '%s'", name);
 }
 

@@ -87,6 +87,9 @@ int plb_fgmres(plb_ctx* ctx, plb_reduce_ws* rws, plb_fgmres_ws* ws, Residual res
         double beta = sqrt(ws->h_coef[0]);
         if (!(beta == beta)) PLB_FAIL(ctx, "FGMRES: residual is NaN");
         res->relres = beta / bnorm;
+        if (getenv("PLB_DEBUG_FGMRES"))
+            fprintf(stderr, "  fgmres restart at it %d: TRUE relres %.6e (Arnoldi estimate at the end of the cycle before: %.6e)\n",
+                    total, res->relres, est_prev >= 0 ? est_prev / bnorm : -1.0);
         // (after at least one cycle a true residual within 1.5x of the target is accepted: another
         // restart cycle would spend tens of iterations on a few percent)
         if (beta <= rtol * bnorm || (total > 0 && beta <= 1.5 * rtol * bnorm)) {

@@ -4,6 +4,8 @@
 //
 // Reference behaviour restated (never copied): pylamp_trac.py:30-158 (grid2trac), :161-318
 // (trac2grid), :321-388 (RK); pylamp2.py:291-303, :471-476, :558-572, :588-593.
+#include <algorithm>
+
 #include "comm.cuh"
 
 namespace {
@@ -802,6 +804,285 @@ k_subgrid_fused2(long long M, const double2* __restrict__ trx, G2TGrid g, const 
     if ((threadIdx.x & 31) == 0 && bad_local) atomicAdd(n_outside, (unsigned long long)bad_local);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused marker->grid pass for the targets of one time step (pylamp2.py:309-313: nodes, cell centres
+// and the two half-staggered grids; :478: the subgrid term on the nodes).
+//
+// A CTA stages a chunk of TF_NM consecutive markers -- the coordinates and every distinct property
+// column, each read from HBM exactly once per step -- in shared memory with 1-D bulk async copies
+// (TMA: cp.async.bulk + mbarrier), takes the logarithm of the geometrically averaged columns in
+// place, and splits the chunk into RUNS of consecutive markers of one node-grid cell (after the
+// marker-by-cell sort a run is a cell's whole population).  A thread then owns a (run, target) pair:
+// it walks the run's markers in shared memory and keeps the sums of that cell's destination nodes
+// (2x2 on the node grid; 3x3 / 3x2 / 2x3 on the staggered grids, where the half cell a marker lies
+// in selects two of three candidate nodes per staggered axis) in registers -- one FMA per
+// (marker, node, quantity), no shuffles, no masks -- and adds them to the planes once per run.
+// Correct for any marker order (an unsorted cloud just has runs of length one).  Same weights as the
+// reference: (1-a), 1-(1-a) per axis, multiplied x then z (pylamp_trac.py:247-255).
+// ---------------------------------------------------------------------------------------------
+constexpr int TF_NM = 1024, TF_THREADS = 256, TF_MAXC = 8, TF_MAXT = 8;
+
+struct TFTask {
+    int type;              // 0: 2x2 (node axes), 1: 3x3 (both axes staggered), 2: 3x2 (z staggered), 3: 2x3 (x staggered)
+    int nf, ws;            // fields of this task (type 0: <= 3, else 1); accumulate the weight sums too
+    int col[3];            // staged column of each field
+    const double2* tz;     // {coordinate, 1/spacing} of the target's (ghost-extended) axes
+    const double2* tx;
+    int lz, lx;            // extended index of the first destination row / column of node-grid cell 0
+    int nxe;               // row length of the target's planes
+    double* wsum;
+    double* acc[3];
+};
+
+struct TFArgs {
+    const double* col[TF_MAXC];
+    int ncol;
+    unsigned logmask;      // columns averaged geometrically: staged as log(value)
+    double z0, x0, sz, sx; // node grid: first node and cells per unit length
+    int ncz, ncx;          // node-grid cells
+    TFTask t[TF_MAXT];
+    int nt;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tf_bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ int tf_cell(double v, double v0, double s, int nc) {
+    int i = __double2int_rd((v - v0) * s);
+    return i < 0 ? 0 : (i > nc - 1 ? nc - 1 : i);
+}
+
+template <int R>
+__device__ __forceinline__ void tf_axis_weights(double v, const double2& t0, const double2& t1, double (&w)[R]) {
+    if (R == 2) {
+        const double a = (v - t0.x) * t0.y;          // pylamp_trac.py:247
+        w[0] = 1 - a;                                 // :252 (1 - a)
+        w[1] = 1 - w[0];                              // :249, :253 (1 - b), b = 1 - a
+    } else {
+        const bool lower = v < t1.x;                  // which half of the node-grid cell
+        const double2 t = lower ? t0 : t1;
+        const double a = (v - t.x) * t.y;
+        const double u = 1 - a, q = 1 - u;
+        w[0] = lower ? u : 0.0;
+        w[1] = lower ? q : u;
+        w[R - 1] = lower ? 0.0 : q;
+    }
+}
+
+// PARTS lanes share a run: each walks 1/PARTS of its markers (shorter dependent chains, finer work items),
+// the partial sums are combined with xor-shuffles and the first lane of the group adds them to the planes.
+// Every lane of the warp calls this (lanes without a run pass len = 0): the shuffles are warp-wide.
+template <int RZ, int RX, int NF, int PARTS>
+__device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const double2* __restrict__ sx,
+                                       const double* __restrict__ sv, int s, int len, int run, int part) {
+    const double2 p0 = sx[s];                            // (lanes without a run pass s = 0, len = 0)
+    const int ie = tf_cell(p0.x, a.z0, a.sz, a.ncz), je = tf_cell(p0.y, a.x0, a.sx, a.ncx);
+    const int ez = ie + t.lz, ex = je + t.lx;
+    const double2 tz0 = __ldg(t.tz + ez), tx0 = __ldg(t.tx + ex);
+    double2 tz1 = tz0, tx1 = tx0;
+    if (RZ == 3) tz1 = __ldg(t.tz + ez + 1);
+    if (RX == 3) tx1 = __ldg(t.tx + ex + 1);
+    double W[RZ * RX], A[NF][RZ * RX];
+#pragma unroll
+    for (int c = 0; c < RZ * RX; c++) {
+        W[c] = 0;
+#pragma unroll
+        for (int f = 0; f < NF; f++) A[f][c] = 0;
+    }
+    const double* cf[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) cf[f] = sv + t.col[f] * TF_NM + s;
+    const bool ws = t.ws != 0;
+    // lanes of a warp walk different runs: start at different offsets (freshly sorted runs are 16 markers =
+    // one full bank cycle apart, so equal offsets would hit one bank)
+    const int b0 = (len * part) / PARTS, sub = (len * (part + 1)) / PARTS - b0;
+    int idx = run & 15;
+    if (idx >= sub) idx = 0;
+    for (int it = 0; it < sub; it++) {
+        const double2 p = sx[s + b0 + idx];
+        double v[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++) v[f] = cf[f][b0 + idx];
+        double wz[RZ], wx[RX];
+        tf_axis_weights<RZ>(p.x, tz0, tz1, wz);
+        tf_axis_weights<RX>(p.y, tx0, tx1, wx);
+#pragma unroll
+        for (int r = 0; r < RZ; r++)
+#pragma unroll
+            for (int c = 0; c < RX; c++) {
+                const double w = wx[c] * wz[r];       // :252-255
+                if (ws) W[r * RX + c] += w;
+#pragma unroll
+                for (int f = 0; f < NF; f++) A[f][r * RX + c] = fma(v[f], w, A[f][r * RX + c]);
+            }
+        idx++;
+        if (idx == sub) idx = 0;
+    }
+    if (PARTS > 1) {
+#pragma unroll
+        for (int o = 1; o < PARTS; o <<= 1) {
+#pragma unroll
+            for (int c = 0; c < RZ * RX; c++) {
+                W[c] += __shfl_xor_sync(0xffffffffu, W[c], o);
+#pragma unroll
+                for (int f = 0; f < NF; f++) A[f][c] += __shfl_xor_sync(0xffffffffu, A[f][c], o);
+            }
+        }
+        if (part != 0 || len == 0) return;
+    } else if (len == 0) {
+        return;
+    }
+    const long long base = (long long)ez * t.nxe + ex;
+    // A non-finite property value (log of 0, NaN of a marker injected into an empty cell) must reach the nodes
+    // the reference adds it to and no others (pylamp_trac.py:276-298 multiplies by the four real corner weights
+    // only); above it has also met the structurally zero weights of the staggered patterns.  Such a run -- it
+    // shows as a non-finite sum -- is redone marker by marker with the four real corners.
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < RZ * RX; c++)
+#pragma unroll
+        for (int f = 0; f < NF; f++) finite = finite && (fabs(A[f][c]) <= 1.79769313486231570e308);
+    if (!finite) {
+        for (int it = 0; it < len; it++) {
+            const double2 p = sx[s + it];
+            const bool lowz = RZ == 2 || p.x < tz1.x, lowx = RX == 2 || p.y < tx1.x;
+            const double2 az = lowz ? tz0 : tz1, ax = lowx ? tx0 : tx1;
+            const double uz = 1 - (p.x - az.x) * az.y, ux = 1 - (p.y - ax.x) * ax.y;
+            const double w4[4] = {ux * uz, ux * (1 - uz), (1 - ux) * uz, (1 - ux) * (1 - uz)};
+            const long long o = base + (lowz ? 0 : t.nxe) + (lowx ? 0 : 1);
+            const long long o4[4] = {o, o + t.nxe, o + 1, o + t.nxe + 1};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (ws) atomicAdd(t.wsum + o4[c], w4[c]);
+#pragma unroll
+                for (int f = 0; f < NF; f++) atomicAdd(t.acc[f] + o4[c], cf[f][it] * w4[c]);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < RZ; r++)
+#pragma unroll
+        for (int c = 0; c < RX; c++) {
+            const long long o = base + (long long)r * t.nxe + c;
+            // (a destination none of the run's markers reaches keeps exact zeros: nothing to add)
+            if (ws && W[r * RX + c] != 0.0) atomicAdd(t.wsum + o, W[r * RX + c]);
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                if (A[f][r * RX + c] != 0.0) atomicAdd(t.acc[f] + o, A[f][r * RX + c]);
+        }
+}
+
+template <int PARTS>
+__global__ void __launch_bounds__(TF_THREADS, 2)
+k_t2g_fused(long long M, const double2* __restrict__ trx, const TFArgs a, int use_tma) {
+    extern __shared__ __align__(128) unsigned char tf_smem[];
+    double2* sx = (double2*)tf_smem;                                     // [TF_NM]
+    double* sv = (double*)(tf_smem + (size_t)TF_NM * 16);                // [ncol][TF_NM]
+    unsigned short* rstart = (unsigned short*)(sv + (size_t)a.ncol * TF_NM);   // [TF_NM + 1]
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ int cnt[32];
+    __shared__ int nrun_s;
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long m0 = (long long)blockIdx.x * TF_NM;
+    const int n = (int)((M - m0) < (long long)TF_NM ? (M - m0) : (long long)TF_NM);
+    // ---- stage the chunk
+    if (use_tma && n == TF_NM) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)TF_NM * 16u + (unsigned)a.ncol * TF_NM * 8u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+            tf_bulk_load(sx, trx + m0, TF_NM * 16u, &mbar);
+            for (int c = 0; c < a.ncol; c++) tf_bulk_load(sv + (size_t)c * TF_NM, a.col[c] + m0, TF_NM * 8u, &mbar);
+        }
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        }
+    } else {
+        for (int m = tid; m < n; m += TF_THREADS) sx[m] = trx[m0 + m];
+        for (int c = 0; c < a.ncol; c++)
+            for (int m = tid; m < n; m += TF_THREADS) sv[(size_t)c * TF_NM + m] = a.col[c][m0 + m];
+        __syncthreads();
+    }
+    // ---- logarithm of the geometrically averaged columns, in place (once per marker and step)
+    for (int c = 0; c < a.ncol; c++)
+        if ((a.logmask >> c) & 1u)
+            for (int m = tid; m < n; m += TF_THREADS) sv[(size_t)c * TF_NM + m] = log(sv[(size_t)c * TF_NM + m]);
+    // ---- runs of equal node-grid cells: heads -> ordered list of run starts
+    unsigned hb[TF_NM / TF_THREADS];
+#pragma unroll
+    for (int r = 0; r < TF_NM / TF_THREADS; r++) {
+        const int m = r * TF_THREADS + tid;
+        const bool valid = m < n;
+        int key = -2;
+        if (valid) {
+            const double2 p = sx[m];
+            key = tf_cell(p.x, a.z0, a.sz, a.ncz) * a.ncx + tf_cell(p.y, a.x0, a.sx, a.ncx);
+        }
+        int prev = __shfl_up_sync(full, key, 1);
+        if (lane == 0) {
+            prev = -1;
+            if (valid && m > 0) {
+                const double2 p = sx[m - 1];
+                prev = tf_cell(p.x, a.z0, a.sz, a.ncz) * a.ncx + tf_cell(p.y, a.x0, a.sx, a.ncx);
+            }
+        }
+        hb[r] = __ballot_sync(full, valid && key != prev);
+        if (lane == 0) cnt[r * (TF_THREADS / 32) + warp] = __popc(hb[r]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int v = cnt[lane];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full, inc, o);
+            if (lane >= o) inc += t;
+        }
+        cnt[lane] = inc - v;
+        if (lane == 31) nrun_s = inc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TF_NM / TF_THREADS; r++)
+        if ((hb[r] >> lane) & 1u)
+            rstart[cnt[r * (TF_THREADS / 32) + warp] + __popc(hb[r] & ((1u << lane) - 1u))] = (unsigned short)(r * TF_THREADS + tid);
+    if (tid == 0) rstart[nrun_s] = (unsigned short)n;
+    __syncthreads();
+    // ---- work items (task, run, part); the item count of a task is padded to whole warps, so a warp's 32
+    // items share the task (uniform switch) and all its lanes reach the shuffles of tf_run
+    const int nrun = nrun_s, nip = (nrun * PARTS + 31) & ~31, total = a.nt * nip;
+    for (int q = tid; q < total; q += TF_THREADS) {
+        const int ty = q / nip, item = q - ty * nip;
+        const int run = item / PARTS, part = item - run * PARTS;
+        const bool live = run < nrun;
+        const int s = live ? rstart[run] : 0, len = live ? (int)rstart[run + 1] - s : 0;
+        const TFTask& t = a.t[ty];
+        switch (t.type) {
+            case 0:
+                if (t.nf == 1) tf_run<2, 2, 1, PARTS>(a, t, sx, sv, s, len, run, part);
+                else if (t.nf == 2) tf_run<2, 2, 2, PARTS>(a, t, sx, sv, s, len, run, part);
+                else tf_run<2, 2, 3, PARTS>(a, t, sx, sv, s, len, run, part);
+                break;
+            case 1: tf_run<3, 3, 1, PARTS>(a, t, sx, sv, s, len, run, part); break;
+            case 2: tf_run<3, 2, 1, PARTS>(a, t, sx, sv, s, len, run, part); break;
+            default: tf_run<2, 3, 1, PARTS>(a, t, sx, sv, s, len, run, part); break;
+        }
+    }
+}
+
 template <int K>
 void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& a) {
     int threads = 256;
@@ -931,6 +1212,141 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
     k_t2g_finalise<<<plb_grid_for(ctx, (long long)nz * nxx, 256, 8), 256, 0, ctx->stream>>>(
         a, crop_z0, crop_x0, nz, nxx, ld);
     PLB_LAUNCHED(ctx);
+    return 0;
+}
+
+// The step's marker->grid targets in ONE pass over the markers (k_t2g_fused above).  Every target is
+// a (nz x nxx) field on the node grid or on one of its half-staggered companions (kind 1..3: the
+// staggered axes hold the midpoints of the node axis, pylamp2.py:92-95, ghost-extended by >= 1 node on
+// the low side); all schemes must be weighted (ARITHW / GEOMW); at most TF_MAXC distinct columns.
+// Returns 3 (and touches nothing) when the request does not fit these rules: the caller then uses
+// plb_trac2grid once per target.
+int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, int nxx, int ld, double z0,
+                        double zlen, double x0, double xlen, int ntargets, const plb_t2g_target* tg) {
+    if (!ctx || !tg || ntargets < 1) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    TFArgs a;
+    memset(&a, 0, sizeof(a));
+    // ---- distinct columns, task list, plane layout
+    size_t plane_off[8], tab_off[8], ndbl = 0;
+    if (ntargets > 8) return 3;
+    for (int i = 0; i < ntargets; i++) {
+        const plb_t2g_target& T = tg[i];
+        if (T.kind < 0 || T.kind > 3 || T.k < 1 || T.k > PLB_MAX_FIELDS) return 3;
+        const bool sz_ = T.kind == 1 || T.kind == 2, sx_ = T.kind == 1 || T.kind == 3;
+        if ((sz_ && T.crop_z0 < 1) || (sx_ && T.crop_x0 < 1)) return 3;
+        if (T.crop_z0 + nz > T.nze || T.crop_x0 + nxx > T.nxe) return 3;
+        if ((size_t)T.nze * T.nxe >= ((size_t)1 << 31)) return 3;
+        for (int f = 0; f < T.k; f++)
+            if ((T.scheme[f] & (PLB_AVG_ARITHMETIC | PLB_AVG_GEOMETRIC | PLB_AVG_WEIGHTED)) != (PLB_AVG_ARITHMETIC | PLB_AVG_WEIGHTED) &&
+                (T.scheme[f] & (PLB_AVG_ARITHMETIC | PLB_AVG_GEOMETRIC | PLB_AVG_WEIGHTED)) != (PLB_AVG_GEOMETRIC | PLB_AVG_WEIGHTED))
+                return 3;
+        plane_off[i] = ndbl;
+        ndbl += (size_t)(1 + T.k) * T.nze * T.nxe;
+    }
+    const size_t nplane_dbl = ndbl;
+    ndbl = (ndbl + 1) & ~(size_t)1;
+    for (int i = 0; i < ntargets; i++) {
+        tab_off[i] = ndbl;
+        ndbl += 2 * (size_t)(tg[i].nze + tg[i].nxe);          // double2 tables of both axes
+    }
+    const size_t recip_off = ndbl;
+    size_t maxax = 0;
+    for (int i = 0; i < ntargets; i++) maxax = std::max(maxax, (size_t)(tg[i].nze + tg[i].nxe));
+    ndbl += maxax;
+    bool aligned = ((uintptr_t)d_tr_x & 15) == 0;
+    for (int i = 0; i < ntargets; i++) {
+        const plb_t2g_target& T = tg[i];
+        const bool sz_ = T.kind == 1 || T.kind == 2, sx_ = T.kind == 1 || T.kind == 3;
+        const int type = T.kind == 0 ? 0 : (T.kind == 1 ? 1 : (T.kind == 2 ? 2 : 3));
+        const int per = type == 0 ? 3 : 1;                      // fields per task
+        for (int f0 = 0; f0 < T.k; f0 += per) {
+            if (a.nt >= TF_MAXT) return 3;
+            TFTask& t = a.t[a.nt++];
+            t.type = type, t.nf = std::min(per, T.k - f0), t.ws = f0 == 0;
+            t.lz = T.crop_z0 - (sz_ ? 1 : 0), t.lx = T.crop_x0 - (sx_ ? 1 : 0), t.nxe = T.nxe;
+            for (int f = 0; f < t.nf; f++) {
+                const double* p = T.fields[f0 + f];
+                const bool lg = !(T.scheme[f0 + f] & PLB_AVG_ARITHMETIC);
+                int c = -1;
+                for (int q = 0; q < a.ncol; q++)
+                    if (a.col[q] == p) c = q;
+                if (c < 0) {
+                    if (a.ncol >= TF_MAXC) return 3;
+                    c = a.ncol++;
+                    a.col[c] = p;
+                    if (lg) a.logmask |= 1u << c;
+                    aligned = aligned && ((uintptr_t)p & 15) == 0;
+                } else if (lg != (((a.logmask >> c) & 1u) != 0)) {
+                    return 3;                                    // one column, two different transforms
+                }
+                t.col[f] = c;
+            }
+        }
+    }
+    if (plb_ws_reserve(ctx, ndbl * sizeof(double))) return 2;
+    double* w = (double*)ctx->ws;
+    // planes, tables
+    PLB_CUDA(ctx, cudaMemsetAsync(w, 0, nplane_dbl * sizeof(double), ctx->stream));
+    int ti = 0;
+    for (int i = 0; i < ntargets; i++) {
+        const plb_t2g_target& T = tg[i];
+        double2* tab = (double2*)(w + tab_off[i]);
+        double* recip = w + recip_off;
+        k_axis_recip<<<plb_blocks(T.nze, 256), 256, 0, ctx->stream>>>(T.nze, T.axis_z, recip, tab);
+        PLB_LAUNCHED(ctx);
+        k_axis_recip<<<plb_blocks(T.nxe, 256), 256, 0, ctx->stream>>>(T.nxe, T.axis_x, recip + T.nze, tab + T.nze);
+        PLB_LAUNCHED(ctx);
+        const size_t plane = (size_t)T.nze * T.nxe;
+        const int per = T.kind == 0 ? 3 : 1;
+        for (int f0 = 0; f0 < T.k; f0 += per, ti++) {
+            TFTask& t = a.t[ti];
+            t.tz = tab, t.tx = tab + T.nze;
+            t.wsum = w + plane_off[i];
+            for (int f = 0; f < t.nf; f++) t.acc[f] = w + plane_off[i] + (size_t)(1 + f0 + f) * plane;
+        }
+    }
+    a.z0 = z0, a.x0 = x0, a.ncz = nz - 1, a.ncx = nxx - 1;
+    a.sz = (double)(nz - 1) / zlen, a.sx = (double)(nxx - 1) / xlen;
+    if (M > 0) {
+        const size_t smem = (size_t)TF_NM * 16 + (size_t)a.ncol * TF_NM * 8 + (TF_NM + 2) * sizeof(unsigned short);
+        static bool attr_set = false;
+        if (!attr_set) {
+            PLB_CUDA(ctx, cudaFuncSetAttribute(k_t2g_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            PLB_CUDA(ctx, cudaFuncSetAttribute(k_t2g_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            PLB_CUDA(ctx, cudaFuncSetAttribute(k_t2g_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set = true;
+        }
+        plb_prof_scope prof_(ctx, PLB_K_T2G, (16.0 + 8.0 * a.ncol) * (double)M);
+        const long long nchunk = (M + TF_NM - 1) / TF_NM;
+        if (nchunk > 0x7fffffffLL) PLB_FAIL(ctx, "plb_trac2grid_fused: too many markers");
+        // lanes per run: a sorted chunk holds ~TF_NM/16 runs; few tasks -> more lanes per run fill the CTA
+        int parts = ctx->t2g_parts > 0 ? ctx->t2g_parts : (a.nt >= 4 ? 2 : 4);
+        const double2* xx = (const double2*)d_tr_x;
+        const unsigned g = (unsigned)nchunk;
+        if (parts >= 4) k_t2g_fused<4><<<g, TF_THREADS, smem, ctx->stream>>>(M, xx, a, aligned ? 1 : 0);
+        else if (parts == 2) k_t2g_fused<2><<<g, TF_THREADS, smem, ctx->stream>>>(M, xx, a, aligned ? 1 : 0);
+        else k_t2g_fused<1><<<g, TF_THREADS, smem, ctx->stream>>>(M, xx, a, aligned ? 1 : 0);
+        PLB_LAUNCHED(ctx);
+    }
+    // marker-parallel ranks with replicated grids: sum the raw node sums over the ranks before dividing
+    if (plb_comm_size(ctx) > 1 && plb_comm_allreduce(ctx, w, nplane_dbl, PLB_OP_SUM)) return 2;
+    for (int i = 0; i < ntargets; i++) {
+        const plb_t2g_target& T = tg[i];
+        T2GArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        const size_t plane = (size_t)T.nze * T.nxe;
+        fa.wsum = w + plane_off[i];
+        for (int f = 0; f < T.k; f++) {
+            fa.acc[f] = w + plane_off[i] + (size_t)(1 + f) * plane;
+            fa.out[f] = T.out[f];
+            fa.scheme[f] = T.scheme[f];
+        }
+        fa.nze = T.nze, fa.nxe = T.nxe, fa.k = T.k;
+        k_t2g_finalise<<<plb_grid_for(ctx, (long long)nz * nxx, 256, 8), 256, 0, ctx->stream>>>(fa, T.crop_z0, T.crop_x0,
+                                                                                            nz, nxx, ld);
+        PLB_LAUNCHED(ctx);
+    }
     return 0;
 }
 

@@ -57,7 +57,8 @@ class Options:
         self.stokes_params = {"warm_start": 1}     # start each solve from the previous step's iterate
         self.heat_rtol = 1e-13
         self.heat_extrapolate = True  # heat solve starts from T + the previous step's increment
-        self.resort_every = 0         # > 0: re-order the markers by cell every n-th step
+        self.resort_every = 0         # > 0: re-order the markers by cell every n-th step (device counting sort)
+        self.fused_t2g = True         # the step's marker->grid targets in one pass (plb_trac2grid_fused)
         self.tracdens, self.tracdens_min = 45, 0   # marker injection (pylamp2.py:594-633); 0 = off
         # several ranks: "index" = every rank keeps the markers it started with (any marker may be
         # processed by any rank); "slab" = rank r owns the markers in its cell rows, markers that
@@ -149,7 +150,7 @@ def timestep(s, o, want_kelem=True, phases=False):
     ph.mark("start")
     s.it += 1
     if o.resort_every and s.it > 1 and (s.it - 1) % o.resort_every == 0:
-        s.tr_x, s.cols, _ = markers.sort_by_cell(s.tr_x, s.cols, s.nx, s.L)
+        s.tr_x, s.cols, _ = markers.sort_by_cell(s.tr_x, s.cols, s.nx, s.L, consume=True)
     nx, grid, gridmp = s.nx, s.grid, s.gridmp
     cols, tr_x = s.cols, s.tr_x
     # marker property update, pylamp2.py:291-303
@@ -165,13 +166,19 @@ def timestep(s, o, want_kelem=True, phases=False):
 
         def t2g(ctx_, x_, cols_, schemes_, grid_, out_, mm_):
             return pylamp_trac.trac2grid_slab(ctx_, x_, cols_, schemes_, grid_, out_, mm_, slab_bounds)
+    fused = o.fused_t2g and t2g is pylamp_trac.trac2grid_device
     if o.do_advect and o.do_heatdiff:
-        t2g(ctx, tr_x, [cols[k] for k in (TR_RHO, TR_ETA, TR_HCP, TR_TMP, TR_IHT, TR_MAT)],
-            [INTERP_AVG_ARITHW, INTERP_AVG_GEOMW] + [INTERP_AVG_ARITHW] * 4, grid,
-            [s.f_rho, s.f_etas, s.f_Cp, s.f_T, s.f_H, s.f_mat], mm)
-        t2g(ctx, tr_x, [cols[TR_ETA]], [INTERP_AVG_GEOMW], gridmp, [s.f_etan], mm)
-        t2g(ctx, tr_x, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [gridmp[IZ], grid[IX]], [s.f_k[IZ]], mm)
-        t2g(ctx, tr_x, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [grid[IZ], gridmp[IX]], [s.f_k[IX]], mm)
+        node_cols = [cols[k] for k in (TR_RHO, TR_ETA, TR_HCP, TR_TMP, TR_IHT, TR_MAT)]
+        node_sch = [INTERP_AVG_ARITHW, INTERP_AVG_GEOMW] + [INTERP_AVG_ARITHW] * 4
+        node_out = [s.f_rho, s.f_etas, s.f_Cp, s.f_T, s.f_H, s.f_mat]
+        if not (fused and pylamp_trac.trac2grid_fused_device(
+                ctx, tr_x, [(0, node_cols, node_sch, node_out), (1, [cols[TR_ETA]], [INTERP_AVG_GEOMW], [s.f_etan]),
+                            (2, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [s.f_k[IZ]]),
+                            (3, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [s.f_k[IX]])], grid, gridmp, mm)):
+            t2g(ctx, tr_x, node_cols, node_sch, grid, node_out, mm)
+            t2g(ctx, tr_x, [cols[TR_ETA]], [INTERP_AVG_GEOMW], gridmp, [s.f_etan], mm)
+            t2g(ctx, tr_x, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [gridmp[IZ], grid[IX]], [s.f_k[IZ]], mm)
+            t2g(ctx, tr_x, [cols[TR_HCD]], [INTERP_AVG_ARITHW], [grid[IZ], gridmp[IX]], [s.f_k[IX]], mm)
     elif o.do_advect:
         t2g(ctx, tr_x, [cols[TR_RHO], cols[TR_ETA]], [INTERP_AVG_ARITHW, INTERP_AVG_GEOMW], grid,
             [s.f_rho, s.f_etas], mm)
@@ -198,8 +205,10 @@ def timestep(s, o, want_kelem=True, phases=False):
     if o.surface_stabilization and o.surfstab_tstep >= 0:                           # :354-355
         s.stokes_op.set_surfstab(o.surfstab_tstep, o.surfstab_theta)
     x = s.stokes_op.solve(None, rtol=o.stokes_rtol, maxit=o.stokes_maxit)
+    st = s.stokes_op.stats
     s.stats["stokes_iters"] = s.stokes_op.iterations
     s.stats["stokes_relres"] = s.stokes_op.relres
+    s.stats["stokes_status"], s.stats["stokes_rtol_eff"], s.stats["stokes_floor"] = st["status"], st["rtol_eff"], st["floor"]
     ph.mark("stokes_solve")
     s.newvel, s.newpres = pylamp_stokes.x2vp(x, nx)
     vmax = max(markers.field_max(s.newvel[IZ]), markers.field_max(s.newvel[IX]))   # :364 (signed)
@@ -258,7 +267,9 @@ def timestep(s, o, want_kelem=True, phases=False):
                 # T = Tsg - interp(f_sgc) (:479-480)
                 Tsg, dT = markers.subgrid_fused(1, tr_x, grid, dT_grid, T, tstep, s.dx[IZ], s.dx[IX],
                                                 cols[TR_HCP], cols[TR_RHO], cols[TR_HCD])
-                t2g(ctx, tr_x, [dT], [INTERP_AVG_ARITHW], grid, [s.f_sgc], mm)
+                if not (fused and pylamp_trac.trac2grid_fused_device(
+                        ctx, tr_x, [(0, [dT], [INTERP_AVG_ARITHW], [s.f_sgc])], grid, gridmp, mm)):
+                    t2g(ctx, tr_x, [dT], [INTERP_AVG_ARITHW], grid, [s.f_sgc], mm)
                 markers.subgrid_fused(2, tr_x, grid, s.f_sgc, T, Tsg=Tsg)
             else:
                 nbad = g2t(ctx, tr_x, grid, [dT_grid], nx, INTERP_METHOD_LINEAR, float("nan"), [interp])

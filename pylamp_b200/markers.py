@@ -129,23 +129,45 @@ def subgrid_stage2(Tsg, back, T_out):
     _ctx(Tsg).call("plb_subgrid_stage2", Tsg.shape[0], Tsg.data_ptr(), back.data_ptr(), T_out.data_ptr())
 
 
-def sort_by_cell(tr_x, cols, nx, L, extra=()):
+def sort_by_cell(tr_x, cols, nx, L, extra=(), want_cell_start=False, consume=False):
     """Physically re-order the marker arrays by cell index (cell-major, like the setups generate
-    them).  The results of every kernel are order-independent (up to fp64 summation order in
-    trac2grid); a cell-ordered cloud keeps trac2grid's run aggregation effective -- one atomic per
+    them) with the device counting sort of csrc/sort.cu (plb_sort_plan + one plb_permute per distinct
+    array).  The results of every kernel are order-independent (up to fp64 summation order in
+    trac2grid); a cell-ordered cloud keeps trac2grid's run aggregation effective -- one reduction per
     cell run instead of one per marker -- and the grid gathers of grid2trac/RK4 cache-local.
-    Returns (tr_x, cols, extra) as new tensors.  Device-side (torch) sort: plumbing, not a kernel."""
-    kelem, _ = cell_index_count(tr_x, nx, L, want_kelem=True)
-    order = torch.argsort(kelem)
-    del kelem
-    tr_x = tr_x.index_select(0, order)
+    Returns (tr_x, cols, extra) as new tensors (+ the (ncell+1,) int32 first-slot table if asked).
+    `extra`: further (M,) or (M,2) float64 tensors to carry along (e.g. marker velocities).
+    `consume=True`: the input tensors may be overwritten (each permuted array's old storage becomes the
+    next array's destination: one spare array instead of a second copy of the whole cloud)."""
+    ctx = _ctx(tr_x)
+    M = tr_x.shape[0]
+    nz, nxx = int(nx[IZ]), int(nx[IX])
+    dest = torch.empty(M, dtype=torch.int32, device=tr_x.device)
+    start = torch.empty((nz - 1) * (nxx - 1) + 1, dtype=torch.int32, device=tr_x.device) if want_cell_start else None
+    ctx.call("plb_sort_plan", M, tr_x.data_ptr(), nz, nxx, float(L[IZ]), float(L[IX]), dest.data_ptr(),
+             start.data_ptr() if want_cell_start else None)
+    spare = {}          # the array permuted last becomes the next one's destination (one spare per shape)
+
+    def perm(t):
+        width = 1 if t.dim() == 1 else int(t.shape[1])
+        out = spare.pop(width, None) if consume else None
+        if out is None or out.shape[0] != M or out.data_ptr() == t.data_ptr():
+            out = torch.empty_like(t)
+        ctx.call("plb_permute", M, dest.data_ptr(), t.data_ptr(), out.data_ptr(), width)
+        if consume:
+            spare[width] = t
+        return out
+
+    tr_x = perm(tr_x.contiguous())
     seen, out = {}, []
     for c in cols:                      # columns may alias each other (shared zero column)
         key = c.data_ptr()
         if key not in seen:
-            seen[key] = c.index_select(0, order)
+            seen[key] = perm(c)
         out.append(seen[key])
-    extra = [e.index_select(0, order) for e in extra]
+    extra = [perm(e.contiguous()) for e in extra]
+    if want_cell_start:
+        return tr_x, out, extra, start
     return tr_x, out, extra
 
 

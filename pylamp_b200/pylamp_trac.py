@@ -51,12 +51,13 @@ def _axis_np(a):
     return np.asarray(a, dtype=np.float64)
 
 
-def _extended_axis(coords, lo, hi):
+def _extended_axis(coords, lo, hi, min_left=0):
     """Ghost-node extension of one axis (pylamp_trac.py:207-217): while markers lie outside the
-    grid, prepend/append one node at the edge spacing."""
+    grid, prepend/append one node at the edge spacing.  `min_left`: prepend at least that many (an
+    unused ghost node changes nothing: the result is cropped to the real nodes, :313-316)."""
     ax = np.array(coords, dtype=np.float64, copy=True)
     nleft = nright = 0
-    while lo < ax[0]:
+    while lo < ax[0] or nleft < min_left:
         ax = np.concatenate([[ax[0] - (ax[1] - ax[0])], ax])
         nleft += 1
     while hi > ax[-1]:
@@ -90,6 +91,47 @@ def trac2grid_device(ctx, tr_x_d, cols_d, schemes, grid, out_d, minmax=None):
              axx.shape[0], float(axz[0]), float(axz[-1] - axz[0]), float(axx[0]),
              float(axx[-1] - axx[0]), lz, lx, nz, nxx, nxx, _lib.ptr_array(out_d))
     return minmax
+
+
+def trac2grid_fused_device(ctx, tr_x_d, targets, grid, gridmp, minmax):
+    """All marker->grid targets of a time step in one pass over the markers (plb_trac2grid_fused:
+    coordinates and every distinct column read once).  `targets`: list of (kind, cols_d, schemes, outs_d)
+    with kind 0 = nodes (grid, grid), 1 = centres (gridmp, gridmp), 2 = (gridmp_z, grid_x),
+    3 = (grid_z, gridmp_x) -- the four targets of pylamp2.py:309-313.  Returns False (nothing written)
+    when the request does not fit the fused kernel (unweighted scheme, markers outside the node grid,
+    more than 8 distinct columns): the caller then falls back to `trac2grid_device` per target."""
+    gz, gx = _axis_np(grid[IZ]), _axis_np(grid[IX])
+    if minmax[0] < gz[0] or minmax[1] > gz[-1] or minmax[2] < gx[0] or minmax[3] > gx[-1]:
+        return False
+    gmz, gmx = _axis_np(gridmp[IZ]), _axis_np(gridmp[IX])
+    nz, nxx = gz.shape[0], gx.shape[0]
+    keep, arr = [], (_lib.T2GTarget * len(targets))()
+    ext = {}
+
+    def axis(stag, d):
+        if (stag, d) not in ext:
+            ax, nl, _ = _extended_axis((gmz, gmx)[d] if stag else (gz, gx)[d], minmax[2 * d], minmax[2 * d + 1],
+                                       min_left=1 if stag else 0)
+            ext[(stag, d)] = (_to_dev(ax, ctx), ax.shape[0], nl)
+        return ext[(stag, d)]
+
+    for t, (kind, cols_d, schemes, outs_d) in zip(arr, targets):
+        if any((int(s) & INTERP_AVG_WEIGHTED) == 0 for s in schemes) or len(cols_d) > 8:
+            return False
+        az, ax = axis(kind in (1, 2), IZ), axis(kind in (1, 3), IX)
+        t.kind, t.k = int(kind), len(cols_d)
+        for f, (c, s, o) in enumerate(zip(cols_d, schemes, outs_d)):
+            assert tuple(o.shape) == (nz, nxx) and o.is_contiguous() and c.is_contiguous()
+            t.fields[f], t.scheme[f], t.out[f] = c.data_ptr(), int(s), o.data_ptr()
+        t.axis_z, t.nze, t.crop_z0 = az[0].data_ptr(), az[1], az[2]
+        t.axis_x, t.nxe, t.crop_x0 = ax[0].data_ptr(), ax[1], ax[2]
+        keep.append((cols_d, outs_d))
+    rc = ctx.lib.plb_trac2grid_fused(ctx.h, tr_x_d.shape[0], tr_x_d.data_ptr(), nz, nxx, nxx, float(gz[0]),
+                                     float(gz[-1] - gz[0]), float(gx[0]), float(gx[-1] - gx[0]), len(targets), arr)
+    if rc == 3:
+        return False
+    ctx.check(rc)
+    return True
 
 
 def trac2grid_slab(ctx, tr_x_d, cols_d, schemes, grid, out_d, minmax, bounds, group=None, check=False):

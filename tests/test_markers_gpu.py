@@ -191,6 +191,38 @@ def test_sort_by_cell_keeps_results(T):
     assert np.allclose(out_a[0], ref[0], rtol=1e-12) and np.allclose(out_b[0], ref[0], rtol=1e-12)
 
 
+def test_device_sort_is_a_cell_major_permutation(T):
+    """csrc/sort.cu: the slot table is a permutation, the result is cell-major (keys as pylamp2.py:588-589,
+    markers outside the box clamped into the nearest cell), the first-slot table equals the exclusive scan of
+    np.bincount, every carried array (incl. (M,2) extras and aliased columns) moves with its marker."""
+    from pylamp_b200 import markers
+    rng = np.random.default_rng(10)
+    for nx, L, M in (([65, 49], [1.0, 0.75], 300001), ([9, 1030], [0.3, 2.0], 70000), ([6, 6], [1.0, 1.0], 37)):
+        x = rng.random((M, 2)) * L
+        x[:7] = [-0.01, 0.5 * L[1]]              # outside (fence disabled / FLOWTHRU): clamped keys
+        x[7:11] = [0.5 * L[0], 1.2 * L[1]]
+        ident = np.arange(M, dtype=np.float64)
+        vel = rng.normal(size=(M, 2))
+        xd, idd, vd = torch.as_tensor(x).cuda(), torch.as_tensor(ident).cuda(), torch.as_tensor(vel).cuda()
+        for consume in (False, True):
+            xin, idin, vin = (xd.clone(), idd.clone(), vd.clone()) if consume else (xd, idd, vd)
+            xs, cols, (vs,), start = markers.sort_by_cell(xin, [idin, idin], nx, L, extra=[vin], want_cell_start=True,
+                                                          consume=consume)
+            assert cols[0].data_ptr() == cols[1].data_ptr()          # aliased columns stay aliased
+            order = cols[0].cpu().numpy().astype(np.int64)
+            assert np.array_equal(np.sort(order), np.arange(M))       # a permutation
+            assert np.array_equal(xs.cpu().numpy(), x[order]) and np.array_equal(vs.cpu().numpy(), vel[order])
+            ie = np.clip(np.floor((nx[0] - 1) * x[:, 0] / L[0]).astype(np.int64), 0, nx[0] - 2)
+            je = np.clip(np.floor((nx[1] - 1) * x[:, 1] / L[1]).astype(np.int64), 0, nx[1] - 2)
+            key = ie * (nx[1] - 1) + je
+            assert bool(np.all(np.diff(key[order]) >= 0))             # cell-major
+            ncell = (nx[0] - 1) * (nx[1] - 1)
+            want = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=ncell))])
+            assert np.array_equal(start.cpu().numpy().astype(np.int64), want)
+        if not consume:
+            assert np.array_equal(xd.cpu().numpy(), x)                # inputs untouched without `consume`
+
+
 def _t2g_dev(T, x, cols, schemes, grid, nx, variant, view_offset=0):
     """trac2grid_device on CUDA tensors with the given scatter-kernel variant; `view_offset` > 0
     passes views that start `view_offset` markers into larger allocations (not 32-byte aligned)."""
@@ -245,6 +277,101 @@ def test_trac2grid_chunk_kernel_matches_generic_and_oracle(T, cloud, ragged):
                 assert np.array_equal(np.isnan(a), np.isnan(r)), variant
                 # the arithmetic mean of values in (-1,1) can cancel: absolute floor of a few ulps of 1
                 assert np.allclose(a, r, rtol=1e-12, atol=1e-14, equal_nan=True), variant
+
+
+def _fused_case(T, x, nx, L, node_k, centre_k, view_offset=0, poison=False, seed=13):
+    """plb_trac2grid_fused (all targets of a step in one pass) against the oracle's trac2grid per target."""
+    from pylamp_b200 import _lib
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(seed)
+    grid, mesh, gridmp, meshmp = O.make_grids(nx, L)
+    M = x.shape[0]
+    ncols = node_k + 2
+    cols = [rng.uniform(-1, 1, M) if c % 3 == 2 else 10 ** rng.uniform(18, 24, M) if c % 3 == 1 else rng.uniform(1, 2, M)
+            for c in range(ncols)]
+    if poison:
+        cols[1][[3, M // 2, M - 1]] = 0.0            # log -> -inf: nodes zeroed before exp (pylamp_trac.py:301)
+        cols[0][[7, M // 3]] = np.nan                 # NaN property (marker injected into an empty cell)
+    sch = lambda c: 6 if c % 3 == 1 else 5
+    pad = lambda a: torch.as_tensor(np.concatenate([np.ones((view_offset,) + a.shape[1:]), a])).cuda()[view_offset:]
+    xd, cd = pad(x), [pad(c) for c in cols]
+    new = lambda: torch.full(tuple(nx), -7.0, dtype=torch.float64, device="cuda")
+    node_ids = list(range(node_k))
+    centre_ids = [1, 0][:centre_k]                     # the geometric column first (shared with the node target)
+    targets = [(0, node_ids), (1, centre_ids), (2, [ncols - 1]), (3, [ncols - 1])]
+    grids = {0: [grid[0], grid[1]], 1: [gridmp[0], gridmp[1]], 2: [gridmp[0], grid[1]], 3: [grid[0], gridmp[1]]}
+    outs = {kind: [new() for _ in ids] for kind, ids in targets}
+    mm = T.marker_minmax(xd, ctx)
+    ok = T.trac2grid_fused_device(ctx, xd, [(kind, [cd[c] for c in ids], [sch(c) for c in ids], outs[kind])
+                                            for kind, ids in targets], grid, gridmp, mm)
+    inside = x[:, 0].min() >= 0 and x[:, 0].max() <= L[0] and x[:, 1].min() >= 0 and x[:, 1].max() <= L[1]
+    assert ok == bool(inside)
+    if not ok:
+        assert all(bool((o == -7.0).all()) for os_ in outs.values() for o in os_)      # nothing written
+        return
+    for kind, ids in targets:
+        ref = [np.zeros(nx) for _ in ids]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            O.trac2grid(x, np.stack([cols[c] for c in ids], axis=1), None, grids[kind], ref, nx,
+                        avgscheme=[sch(c) for c in ids])
+        for o, r in zip(outs[kind], ref):
+            a = o.cpu().numpy()
+            assert np.array_equal(np.isnan(a), np.isnan(r)), (kind, int(np.isnan(a).sum()), int(np.isnan(r).sum()))
+            assert np.allclose(a, r, rtol=1e-12, atol=1e-14, equal_nan=True), kind
+
+
+@pytest.mark.parametrize("cloud", ["random", "sorted", "drifted", "outside", "on_nodes"])
+@pytest.mark.parametrize("ragged", [0, 3])
+def test_trac2grid_fused_matches_oracle(T, cloud, ragged):
+    """The fused step kernel on clouds that exercise every path: unordered (runs of one marker), cell-ordered
+    (one run per cell), cell-ordered then displaced, markers exactly on nodes / cell faces / midpoints (weights
+    0 and 1, half-cell ties), markers beyond the grid (request refused -> caller falls back), chunks that are
+    not full (plain loads instead of bulk copies)."""
+    from pylamp_b200 import setups
+    rng = np.random.default_rng(11)
+    ncz, ncx, L = 48, 40, [1.0, 0.75]
+    nx = [ncz + 1, ncx + 1]
+    if cloud == "random":
+        x = rng.random((60000, 2)) * L
+    elif cloud == "on_nodes":
+        g = O.make_grids(nx, L)
+        # (not the last node: floor((n-1)(x-Lmin)/L) = n-1 there, which the reference itself cannot index)
+        zz, xx = np.meshgrid(np.concatenate([g[0][0][:-1], g[2][0][:-1]]), np.concatenate([g[0][1][:-1], g[2][1][:-1]]), indexing="ij")
+        x = np.stack([zz.ravel(), xx.ravel()], axis=1)
+        x = np.concatenate([x, rng.random((5000, 2)) * L])
+    else:
+        x = setups.lattice_markers(ncz, ncx, L, 4, seed=3)[0]
+        if cloud == "drifted":
+            x = x + np.array([0.37 * L[0] / ncz, 0.61 * L[1] / ncx])
+            x = np.minimum(np.maximum(x, 1e-9), np.array(L) - 1e-9)
+        if cloud == "outside":
+            x = x + np.array([-0.4 * L[0] / ncz, 0.3 * L[1] / ncx])      # beyond z=0 and x=L
+    if ragged:
+        x = x[:x.shape[0] - 4 + ragged]
+    _fused_case(T, x, nx, L, node_k=6, centre_k=1)
+
+
+def test_trac2grid_fused_shapes_alignment_and_nonfinite_values(T):
+    from pylamp_b200 import setups
+    ncz, ncx, L = 24, 36, [0.5, 1.0]
+    nx = [ncz + 1, ncx + 1]
+    x = setups.lattice_markers(ncz, ncx, L, 4, seed=4)[0]
+    for node_k, centre_k in ((1, 1), (2, 2), (4, 1), (6, 2)):             # 1..2 node tasks, 1..2 centre tasks
+        _fused_case(T, x, nx, L, node_k, centre_k)
+    from pylamp_b200 import _lib
+    for parts in (1, 2, 4):                                                # lanes per run (default: automatic)
+        _lib.default_context().set_param("t2g_parts", parts)
+        try:
+            _fused_case(T, x, nx, L, 6, 1)
+            _fused_case(T, x[5:3000], nx, L, 1, 1, poison=True)
+        finally:
+            _lib.default_context().set_param("t2g_parts", 0)
+    _fused_case(T, x, nx, L, 6, 1, view_offset=1)                          # 8-byte aligned views: no bulk copies
+    _fused_case(T, x[:1], nx, L, 3, 1)                                     # a single marker
+    _fused_case(T, x[:1024 * 3], nx, L, 6, 1)                              # whole chunks only
+    _fused_case(T, x, nx, L, 6, 1, poison=True)                            # log(0) = -inf and NaN properties
+    rng = np.random.default_rng(5)
+    _fused_case(T, rng.random((20000, 2)) * L, nx, L, 6, 1, poison=True)   # the same, unordered
 
 
 def test_trac2grid_chunk_kernel_falls_back_on_unaligned_views_and_counts(T):
