@@ -30,7 +30,10 @@ struct plb_ctx {
     double* prof_bytes;    // algorithmic bytes per recorded pair
     // tuning knobs (plb_ctx_set_param)
     int t2g_variant;       // 1: wide-load chunk kernel for weighted schemes (default), 0: generic kernel only
-    int t2g_parts;         // fused step kernel: lanes per run (0: automatic; 1, 2, 4)
+    int t2g_parts;         // fused step kernel: lanes per run (0 = 1; 1, 2, 4)
+    int t2g_nm;            // fused step kernel: markers per CTA (960 default, 1024)
+    int t2g_nfmax;         // fused step kernel: fields per node-target work item (default 6)
+    int t2g_minb;          // fused step kernel: 2 = at most two resident CTAs per SM (default: three when they fit)
 };
 
 // kernel classes for plb_profile_* (bench.py's roofline block)

@@ -83,6 +83,18 @@ int plb_ctx_set_param(plb_ctx* ctx, const char* name, double value) {
         ctx->t2g_parts = (int)value;
         return 0;
     }
+    if (!strcmp(name, "t2g_nm")) {
+        ctx->t2g_nm = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "t2g_minb")) {
+        ctx->t2g_minb = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "t2g_nfmax")) {
+        ctx->t2g_nfmax = (int)value;
+        return 0;
+    }
     PLB_FAIL(ctx, "plb_ctx_set_param: unknown parameter '%s'", name);
 }
 

@@ -821,18 +821,18 @@ k_subgrid_fused2(long long M, const double2* __restrict__ trx, G2TGrid g, const 
 // Correct for any marker order (an unsorted cloud just has runs of length one).  Same weights as the
 // reference: (1-a), 1-(1-a) per axis, multiplied x then z (pylamp_trac.py:247-255).
 // ---------------------------------------------------------------------------------------------
-constexpr int TF_NM = 1024, TF_THREADS = 256, TF_MAXC = 8, TF_MAXT = 8;
+constexpr int TF_THREADS = 256, TF_MAXC = 8, TF_MAXT = 8, TF_NFMAX = 6;
 
 struct TFTask {
     int type;              // 0: 2x2 (node axes), 1: 3x3 (both axes staggered), 2: 3x2 (z staggered), 3: 2x3 (x staggered)
-    int nf, ws;            // fields of this task (type 0: <= 3, else 1); accumulate the weight sums too
-    int col[3];            // staged column of each field
+    int nf, ws;            // fields of this task (type 0: <= TF_NFMAX, else 1); accumulate the weight sums too
+    int col[TF_NFMAX];     // staged column of each field
     const double2* tz;     // {coordinate, 1/spacing} of the target's (ghost-extended) axes
     const double2* tx;
     int lz, lx;            // extended index of the first destination row / column of node-grid cell 0
     int nxe;               // row length of the target's planes
     double* wsum;
-    double* acc[3];
+    double* acc[TF_NFMAX];
 };
 
 struct TFArgs {
@@ -874,12 +874,12 @@ __device__ __forceinline__ void tf_axis_weights(double v, const double2& t0, con
     }
 }
 
-// PARTS lanes share a run: each walks 1/PARTS of its markers (shorter dependent chains, finer work items),
-// the partial sums are combined with xor-shuffles and the first lane of the group adds them to the planes.
-// Every lane of the warp calls this (lanes without a run pass len = 0): the shuffles are warp-wide.
-template <int RZ, int RX, int NF, int PARTS>
+// One (run, task) work item.  PARTS lanes may share a run: each walks 1/PARTS of its markers, the partial
+// sums are combined with xor-shuffles and the first lane of the group adds them to the planes.  Every lane
+// of the warp calls this (lanes without a run pass len = 0): the shuffles are warp-wide.
+template <int RZ, int RX, int NF, int PARTS, int NM>
 __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const double2* __restrict__ sx,
-                                       const double* __restrict__ sv, int s, int len, int run, int part) {
+                                       const double* __restrict__ sv, int s, int len, int part) {
     const double2 p0 = sx[s];                            // (lanes without a run pass s = 0, len = 0)
     const int ie = tf_cell(p0.x, a.z0, a.sz, a.ncz), je = tf_cell(p0.y, a.x0, a.sx, a.ncx);
     const int ez = ie + t.lz, ex = je + t.lx;
@@ -894,20 +894,52 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
 #pragma unroll
         for (int f = 0; f < NF; f++) A[f][c] = 0;
     }
+    const bool ws = t.ws != 0;
+    const int b0 = PARTS == 1 ? 0 : (len * part) / PARTS, sub = (PARTS == 1 ? len : (len * (part + 1)) / PARTS) - b0;
+    const double2* px = sx + s + b0;
     const double* cf[NF];
 #pragma unroll
-    for (int f = 0; f < NF; f++) cf[f] = sv + t.col[f] * TF_NM + s;
-    const bool ws = t.ws != 0;
-    // lanes of a warp walk different runs: start at different offsets (freshly sorted runs are 16 markers =
-    // one full bank cycle apart, so equal offsets would hit one bank)
-    const int b0 = (len * part) / PARTS, sub = (len * (part + 1)) / PARTS - b0;
-    int idx = run & 15;
+    for (int f = 0; f < NF; f++) cf[f] = sv + t.col[f] * NM + s + b0;
+    // The lanes of a warp walk different runs.  Each starts at the marker whose shared-memory bank matches its
+    // lane number and wraps around, so that the 16 lanes of a memory phase read 16 different banks whatever the
+    // run starts are (a linear walk of freshly sorted runs, which start 16 markers apart, would put all lanes
+    // on one bank: measured 1.6x slower).
+    int idx = ((threadIdx.x & 15) - (s + b0)) & 15;
     if (idx >= sub) idx = 0;
-    for (int it = 0; it < sub; it++) {
-        const double2 p = sx[s + b0 + idx];
+    // two markers per trip: both sets of loads are issued before the first is used
+    int it = 0;
+    for (; it + 2 <= sub; it += 2) {
+        int idx2 = idx + 1;
+        if (idx2 == sub) idx2 = 0;
+        const double2 pa = px[idx], pb = px[idx2];
+        double va[NF], vb[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++) va[f] = cf[f][idx], vb[f] = cf[f][idx2];
+        double wza[RZ], wxa[RX], wzb[RZ], wxb[RX];
+        tf_axis_weights<RZ>(pa.x, tz0, tz1, wza);
+        tf_axis_weights<RX>(pa.y, tx0, tx1, wxa);
+        tf_axis_weights<RZ>(pb.x, tz0, tz1, wzb);
+        tf_axis_weights<RX>(pb.y, tx0, tx1, wxb);
+#pragma unroll
+        for (int r = 0; r < RZ; r++)
+#pragma unroll
+            for (int c = 0; c < RX; c++) {
+                const double w1 = wxa[c] * wza[r], w2 = wxb[c] * wzb[r];       // :252-255
+                if (ws) W[r * RX + c] += w1, W[r * RX + c] += w2;
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    A[f][r * RX + c] = fma(va[f], w1, A[f][r * RX + c]);
+                    A[f][r * RX + c] = fma(vb[f], w2, A[f][r * RX + c]);
+                }
+            }
+        idx = idx2 + 1;
+        if (idx == sub) idx = 0;
+    }
+    if (it < sub) {
+        const double2 p = px[idx];
         double v[NF];
 #pragma unroll
-        for (int f = 0; f < NF; f++) v[f] = cf[f][b0 + idx];
+        for (int f = 0; f < NF; f++) v[f] = cf[f][idx];
         double wz[RZ], wx[RX];
         tf_axis_weights<RZ>(p.x, tz0, tz1, wz);
         tf_axis_weights<RX>(p.y, tx0, tx1, wx);
@@ -915,13 +947,11 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
         for (int r = 0; r < RZ; r++)
 #pragma unroll
             for (int c = 0; c < RX; c++) {
-                const double w = wx[c] * wz[r];       // :252-255
+                const double w = wx[c] * wz[r];
                 if (ws) W[r * RX + c] += w;
 #pragma unroll
                 for (int f = 0; f < NF; f++) A[f][r * RX + c] = fma(v[f], w, A[f][r * RX + c]);
             }
-        idx++;
-        if (idx == sub) idx = 0;
     }
     if (PARTS > 1) {
 #pragma unroll
@@ -933,21 +963,20 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
                 for (int f = 0; f < NF; f++) A[f][c] += __shfl_xor_sync(0xffffffffu, A[f][c], o);
             }
         }
-        if (part != 0 || len == 0) return;
-    } else if (len == 0) {
-        return;
+        if (part != 0) return;
     }
+    if (len == 0) return;
     const long long base = (long long)ez * t.nxe + ex;
     // A non-finite property value (log of 0, NaN of a marker injected into an empty cell) must reach the nodes
     // the reference adds it to and no others (pylamp_trac.py:276-298 multiplies by the four real corner weights
     // only); above it has also met the structurally zero weights of the staggered patterns.  Such a run -- it
     // shows as a non-finite sum -- is redone marker by marker with the four real corners.
-    bool finite = true;
+    double chk = 0;
 #pragma unroll
     for (int c = 0; c < RZ * RX; c++)
 #pragma unroll
-        for (int f = 0; f < NF; f++) finite = finite && (fabs(A[f][c]) <= 1.79769313486231570e308);
-    if (!finite) {
+        for (int f = 0; f < NF; f++) chk += A[f][c] * 0.0;          // 0 for finite sums, NaN otherwise
+    if (chk != 0.0) {
         for (int it = 0; it < len; it++) {
             const double2 p = sx[s + it];
             const bool lowz = RZ == 2 || p.x < tz1.x, lowx = RX == 2 || p.y < tx1.x;
@@ -960,7 +989,7 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
             for (int c = 0; c < 4; c++) {
                 if (ws) atomicAdd(t.wsum + o4[c], w4[c]);
 #pragma unroll
-                for (int f = 0; f < NF; f++) atomicAdd(t.acc[f] + o4[c], cf[f][it] * w4[c]);
+                for (int f = 0; f < NF; f++) atomicAdd(t.acc[f] + o4[c], sv[t.col[f] * NM + s + it] * w4[c]);
             }
         }
         return;
@@ -970,40 +999,42 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
 #pragma unroll
         for (int c = 0; c < RX; c++) {
             const long long o = base + (long long)r * t.nxe + c;
-            // (a destination none of the run's markers reaches keeps exact zeros: nothing to add)
-            if (ws && W[r * RX + c] != 0.0) atomicAdd(t.wsum + o, W[r * RX + c]);
+            // (3-wide patterns: a destination none of the run's markers reaches keeps exact zeros -- nothing to add)
+            const bool any = (RZ == 2 && RX == 2) || W[r * RX + c] != 0.0 || !ws;
+            if (ws && any) atomicAdd(t.wsum + o, W[r * RX + c]);
 #pragma unroll
             for (int f = 0; f < NF; f++)
-                if (A[f][r * RX + c] != 0.0) atomicAdd(t.acc[f] + o, A[f][r * RX + c]);
+                if (any) atomicAdd(t.acc[f] + o, A[f][r * RX + c]);
         }
 }
 
-template <int PARTS>
-__global__ void __launch_bounds__(TF_THREADS, 2)
+template <int PARTS, int NM, int MINB>
+__global__ void __launch_bounds__(TF_THREADS, MINB)
 k_t2g_fused(long long M, const double2* __restrict__ trx, const TFArgs a, int use_tma) {
+    constexpr int ROUNDS = (NM + TF_THREADS - 1) / TF_THREADS;
     extern __shared__ __align__(128) unsigned char tf_smem[];
-    double2* sx = (double2*)tf_smem;                                     // [TF_NM]
-    double* sv = (double*)(tf_smem + (size_t)TF_NM * 16);                // [ncol][TF_NM]
-    unsigned short* rstart = (unsigned short*)(sv + (size_t)a.ncol * TF_NM);   // [TF_NM + 1]
+    double2* sx = (double2*)tf_smem;                                     // [NM]
+    double* sv = (double*)(tf_smem + (size_t)NM * 16);                   // [ncol][NM]
+    unsigned short* rstart = (unsigned short*)(sv + (size_t)a.ncol * NM);   // [NM + 1]
     __shared__ __align__(8) unsigned long long mbar;
-    __shared__ int cnt[32];
+    __shared__ int cnt[ROUNDS * (TF_THREADS / 32)];
     __shared__ int nrun_s;
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long m0 = (long long)blockIdx.x * TF_NM;
-    const int n = (int)((M - m0) < (long long)TF_NM ? (M - m0) : (long long)TF_NM);
+    const long long m0 = (long long)blockIdx.x * NM;
+    const int n = (int)((M - m0) < (long long)NM ? (M - m0) : (long long)NM);
     // ---- stage the chunk
-    if (use_tma && n == TF_NM) {
+    if (use_tma && n == NM) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         if (tid == 0) {
-            const unsigned bytes = (unsigned)TF_NM * 16u + (unsigned)a.ncol * TF_NM * 8u;
+            const unsigned bytes = (unsigned)NM * 16u + (unsigned)a.ncol * NM * 8u;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(bytes) : "memory");
-            tf_bulk_load(sx, trx + m0, TF_NM * 16u, &mbar);
-            for (int c = 0; c < a.ncol; c++) tf_bulk_load(sv + (size_t)c * TF_NM, a.col[c] + m0, TF_NM * 8u, &mbar);
+            tf_bulk_load(sx, trx + m0, NM * 16u, &mbar);
+            for (int c = 0; c < a.ncol; c++) tf_bulk_load(sv + (size_t)c * NM, a.col[c] + m0, NM * 8u, &mbar);
         }
         unsigned done = 0;
         while (!done) {
@@ -1013,17 +1044,17 @@ k_t2g_fused(long long M, const double2* __restrict__ trx, const TFArgs a, int us
     } else {
         for (int m = tid; m < n; m += TF_THREADS) sx[m] = trx[m0 + m];
         for (int c = 0; c < a.ncol; c++)
-            for (int m = tid; m < n; m += TF_THREADS) sv[(size_t)c * TF_NM + m] = a.col[c][m0 + m];
+            for (int m = tid; m < n; m += TF_THREADS) sv[(size_t)c * NM + m] = a.col[c][m0 + m];
         __syncthreads();
     }
     // ---- logarithm of the geometrically averaged columns, in place (once per marker and step)
     for (int c = 0; c < a.ncol; c++)
         if ((a.logmask >> c) & 1u)
-            for (int m = tid; m < n; m += TF_THREADS) sv[(size_t)c * TF_NM + m] = log(sv[(size_t)c * TF_NM + m]);
+            for (int m = tid; m < n; m += TF_THREADS) sv[(size_t)c * NM + m] = log(sv[(size_t)c * NM + m]);
     // ---- runs of equal node-grid cells: heads -> ordered list of run starts
-    unsigned hb[TF_NM / TF_THREADS];
+    unsigned hb[ROUNDS];
 #pragma unroll
-    for (int r = 0; r < TF_NM / TF_THREADS; r++) {
+    for (int r = 0; r < ROUNDS; r++) {
         const int m = r * TF_THREADS + tid;
         const bool valid = m < n;
         int key = -2;
@@ -1044,19 +1075,19 @@ k_t2g_fused(long long M, const double2* __restrict__ trx, const TFArgs a, int us
     }
     __syncthreads();
     if (warp == 0) {
-        const int v = cnt[lane];
+        const int v = lane < ROUNDS * (TF_THREADS / 32) ? cnt[lane] : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(full, inc, o);
             if (lane >= o) inc += t;
         }
-        cnt[lane] = inc - v;
+        if (lane < ROUNDS * (TF_THREADS / 32)) cnt[lane] = inc - v;
         if (lane == 31) nrun_s = inc;
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < TF_NM / TF_THREADS; r++)
+    for (int r = 0; r < ROUNDS; r++)
         if ((hb[r] >> lane) & 1u)
             rstart[cnt[r * (TF_THREADS / 32) + warp] + __popc(hb[r] & ((1u << lane) - 1u))] = (unsigned short)(r * TF_THREADS + tid);
     if (tid == 0) rstart[nrun_s] = (unsigned short)n;
@@ -1072,13 +1103,18 @@ k_t2g_fused(long long M, const double2* __restrict__ trx, const TFArgs a, int us
         const TFTask& t = a.t[ty];
         switch (t.type) {
             case 0:
-                if (t.nf == 1) tf_run<2, 2, 1, PARTS>(a, t, sx, sv, s, len, run, part);
-                else if (t.nf == 2) tf_run<2, 2, 2, PARTS>(a, t, sx, sv, s, len, run, part);
-                else tf_run<2, 2, 3, PARTS>(a, t, sx, sv, s, len, run, part);
+                switch (t.nf) {
+                    case 1: tf_run<2, 2, 1, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+                    case 2: tf_run<2, 2, 2, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+                    case 3: tf_run<2, 2, 3, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+                    case 4: tf_run<2, 2, 4, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+                    case 5: tf_run<2, 2, 5, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+                    default: tf_run<2, 2, 6, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+                }
                 break;
-            case 1: tf_run<3, 3, 1, PARTS>(a, t, sx, sv, s, len, run, part); break;
-            case 2: tf_run<3, 2, 1, PARTS>(a, t, sx, sv, s, len, run, part); break;
-            default: tf_run<2, 3, 1, PARTS>(a, t, sx, sv, s, len, run, part); break;
+            case 1: tf_run<3, 3, 1, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+            case 2: tf_run<3, 2, 1, PARTS, NM>(a, t, sx, sv, s, len, part); break;
+            default: tf_run<2, 3, 1, PARTS, NM>(a, t, sx, sv, s, len, part); break;
         }
     }
 }
@@ -1227,6 +1263,7 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     TFArgs a;
     memset(&a, 0, sizeof(a));
+    const int nfmax = (ctx->t2g_nfmax >= 1 && ctx->t2g_nfmax <= TF_NFMAX) ? ctx->t2g_nfmax : TF_NFMAX;
     // ---- distinct columns, task list, plane layout
     size_t plane_off[8], tab_off[8], ndbl = 0;
     if (ntargets > 8) return 3;
@@ -1259,7 +1296,7 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
         const plb_t2g_target& T = tg[i];
         const bool sz_ = T.kind == 1 || T.kind == 2, sx_ = T.kind == 1 || T.kind == 3;
         const int type = T.kind == 0 ? 0 : (T.kind == 1 ? 1 : (T.kind == 2 ? 2 : 3));
-        const int per = type == 0 ? 3 : 1;                      // fields per task
+        const int per = type == 0 ? nfmax : 1;                  // fields per task
         for (int f0 = 0; f0 < T.k; f0 += per) {
             if (a.nt >= TF_MAXT) return 3;
             TFTask& t = a.t[a.nt++];
@@ -1298,7 +1335,7 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
         k_axis_recip<<<plb_blocks(T.nxe, 256), 256, 0, ctx->stream>>>(T.nxe, T.axis_x, recip + T.nze, tab + T.nze);
         PLB_LAUNCHED(ctx);
         const size_t plane = (size_t)T.nze * T.nxe;
-        const int per = T.kind == 0 ? 3 : 1;
+        const int per = T.kind == 0 ? nfmax : 1;
         for (int f0 = 0; f0 < T.k; f0 += per, ti++) {
             TFTask& t = a.t[ti];
             t.tz = tab, t.tx = tab + T.nze;
@@ -1309,24 +1346,40 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
     a.z0 = z0, a.x0 = x0, a.ncz = nz - 1, a.ncx = nxx - 1;
     a.sz = (double)(nz - 1) / zlen, a.sx = (double)(nxx - 1) / xlen;
     if (M > 0) {
-        const size_t smem = (size_t)TF_NM * 16 + (size_t)a.ncol * TF_NM * 8 + (TF_NM + 2) * sizeof(unsigned short);
-        static bool attr_set = false;
-        if (!attr_set) {
-            PLB_CUDA(ctx, cudaFuncSetAttribute(k_t2g_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            PLB_CUDA(ctx, cudaFuncSetAttribute(k_t2g_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            PLB_CUDA(ctx, cudaFuncSetAttribute(k_t2g_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = true;
-        }
+        const int nm = ctx->t2g_nm == 1024 ? 1024 : 960;          // markers per CTA (960 = 60 full cells of 16: <= 64 runs)
+        const size_t smem = (size_t)nm * 16 + (size_t)a.ncol * nm * 8 + (nm + 2) * sizeof(unsigned short);
         plb_prof_scope prof_(ctx, PLB_K_T2G, (16.0 + 8.0 * a.ncol) * (double)M);
-        const long long nchunk = (M + TF_NM - 1) / TF_NM;
+        const long long nchunk = (M + nm - 1) / nm;
         if (nchunk > 0x7fffffffLL) PLB_FAIL(ctx, "plb_trac2grid_fused: too many markers");
-        // lanes per run: a sorted chunk holds ~TF_NM/16 runs; few tasks -> more lanes per run fill the CTA
-        int parts = ctx->t2g_parts > 0 ? ctx->t2g_parts : (a.nt >= 4 ? 2 : 4);
+        const int parts = ctx->t2g_parts > 0 ? ctx->t2g_parts : 1;     // lanes per run
         const double2* xx = (const double2*)d_tr_x;
         const unsigned g = (unsigned)nchunk;
-        if (parts >= 4) k_t2g_fused<4><<<g, TF_THREADS, smem, ctx->stream>>>(M, xx, a, aligned ? 1 : 0);
-        else if (parts == 2) k_t2g_fused<2><<<g, TF_THREADS, smem, ctx->stream>>>(M, xx, a, aligned ? 1 : 0);
-        else k_t2g_fused<1><<<g, TF_THREADS, smem, ctx->stream>>>(M, xx, a, aligned ? 1 : 0);
+        const int tma = aligned ? 1 : 0;
+#define TF_LAUNCH(P, N, B)                                                                                           \
+    do {                                                                                                             \
+        PLB_CUDA(ctx, cudaFuncSetAttribute(k_t2g_fused<P, N, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+        k_t2g_fused<P, N, B><<<g, TF_THREADS, smem, ctx->stream>>>(M, xx, a, tma);                                   \
+    } while (0)
+        // 3 resident CTAs per SM (<= 80 registers) while the staged chunk allows it, else 2
+        int nf_big = 0;
+        for (int i = 0; i < a.nt; i++) nf_big = std::max(nf_big, a.t[i].nf);
+        // (measured, 2048^2: 6 fields per node item want the registers of 2 CTAs/SM -- 2.48 vs 3.29 ms; <= 3 fields
+        // per item run as fast with 3 CTAs/SM, and a single-field call is 25 % faster with them)
+        const bool three = (ctx->t2g_minb == 3 || (ctx->t2g_minb != 2 && nf_big <= 3)) && 3 * (smem + 1280) <= 227 * 1024;
+        if (nm == 1024) {
+            if (parts >= 4) TF_LAUNCH(4, 1024, 2);
+            else if (parts == 2) TF_LAUNCH(2, 1024, 2);
+            else TF_LAUNCH(1, 1024, 2);
+        } else if (three) {
+            if (parts >= 4) TF_LAUNCH(4, 960, 3);
+            else if (parts == 2) TF_LAUNCH(2, 960, 3);
+            else TF_LAUNCH(1, 960, 3);
+        } else {
+            if (parts >= 4) TF_LAUNCH(4, 960, 2);
+            else if (parts == 2) TF_LAUNCH(2, 960, 2);
+            else TF_LAUNCH(1, 960, 2);
+        }
+#undef TF_LAUNCH
         PLB_LAUNCHED(ctx);
     }
     // marker-parallel ranks with replicated grids: sum the raw node sums over the ranks before dividing

@@ -72,12 +72,15 @@ resorted = markers.sort_by_cell(moved, [], nx, L)[0]
 for name, x in (("ordered", tr_x), ("displaced", moved), ("displaced_resorted", resorted)):
     mm = T.marker_minmax(x, ctx)
     r = {}
-    for parts in (1, 2, 4):
-        ctx.set_param("t2g_parts", parts)
+    for nm, nfmax, parts, minb in ((960, 6, 1, 2), (960, 6, 1, 3), (960, 3, 1, 3), (1024, 6, 1, 2), (960, 2, 1, 3)):
+        ctx.set_param("t2g_parts", parts), ctx.set_param("t2g_nm", nm), ctx.set_param("t2g_nfmax", nfmax)
+        ctx.set_param("t2g_minb", minb)
+        tag = "nm%d_nf%d_p%d_b%d" % (nm, nfmax, parts, minb)
         ms = timed(lambda: fused(x, mm))
-        r["fused4_parts%d_ms" % parts] = ms
-        r["fused4_parts%d_GBps(72B/marker)" % parts] = 72 * M / ms / 1e6
-        r["subgrid_parts%d_ms" % parts] = timed(lambda: subgrid(x, mm))
+        r["fused4_%s_ms" % tag] = round(ms, 3)
+        r["fused4_%s_GBps(72B/marker)" % tag] = round(72 * M / ms / 1e6)
+        r["subgrid_%s_ms" % tag] = round(timed(lambda: subgrid(x, mm)), 3)
+    ctx.set_param("t2g_nm", 0), ctx.set_param("t2g_nfmax", 0), ctx.set_param("t2g_minb", 0)
     ctx.set_param("t2g_parts", 0)
     r["separate4_ms"] = timed(lambda: separate(x, mm))
     res["t2g_" + name] = r

@@ -1,0 +1,8 @@
+#!/bin/bash
+python -m pytest -m gpu tests/test_markers_gpu.py -q -x --timeout 900 -k "fused or sort" 2>&1 | tail -8 > gpurun_out/r2_pytest5.log
+tail -4 gpurun_out/r2_pytest5.log
+python scripts/bench_markers2.py 2048 5 > gpurun_out/r2_bench_markers2_2048.json 2> gpurun_out/r2_bench_markers2.err
+python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_markers2_2048.json'))
+for k,v in d.items(): print(k, v)"
+tail -3 gpurun_out/r2_bench_markers2.err

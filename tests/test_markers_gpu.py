@@ -359,13 +359,14 @@ def test_trac2grid_fused_shapes_alignment_and_nonfinite_values(T):
     for node_k, centre_k in ((1, 1), (2, 2), (4, 1), (6, 2)):             # 1..2 node tasks, 1..2 centre tasks
         _fused_case(T, x, nx, L, node_k, centre_k)
     from pylamp_b200 import _lib
-    for parts in (1, 2, 4):                                                # lanes per run (default: automatic)
-        _lib.default_context().set_param("t2g_parts", parts)
+    ctx = _lib.default_context()
+    for parts, nm, nfmax in ((1, 1024, 3), (2, 960, 6), (4, 1024, 2), (2, 1024, 6)):   # tuning knobs: same results
+        ctx.set_param("t2g_parts", parts), ctx.set_param("t2g_nm", nm), ctx.set_param("t2g_nfmax", nfmax)
         try:
             _fused_case(T, x, nx, L, 6, 1)
             _fused_case(T, x[5:3000], nx, L, 1, 1, poison=True)
         finally:
-            _lib.default_context().set_param("t2g_parts", 0)
+            ctx.set_param("t2g_parts", 0), ctx.set_param("t2g_nm", 0), ctx.set_param("t2g_nfmax", 0)
     _fused_case(T, x, nx, L, 6, 1, view_offset=1)                          # 8-byte aligned views: no bulk copies
     _fused_case(T, x[:1], nx, L, 3, 1)                                     # a single marker
     _fused_case(T, x[:1024 * 3], nx, L, 6, 1)                              # whole chunks only
