@@ -39,7 +39,8 @@ SINGLE_KERNEL_CLASSES = (0, 1, 2, 3, 4, 5, 6, 9)
 # the reference's direct solve in vz / vx / P~ (513^2; north_star asks for 1e-8).  tests/test_stokes_large_gpu.py imports exactly these to hold the
 # time-loop solver (not a specially tightened one) to the 1e-8 parity bound against the reference's direct
 # solve at 513^2 and 1025^2 nodes.
-DEFAULTS = {"warm_start": 5, "nu": 2, "gmres_m": 30, "lmax_every": 8, "stokes_rtol": 1e-9, "heat_rtol": 1e-11}
+DEFAULTS = {"warm_start": 5, "nu": 2, "gmres_m": 30, "lmax_every": 8, "stokes_rtol": 1e-9, "heat_rtol": 1e-11,
+            "resort_every": 16}
 
 
 def stokes_params(warm_start=None, nu=None, gmres_m=None):
@@ -131,7 +132,9 @@ def run_reference(args):
     sec = float(np.mean(times))
     cores = 1
     sample = ("same C4 convection setup at %d^2 cells (%d markers) instead of 4096^2: scipy SuperLU needs "
-              "days and > host RAM at 4096^2 (BASELINE.md); NumPy/SuperLU path is single-threaded" % (ncell, M))
+              "days and > host RAM at 4096^2 (BASELINE.md: 0.15/0.95/11.2/140.6 s per solve at 64^2/128^2/256^2/512^2, "
+              "x12 per doubling); the NumPy/SuperLU path is single-threaded: 1 of the host's %d cores is used"
+              % (ncell, M, os.cpu_count() or 0))
     line = {"impl": "reference", "metric": "timesteps_per_s", "value": 1.0 / sec, "unit": "timesteps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -139,8 +142,9 @@ def run_reference(args):
             "config": {"workload": "C4 thermal convection Ra=1e6 (Stokes+energy+MIC), CPU sample at %d^2 cells, "
                                    "16 markers/cell" % ncell, "grid_nodes": nx, "markers": M},
             "stokes_dof_per_s": 3.0 * nx[0] * nx[1] / sec,
-            "cpu_baseline": {"value": 1.0 / sec, "unit": "timesteps/s", "cores": cores, "kind": "port",
-                             "sample": sample, "phases_s": {k: v / args.steps for k, v in timers.items()}},
+            "cpu_baseline": {"value": 1.0 / sec, "unit": "timesteps/s", "cores": cores, "host_cores": os.cpu_count(),
+                             "kind": "port", "sample": sample,
+                             "phases_s": {k: v / args.steps for k, v in timers.items()}},
             "e2e": {"value": 1.0 / sec, "unit": "timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -166,6 +170,8 @@ def run_b200(args):
     o.heat_rtol = args.heat_rtol
     o.marker_ownership = args.marker_ownership
     o.slab_reduce = bool(args.slab_reduce)
+    o.slab_local = bool(args.slab_local)
+    o.resort_every = args.resort_every
     o.stokes_rtol = args.stokes_rtol
     o.stokes_params = stokes_params(args.warm_start, args.nu, args.gmres_m)
     M = s.ntrac
@@ -267,10 +273,14 @@ def run_b200(args):
                                    "%d^2 cells, %d markers/cell, Stokes+energy+MIC advection" % (ncell, args.per_side ** 2),
                        "grid_nodes": nx, "markers": M, "stokes_dof": 3 * N,
                        "parallelism": "1 GPU" if world == 1 else
-                       "%d GPUs: z-slab Stokes and heat solves (NCCL halo send/recv + all-reduced dots), markers "
-                       "%s, node sums all-reduced, replicated grid fields" %
-                       (world, "owned by z-slab with migration after every step" if args.marker_ownership == "slab"
-                        else "shared by index (no migration needed)"),
+                       "%d GPUs, one 4096^2 problem in z-slabs: %s" %
+                       (world, "slab-owned markers that migrate after every step, slab-local grid fields (boundary-row "
+                        "accumulate + halo rows over NCCL send/recv, all-reduced scalars; no full-plane collective)"
+                        if (args.marker_ownership == "slab" and args.slab_local) else
+                        ("slab-owned markers with migration, replicated fields" if args.marker_ownership == "slab" else
+                         "markers shared by index, replicated fields, raw node sums all-reduced")),
+                       "marker_order": "device counting sort by cell every %d steps (inside the timed region when due)" % args.resort_every
+                       if args.resort_every else "never re-sorted",
                        "l2_policy": "every field (%.0f MB) and marker array exceeds the 126 MB L2; no flush needed" % (8 * N / 1e6),
                        "spinup_steps": args.spinup, "stokes_rtol": o.stokes_rtol,
                        "stokes_rtol_eff_max": max(i.get("stokes_rtol_eff", 0.0) for i in iters),
@@ -287,7 +297,8 @@ def run_b200(args):
     if world == 1 and args.cpu_ncell > 0:
         times, cnx, cM, timers = cpu_reference_steps(args.cpu_ncell, 2, 0)
         sec = float(np.mean(times))
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "timesteps/s", "cores": 1, "kind": "port",
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "timesteps/s", "cores": 1, "host_cores": os.cpu_count(),
+                                "kind": "port",
                                 "sample": "2 steps of the same C4 setup at %d^2 cells (%d markers); the reference "
                                           "cannot run 4096^2 (SuperLU: days, > host RAM)" % (args.cpu_ncell, cM),
                                 "stokes_dof_per_s": 3.0 * cnx[0] * cnx[1] / sec,
@@ -298,28 +309,28 @@ def run_b200(args):
 
 
 def run_e2e(torch, driver, s, o, nsteps):
-    """Same timestep with HOST state: per step, marker coordinates + the 9 live property columns are
-    copied from pinned host memory to the device, the step runs, and new coordinates, marker
-    temperature, marker velocities and the velocity/pressure/temperature grids are copied back."""
-    from pylamp_b200.pylamp_const import (TR_ACE, TR_ALP, TR_ET0, TR_HCD, TR_HCP, TR_IHT, TR_MAT, TR_RH0, TR_TMP)
-    live = [TR_TMP, TR_RH0, TR_ALP, TR_ACE, TR_ET0, TR_HCD, TR_HCP, TR_IHT, TR_MAT]
+    """The same timestep through HOST buffers.  What a time step takes in and hands back is the state that changes:
+    marker coordinates and marker temperature go from pinned host memory to the device, the step runs, and the new
+    coordinates, marker temperature, marker velocities and the velocity / pressure / temperature grids come back
+    (the constant material columns -- rho0, alpha, Ea, eta0, k, Cp, H, material id -- are uploaded once with the
+    set-up, like the grids' axes).  The download of step n's grids overlaps nothing: everything is inside the
+    timed region, one stream, synchronised per step."""
+    from pylamp_b200.pylamp_const import TR_TMP
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
-    h_x = pin(s.tr_x)
-    h_cols = {k: pin(s.cols[k]) for k in live}
+    h_x, h_T = pin(s.tr_x), pin(s.cols[TR_TMP])
     h_v = torch.empty(s.tr_x.shape, dtype=torch.float64, pin_memory=True)
     h_grids = [torch.empty(tuple(s.nx), dtype=torch.float64, pin_memory=True) for _ in range(4)]
-    h2d = h_x.numel() * 8 + sum(c.numel() * 8 for c in h_cols.values())
-    d2h = h_x.numel() * 8 * 2 + h_cols[TR_TMP].numel() * 8 + 4 * h_grids[0].numel() * 8
+    h2d = (h_x.numel() + h_T.numel()) * 8
+    d2h = (h_x.numel() + h_T.numel() + h_v.numel() + 4 * h_grids[0].numel()) * 8
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(nsteps):
         s.tr_x.copy_(h_x, non_blocking=True)
-        for k in live:
-            s.cols[k].copy_(h_cols[k], non_blocking=True)
+        s.cols[TR_TMP].copy_(h_T, non_blocking=True)
         driver.timestep(s, o, want_kelem=False)
         h_x.copy_(s.tr_x, non_blocking=True)
-        h_cols[TR_TMP].copy_(s.cols[TR_TMP], non_blocking=True)
+        h_T.copy_(s.cols[TR_TMP], non_blocking=True)
         h_v.copy_(s.trac_vel, non_blocking=True)
         for h, d in zip(h_grids, (s.newvel[0], s.newvel[1], s.newpres, s.newtemp)):
             h.copy_(d, non_blocking=True)
@@ -345,10 +356,14 @@ def main():
     ap.add_argument("--warm-start", type=int, default=DEFAULTS["warm_start"], help="Stokes initial guess: 0 zero, 1 previous iterate, p >= 2: polynomial extrapolation of the last p iterates")
     ap.add_argument("--nu", type=int, default=DEFAULTS["nu"], help="Chebyshev steps per pre-/post-smoothing")
     ap.add_argument("--gmres-m", type=int, default=DEFAULTS["gmres_m"], help="FGMRES restart length of the Stokes solve")
-    ap.add_argument("--marker-ownership", default="index", choices=["index", "slab"],
-                    help="several GPUs: markers stay with their rank (index) or are owned by z-slab and migrate (slab)")
+    ap.add_argument("--marker-ownership", default="slab", choices=["index", "slab"],
+                    help="several GPUs: markers are owned by z-slab and migrate (slab, default) or stay with their rank (index)")
+    ap.add_argument("--slab-local", type=int, default=1,
+                    help="with --marker-ownership slab: slab-local grid fields, no full-plane collective (default)")
     ap.add_argument("--slab-reduce", type=int, default=0,
-                    help="with --marker-ownership slab: boundary-row exchange + all-gather instead of the all-reduce of node sums")
+                    help="with --marker-ownership slab --slab-local 0: boundary-row exchange + all-gather instead of the all-reduce")
+    ap.add_argument("--resort-every", type=int, default=DEFAULTS["resort_every"],
+                    help="re-sort the markers by cell every n-th step (0: never)")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
     ap.add_argument("--ref-ncell", type=int, default=256, help="--impl reference sample size")
     args = ap.parse_args()

@@ -80,6 +80,18 @@ int plb_comm_init(plb_ctx* ctx, int rank, int size, const char* h_id128);
 int plb_comm_info(plb_ctx* ctx, int* h_rank, int* h_size);
 /* in-place all-reduce of a device buffer of doubles; op: 0 sum, 1 max, 2 min */
 int plb_allreduce(plb_ctx* ctx, double* d_buf, long long count, int op);
+/* Slab-local grid fields (north_star: "the domain shards naturally into slabs"; replaces the replicated data +
+ * Allreduce of pylamp2.py:445-455, :550-555).  After plb_ctx_set_slab(i0, i1, halo) the context's rank keeps
+ * only the node rows [i0, i1) of every (nz x ld) grid field current -- the rows of its z-slab of the Stokes and
+ * heat solvers; the last rank also owns the last node row -- plus `halo` rows of each neighbour, and its markers
+ * must lie in the cell rows [i0, min(i1, nz-1)) (pylamp_b200/migrate.py moves them after advection).  Then
+ * plb_trac2grid / plb_trac2grid_fused add the boundary rows of neighbouring slabs (grouped ncclSend/ncclRecv),
+ * finish the own rows and exchange halo rows of the results instead of all-reducing whole planes;
+ * plb_stokes_solve / plb_diff_solve return their own rows plus halo rows (no zero-filled full-size vector to sum).
+ * i1 <= i0 switches back to replicated fields.  plb_halo_rows: exchange `h` halo rows of narr full-size arrays
+ * (h_row_doubles[a] doubles per row) with both z-neighbours, one NCCL group. */
+int plb_ctx_set_slab(plb_ctx* ctx, int i0, int i1, int halo);
+int plb_halo_rows(plb_ctx* ctx, int narr, double* const* h_ptrs, const long long* h_row_doubles, int i0, int i1, int h);
 void plb_comm_destroy(plb_ctx* ctx);
 
 /* ---- the marker->grid targets of one time step in ONE pass over the markers -------------------

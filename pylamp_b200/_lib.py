@@ -34,6 +34,8 @@ _PROTOS = {
     "plb_comm_info": (I, [VP, IP, IP]),
     "plb_allreduce": (I, [VP, VP, LL, I]),
     "plb_comm_destroy": (None, [VP]),
+    "plb_ctx_set_slab": (I, [VP, I, I, I]),
+    "plb_halo_rows": (I, [VP, I, PP, C.POINTER(LL), I, I, I]),
     "plb_marker_minmax": (I, [VP, LL, VP, DP]),
     "plb_sort_plan": (I, [VP, LL, VP, I, I, D, D, VP, VP]),
     "plb_permute": (I, [VP, LL, VP, VP, VP, I]),
@@ -139,6 +141,7 @@ class Context:
         if rc != 0:
             raise PlbError("plb_ctx_create(device=%d) failed with %d" % (device, rc))
         self.h = h
+        self.slab = None
         # run on torch's current stream so that torch allocations/copies order with our kernels
         self.torch_device = torch.device("cuda", self.device)
         stream = torch.cuda.current_stream(self.torch_device)
@@ -172,6 +175,19 @@ class Context:
         self.call("plb_comm_init", rank, size, C.create_string_buffer(ident, 128))
         self.rank, self.size = rank, size
         return rank, size
+
+    def set_slab(self, i0, i1, halo=3):
+        """Slab-local grid fields (plb_ctx_set_slab): this rank keeps node rows [i0, i1) of every field current,
+        plus `halo` rows of each z-neighbour; i1 <= i0 switches back to replicated fields."""
+        self.call("plb_ctx_set_slab", int(i0), int(i1), int(halo))
+        self.slab = (int(i0), int(i1), int(halo)) if i1 > i0 else None
+
+    def halo_rows(self, tensors, h=None):
+        """Exchange halo rows of full-size (nz, ...) float64 tensors with both z-neighbours (plb_halo_rows)."""
+        i0, i1, halo = self.slab
+        arr = ptr_array(tensors)
+        rd = (LL * len(tensors))(*[int(t[0].numel()) for t in tensors])
+        self.call("plb_halo_rows", len(tensors), arr, rd, i0, i1, halo if h is None else int(h))
 
     def comm_info(self):
         r, s = C.c_int(0), C.c_int(1)

@@ -5,6 +5,8 @@
 // dependency on it and single-GPU use never touches it.
 #include <dlfcn.h>
 
+#include <algorithm>
+
 #include "comm.cuh"
 
 namespace {
@@ -99,7 +101,96 @@ int plb_comm_halo_exchange(plb_ctx* ctx, double* base, int nplanes, size_t plane
     return 0;
 }
 
+int plb_comm_halo_rows(plb_ctx* ctx, int narr, double* const* arrs, const long long* row_doubles, int i0, int i1, int h) {
+    plb_comm* c = ctx->comm;
+    if (!c || c->size == 1 || h <= 0) return 0;
+    const bool has_dn = c->rank > 0, has_up = c->rank < c->size - 1;
+    PLB_NCCL(ctx, api.GroupStart());
+    for (int a = 0; a < narr; a++) {
+        const size_t rd = (size_t)row_doubles[a];
+        double* p = arrs[a];
+        if (has_dn) {
+            PLB_NCCL(ctx, api.Send(p + (size_t)i0 * rd, h * rd, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+            PLB_NCCL(ctx, api.Recv(p + (size_t)(i0 - h) * rd, h * rd, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+        }
+        if (has_up) {
+            PLB_NCCL(ctx, api.Send(p + (size_t)(i1 - h) * rd, h * rd, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+            PLB_NCCL(ctx, api.Recv(p + (size_t)i1 * rd, h * rd, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+        }
+    }
+    PLB_NCCL(ctx, api.GroupEnd());
+    return 0;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) k_add_rows(long long n, const double* __restrict__ src, double* __restrict__ dst) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        dst[t] += src[t];
+}
+}  // namespace
+
+int plb_comm_accumulate_rows(plb_ctx* ctx, int narr, double* const* arrs, const long long* row_doubles,
+                             const int* i0, const int* i1, const int* nrows, int h, double* scratch) {
+    plb_comm* c = ctx->comm;
+    if (!c || c->size == 1 || h <= 0) return 0;
+    const bool has_dn = c->rank > 0, has_up = c->rank < c->size - 1;
+    // what the neighbours wrote into my first / last h rows arrives in scratch, then is added
+    PLB_NCCL(ctx, api.GroupStart());
+    size_t off = 0;
+    for (int a = 0; a < narr; a++) {
+        const size_t rd = (size_t)row_doubles[a];
+        double* p = arrs[a];
+        if ((has_dn && i0[a] < h) || (has_up && nrows[a] - i1[a] < h) || i1[a] - i0[a] < h)
+            PLB_FAIL(ctx, "plb_comm_accumulate_rows: slab [%d, %d) of %d rows is too thin for %d boundary rows", i0[a], i1[a], nrows[a], h);
+        const int hd = h, hu = h;
+        if (has_dn) {
+            PLB_NCCL(ctx, api.Send(p + (size_t)(i0[a] - hd) * rd, hd * rd, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+            PLB_NCCL(ctx, api.Recv(scratch + off, h * rd, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+        }
+        off += h * rd;
+        if (has_up) {
+            PLB_NCCL(ctx, api.Send(p + (size_t)i1[a] * rd, hu * rd, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+            PLB_NCCL(ctx, api.Recv(scratch + off, h * rd, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+        }
+        off += h * rd;
+    }
+    PLB_NCCL(ctx, api.GroupEnd());
+    off = 0;
+    for (int a = 0; a < narr; a++) {
+        const size_t rd = (size_t)row_doubles[a];
+        double* p = arrs[a];
+        const long long n = (long long)h * rd;
+        // the lower neighbour's rows [its i1, its i1 + h) are my rows [i0, i0 + h); the upper one's
+        // [its i0 - h, its i0) are my [i1 - h, i1)
+        if (has_dn) {
+            k_add_rows<<<plb_grid_for(ctx, n, 256, 4), 256, 0, ctx->stream>>>(n, scratch + off, p + (size_t)i0[a] * rd);
+            PLB_LAUNCHED(ctx);
+        }
+        off += h * rd;
+        if (has_up) {
+            k_add_rows<<<plb_grid_for(ctx, n, 256, 4), 256, 0, ctx->stream>>>(n, scratch + off, p + (size_t)(i1[a] - h) * rd);
+            PLB_LAUNCHED(ctx);
+        }
+        off += h * rd;
+    }
+    return 0;
+}
+
 extern "C" {
+
+int plb_ctx_set_slab(plb_ctx* ctx, int i0, int i1, int halo) {
+    if (!ctx) return 1;
+    if (i1 < i0 || halo < 0) PLB_FAIL(ctx, "plb_ctx_set_slab: bad row range [%d, %d) / halo %d", i0, i1, halo);
+    ctx->slab_i0 = i0, ctx->slab_i1 = i1, ctx->slab_halo = halo;
+    ctx->slab_on = i1 > i0;
+    return 0;
+}
+
+int plb_halo_rows(plb_ctx* ctx, int narr, double* const* h_ptrs, const long long* h_row_doubles, int i0, int i1, int h) {
+    if (!ctx) return 1;
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return plb_comm_halo_rows(ctx, narr, h_ptrs, h_row_doubles, i0, i1, h);
+}
 
 int plb_comm_unique_id(plb_ctx* ctx, char* h_id128) {
     if (!ctx || !h_id128) return 1;

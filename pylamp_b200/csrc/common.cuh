@@ -28,6 +28,12 @@ struct plb_ctx {
     int prof_cap, prof_used;
     long long prof_skipped[16];
     double* prof_bytes;    // algorithmic bytes per recorded pair
+    // slab-local fields (several ranks): this rank keeps node rows [slab_i0, slab_i1) of every grid field current,
+    // plus slab_halo rows of each z-neighbour; its markers lie in the cell rows [slab_i0, min(slab_i1, nz-1))
+    bool slab_on;
+    int slab_i0, slab_i1, slab_halo;
+    double* slab_scratch;  // receive buffer of the boundary-row accumulate (grown on demand)
+    size_t slab_scratch_dbl;
     // tuning knobs (plb_ctx_set_param)
     int t2g_variant;       // 1: wide-load chunk kernel for weighted schemes (default), 0: generic kernel only
     int t2g_parts;         // fused step kernel: lanes per run (0 = 1; 1, 2, 4)

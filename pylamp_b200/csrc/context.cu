@@ -40,6 +40,7 @@ void plb_ctx_destroy(plb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     plb_comm_destroy(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->slab_scratch) cudaFree(ctx->slab_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->prof_ev) {
         for (int i = 0; i < 2 * ctx->prof_cap; i++) cudaEventDestroy(ctx->prof_ev[i]);

@@ -124,6 +124,7 @@ struct plb_diff {
     // z-slab ownership when the context has a communicator: rows [i0, i1), stored rows [lo, hi]
     int i0 = 0, i1 = 0, lo = 0, hi = 0;
     bool dist = false;
+    bool slab_fields = false;              // fields and result are slab-local (plb_ctx_set_slab)
     size_t plane = 0;                      // local plane size
     long long shift = 0;
     int m = 40;
@@ -169,7 +170,13 @@ int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_
     PLB_CUDA(ctx, cudaMalloc(&op->d_scal, sizeof(double) * 1024));
     const int R = plb_comm_size(ctx), rank = plb_comm_rank(ctx);
     op->dist = R > 1 && nz >= 4 * R;
-    if (op->dist) {
+    op->slab_fields = op->dist && ctx->slab_on;
+    if (op->slab_fields) {
+        // slab-local fields: the rows the context declared (those of the Stokes slabs)
+        if (ctx->slab_i1 > nz) PLB_FAIL(ctx, "plb_diff_create: slab rows [%d, %d) exceed %d node rows", ctx->slab_i0, ctx->slab_i1, nz);
+        op->i0 = ctx->slab_i0, op->i1 = ctx->slab_i1;
+        op->lo = rank > 0 ? op->i0 - 1 : 0, op->hi = rank < R - 1 ? op->i1 : nz - 1;
+    } else if (op->dist) {
         op->i0 = (int)((long long)rank * nz / R), op->i1 = (int)((long long)(rank + 1) * nz / R);
         op->lo = rank > 0 ? op->i0 - 1 : 0, op->hi = rank < R - 1 ? op->i1 : nz - 1;
     } else {
@@ -294,9 +301,16 @@ int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, do
     if (h_iters) *h_iters = res.iters;
     if (h_relres) *h_relres = res.relres;
     // full-size result: a slab rank fills its own rows, the rest stays zero (summed by the host side)
-    if (op->dist) PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * (size_t)op->nz * op->ld, ctx->stream));
+    // (slab-local fields: own rows only, then halo rows from the neighbours)
+    if (op->dist && !op->slab_fields)
+        PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * (size_t)op->nz * op->ld, ctx->stream));
     PLB_CUDA(ctx, cudaMemcpyAsync(d_x + (size_t)op->i0 * op->ld, x + own_off, sizeof(double) * own_len,
                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    if (op->slab_fields) {
+        double* arrs[1] = {d_x};
+        const long long rd[1] = {op->ld};
+        if (plb_comm_halo_rows(ctx, 1, arrs, rd, op->i0, op->i1, ctx->slab_halo)) return 2;
+    }
     if (!res.converged && res.relres > 1e3 * rtol)
         PLB_FAIL(ctx, "plb_diff_solve: not converged after %d iterations (relres %.3e > rtol %.3e)", res.iters,
                  res.relres, rtol);

@@ -5,6 +5,7 @@
 // Reference behaviour restated (never copied): pylamp_trac.py:30-158 (grid2trac), :161-318
 // (trac2grid), :321-388 (RK); pylamp2.py:291-303, :471-476, :558-572, :588-593.
 #include <algorithm>
+#include <vector>
 
 #include "comm.cuh"
 
@@ -1119,6 +1120,75 @@ k_t2g_fused(long long M, const double2* __restrict__ trx, const TFArgs a, int us
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// From raw node sums to finished fields, for one or several targets whose planes lie in one block:
+//  * one rank: divide / exponentiate (k_t2g_finalise);
+//  * several ranks, replicated fields (any marker on any rank): all-reduce the raw planes first;
+//  * several ranks, slab-local fields (plb_ctx_set_slab: a rank's markers lie in its own cell rows, so its
+//    sums reach at most one node row into a neighbour's slab): add the boundary rows of the neighbouring
+//    slabs (grouped ncclSend/ncclRecv), finish the own rows only, exchange halo rows of the results.
+// ---------------------------------------------------------------------------------------------
+constexpr int T2G_BOUNDARY_ROWS = 2;
+
+struct T2GFinish {
+    T2GArgs a;
+    int crop_z0, crop_x0;
+};
+
+int t2g_finish(plb_ctx* ctx, int n, T2GFinish* fin, double* planes, size_t nplane_dbl, int nz, int nxx, int ld) {
+    const int R = plb_comm_size(ctx);
+    int r0 = 0, r1 = nz;
+    const bool slab = R > 1 && ctx->slab_on;
+    if (slab) {
+        if (ctx->slab_i1 > nz) PLB_FAIL(ctx, "trac2grid: slab rows [%d, %d) exceed the %d node rows", ctx->slab_i0, ctx->slab_i1, nz);
+        r0 = ctx->slab_i0, r1 = ctx->slab_i1;
+        std::vector<double*> arrs;
+        std::vector<long long> rd;
+        std::vector<int> i0, i1, nr;
+        size_t need = 0;
+        for (int t = 0; t < n; t++) {
+            const T2GArgs& a = fin[t].a;
+            auto add = [&](double* p) {
+                if (!p) return;
+                arrs.push_back(p), rd.push_back(a.nxe), i0.push_back(r0 + fin[t].crop_z0), i1.push_back(r1 + fin[t].crop_z0);
+                nr.push_back(a.nze);
+                need += 2 * (size_t)T2G_BOUNDARY_ROWS * a.nxe;
+            };
+            for (int f = 0; f < a.k; f++) add(a.acc[f]);
+            add(a.wsum), add(a.cnt);
+        }
+        if (need > ctx->slab_scratch_dbl) {
+            PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->slab_scratch) cudaFree(ctx->slab_scratch);
+            ctx->slab_scratch = nullptr, ctx->slab_scratch_dbl = 0;
+            PLB_CUDA(ctx, cudaMalloc(&ctx->slab_scratch, need * sizeof(double)));
+            ctx->slab_scratch_dbl = need;
+        }
+        if (plb_comm_accumulate_rows(ctx, (int)arrs.size(), arrs.data(), rd.data(), i0.data(), i1.data(), nr.data(),
+                                     T2G_BOUNDARY_ROWS, ctx->slab_scratch))
+            return 2;
+    } else if (R > 1) {
+        if (plb_comm_allreduce(ctx, planes, nplane_dbl, PLB_OP_SUM)) return 2;
+    }
+    std::vector<double*> outs;
+    std::vector<long long> ord;
+    for (int t = 0; t < n; t++) {
+        T2GArgs a = fin[t].a;
+        for (int f = 0; f < a.k; f++) {
+            outs.push_back(a.out[f]), ord.push_back(ld);
+            a.out[f] += (size_t)r0 * ld;
+        }
+        const int rows = r1 - r0;
+        if (rows > 0) {
+            k_t2g_finalise<<<plb_grid_for(ctx, (long long)rows * nxx, 256, 8), 256, 0, ctx->stream>>>(
+                a, fin[t].crop_z0 + r0, fin[t].crop_x0, rows, nxx, ld);
+            PLB_LAUNCHED(ctx);
+        }
+    }
+    if (slab && plb_comm_halo_rows(ctx, (int)outs.size(), outs.data(), ord.data(), r0, r1, ctx->slab_halo)) return 2;
+    return 0;
+}
+
 template <int K>
 void launch_scatter(plb_ctx* ctx, long long M, const double2* x, const T2GArgs& a) {
     int threads = 256;
@@ -1242,13 +1312,9 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
         }
         PLB_LAUNCHED(ctx);
     }
-    // marker-parallel ranks (each holds a share of the markers, the grids are replicated): sum the
-    // raw node sums over the ranks before dividing
-    if (plb_comm_size(ctx) > 1 && plb_comm_allreduce(ctx, w, nplanes * plane, PLB_OP_SUM)) return 2;
-    k_t2g_finalise<<<plb_grid_for(ctx, (long long)nz * nxx, 256, 8), 256, 0, ctx->stream>>>(
-        a, crop_z0, crop_x0, nz, nxx, ld);
-    PLB_LAUNCHED(ctx);
-    return 0;
+    T2GFinish fin;
+    fin.a = a, fin.crop_z0 = crop_z0, fin.crop_x0 = crop_x0;
+    return t2g_finish(ctx, 1, &fin, w, nplanes * plane, nz, nxx, ld);
 }
 
 // The step's marker->grid targets in ONE pass over the markers (k_t2g_fused above).  Every target is
@@ -1382,11 +1448,10 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
 #undef TF_LAUNCH
         PLB_LAUNCHED(ctx);
     }
-    // marker-parallel ranks with replicated grids: sum the raw node sums over the ranks before dividing
-    if (plb_comm_size(ctx) > 1 && plb_comm_allreduce(ctx, w, nplane_dbl, PLB_OP_SUM)) return 2;
+    T2GFinish fin[8];
     for (int i = 0; i < ntargets; i++) {
         const plb_t2g_target& T = tg[i];
-        T2GArgs fa;
+        T2GArgs& fa = fin[i].a;
         memset(&fa, 0, sizeof(fa));
         const size_t plane = (size_t)T.nze * T.nxe;
         fa.wsum = w + plane_off[i];
@@ -1396,11 +1461,9 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
             fa.scheme[f] = T.scheme[f];
         }
         fa.nze = T.nze, fa.nxe = T.nxe, fa.k = T.k;
-        k_t2g_finalise<<<plb_grid_for(ctx, (long long)nz * nxx, 256, 8), 256, 0, ctx->stream>>>(fa, T.crop_z0, T.crop_x0,
-                                                                                            nz, nxx, ld);
-        PLB_LAUNCHED(ctx);
+        fin[i].crop_z0 = T.crop_z0, fin[i].crop_x0 = T.crop_x0;
     }
-    return 0;
+    return t2g_finish(ctx, ntargets, fin, w, nplane_dbl, nz, nxx, ld);
 }
 
 // plb_trac2grid in two halves for slab-owned markers (pylamp_b200/slabgrid.py): the raw sums land in

@@ -73,6 +73,7 @@ struct plb_stokes {
     double* surf_d = nullptr;
     double Kc = 0, Kb = 0;
     bool coeffs = false, hierarchy = false;
+    bool slab_fields = false;     // coefficient fields and results are slab-local (plb_ctx_set_slab): own rows + halo rows
     plb_reduce_ws rws{};
     double* d_scal = nullptr;     // 128 device scalars
     // dense coarse solve
@@ -804,9 +805,9 @@ k_prolong_add(LevelDev F, LevelDev Cc, const double* __restrict__ ez, const doub
 // with sharp contrasts) or the plain mean of its 2x2 fine cells (narrow)
 __global__ void __launch_bounds__(BX* BY)
 k_coarsen_eta(int nzf, int nxf, int ldf, const double* __restrict__ es, const double* __restrict__ en,
-              int nzc, int nxc, int ldc, double* __restrict__ cs, double* __restrict__ cn, int wide) {
-    const int J = blockIdx.x * BX + threadIdx.x, I = blockIdx.y * BY + threadIdx.y;
-    if (I >= nzc || J >= nxc) return;
+              int nzc, int nxc, int ldc, double* __restrict__ cs, double* __restrict__ cn, int wide, int I0, int I1) {
+    const int J = blockIdx.x * BX + threadIdx.x, I = I0 + blockIdx.y * BY + threadIdx.y;
+    if (I >= I1 || J >= nxc) return;
     const double w3[3] = {0.25, 0.5, 0.25};
     double s = 0;
 #pragma unroll
@@ -1291,12 +1292,32 @@ int vcycle(plb_stokes* op, int l, const double* b, double* xout) {
 int setup_hierarchy(plb_stokes* op) {
     plb_ctx* ctx = op->ctx;
     const int nlev = (int)op->lv.size();
-    // coarse viscosities: full grids, computed redundantly on every rank
+    // coarse viscosities.  Replicated coefficient fields: full grids, computed redundantly on every rank.
+    // Slab-local fields (plb_ctx_set_slab): a rank coarsens the rows of its own slab -- coarse row I needs the fine
+    // rows 2I-1 .. 2I+2, i.e. one halo row either side -- and then exchanges one halo row of the coarse fields;
+    // at the first replicated level every rank contributes its rows and the (small) planes are summed.
     for (int l = 1; l < nlev; l++) {
         Level &F = op->lv[l - 1], &Cc = op->lv[l];
-        k_coarsen_eta<<<grid2d(Cc.nz, Cc.nxx), block2d(), 0, ctx->stream>>>(
-            F.nz, F.nxx, F.ld, F.etas, F.etan, Cc.nz, Cc.nxx, Cc.ld, Cc.etas_own, Cc.etan_own, op->coarsen_wide);
+        int I0 = 0, I1 = Cc.nz;
+        const bool slabf = op->slab_fields && F.dist;
+        if (slabf) {
+            I0 = F.i0 / 2, I1 = (F.i1 + 1) / 2;
+            if (!Cc.dist) {
+                PLB_CUDA(ctx, cudaMemsetAsync(Cc.etas_own, 0, sizeof(double) * Cc.full, ctx->stream));
+                PLB_CUDA(ctx, cudaMemsetAsync(Cc.etan_own, 0, sizeof(double) * Cc.full, ctx->stream));
+            }
+        }
+        k_coarsen_eta<<<grid2d(I1 - I0, Cc.nxx), block2d(), 0, ctx->stream>>>(
+            F.nz, F.nxx, F.ld, F.etas, F.etan, Cc.nz, Cc.nxx, Cc.ld, Cc.etas_own, Cc.etan_own, op->coarsen_wide, I0, I1);
         PLB_LAUNCHED(ctx);
+        if (slabf && Cc.dist) {
+            double* arrs[2] = {Cc.etas_own, Cc.etan_own};
+            const long long rd[2] = {Cc.ld, Cc.ld};
+            if (plb_comm_halo_rows(ctx, 2, arrs, rd, Cc.i0, Cc.i1, 1)) return 2;
+        } else if (slabf) {
+            if (plb_comm_allreduce(ctx, Cc.etas_own, Cc.full, PLB_OP_SUM) || plb_comm_allreduce(ctx, Cc.etan_own, Cc.full, PLB_OP_SUM))
+                return 2;
+        }
     }
     // largest eigenvalue of D^-1 K per level by power iteration.  The estimate (with its 10 % safety
     // margin) is reused for `lmax_every` consecutive coefficient updates: the viscosity field of a
@@ -1530,8 +1551,20 @@ int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_
     double* d = op->d_scal + 920;
     k_set1<<<1, 1, 0, ctx->stream>>>(d, INFINITY);
     PLB_LAUNCHED(ctx);
-    k_min2<<<plb_grid_for(ctx, (long long)L.full, 256, 8), 256, 0, ctx->stream>>>((long long)L.full, d_etas, d_etan, d);
-    PLB_LAUNCHED(ctx);
+    op->slab_fields = ctx->slab_on && L.dist;
+    if (op->slab_fields) {
+        if (ctx->slab_i0 != L.i0 || ctx->slab_i1 != L.i1)
+            PLB_FAIL(ctx, "plb_stokes_set_coeffs: the context's slab rows [%d, %d) are not the solver's [%d, %d)", ctx->slab_i0,
+                     ctx->slab_i1, L.i0, L.i1);
+        // the own rows of both fields (the last rank's include the ghost row), then the minimum over the ranks
+        const long long off = (long long)L.i0 * L.ld, cnt = (long long)(L.i1 - L.i0) * L.ld;
+        k_min2<<<plb_grid_for(ctx, cnt, 256, 8), 256, 0, ctx->stream>>>(cnt, d_etas + off, d_etan + off, d);
+        PLB_LAUNCHED(ctx);
+        if (plb_comm_allreduce(ctx, d, 1, PLB_OP_MIN)) return 2;
+    } else {
+        k_min2<<<plb_grid_for(ctx, (long long)L.full, 256, 8), 256, 0, ctx->stream>>>((long long)L.full, d_etas, d_etan, d);
+        PLB_LAUNCHED(ctx);
+    }
     double mineta;
     if (plb_read_scalars(ctx, d, 1, &mineta)) return 2;
     // avgd = L/n with n = number of NODES (sic), pylamp_stokes.py:119-120
@@ -1816,13 +1849,20 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     if (h_relres) *h_relres = res.relres;
     // full-size interleaved solution; a slab rank fills its own rows and leaves the rest zero (the
     // host side sums the pieces, e.g. with plb_allreduce)
-    if (L.dist) PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * 3 * L.full, ctx->stream));
+    // host side sums the pieces, e.g. with plb_allreduce); with slab-local fields only the own rows are written
+    // and halo rows exchanged with the neighbours below
+    if (L.dist && !op->slab_fields) PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * 3 * L.full, ctx->stream));
     double* panchor = op->d_scal + 930;
     k_get_anchor<<<1, 1, 0, ctx->stream>>>(D, C3(x, 2), panchor);
     PLB_LAUNCHED(ctx);
     if (L.dist && plb_comm_allreduce(ctx, panchor, 1, PLB_OP_SUM)) return 2;
     k_solution_out<<<g, blk, 0, ctx->stream>>>(D, C3(x, 0), C3(x, 1), C3(x, 2), ph, panchor, d_x);
     PLB_LAUNCHED(ctx);
+    if (op->slab_fields) {
+        double* arrs[1] = {d_x};
+        const long long rd[1] = {3LL * L.nxx};
+        if (plb_comm_halo_rows(ctx, 1, arrs, rd, L.i0, L.i1, ctx->slab_halo)) return 2;
+    }
     if (!res.converged && res.relres > op->rtol_accept)
         PLB_FAIL(ctx, "plb_stokes_solve: not converged after %d iterations (relres %.3e > rtol %.3e, "
                       "accept %.1e)", total, res.relres, rtol, op->rtol_accept);

@@ -67,14 +67,48 @@ class Options:
         # slab-owned markers only: combine the node sums by a boundary-row exchange with the neighbouring
         # slabs + an all-gather of the finished rows instead of all-reducing every raw plane (slabgrid.py)
         self.slab_reduce = False
+        # slab-owned markers only: SLAB-LOCAL GRID FIELDS (the north_star decomposition) -- a rank keeps the node rows
+        # of its own z-slab (+ SLAB_HALO rows of each neighbour) of every grid field current and nothing else:
+        # trac2grid adds the boundary rows of neighbouring slabs and exchanges halo rows of the results, the solvers
+        # coarsen / solve / return their own rows, reductions are all-reduced scalars.  No full-plane collective
+        # is left in the step.  Takes precedence over `slab_reduce`.
+        self.slab_local = True
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
             setattr(self, k, v)
 
 
+SLAB_HALO = 3     # halo rows of slab-local fields (RK4 reaches 0.67 cells beyond a marker's cell on the half-shifted
+                  # centre grid; stencils and interpolations need one row)
+
+
 def _clamp(v, lo, hi):
     return max(min(v, hi), lo)
+
+
+def slab_rows(s):
+    """Node rows [i0, i1) this rank owns with slab-local fields (the rows of the z-slab solvers: an even split of
+    the cell rows, the last rank also owns the last node row), or None."""
+    return None if s.ctx.slab is None else s.ctx.slab[:2]
+
+
+def full_field(s, f):
+    """The whole (nz, nxx) field on every rank from slab-local pieces (tests, output): own rows summed over ranks."""
+    rows = slab_rows(s)
+    if rows is None:
+        return f
+    g = torch.zeros_like(f)
+    g[rows[0]:rows[1]] = f[rows[0]:rows[1]]
+    return s.ctx.allreduce(g.view(-1)).view(f.shape) if g.is_contiguous() else g
+
+
+def _gmax(s, v):
+    """max over the ranks of a host scalar (slab-local reductions)."""
+    if s.ctx.slab is None:
+        return v
+    t = torch.tensor([float(v)], dtype=torch.float64, device=s.ctx.torch_device)
+    return float(s.ctx.allreduce(t, "max").item())
 
 
 class State:
@@ -161,7 +195,19 @@ def timestep(s, o, want_kelem=True, phases=False):
     # markers -> grids, pylamp2.py:307-319
     mm = pylamp_trac.marker_minmax(tr_x, ctx)
     t2g = pylamp_trac.trac2grid_device
-    if o.slab_reduce and o.marker_ownership == "slab" and ctx.comm_info()[1] > 1:
+    world = ctx.comm_info()[1]
+    if world > 1 and o.marker_ownership == "slab" and o.slab_local:
+        if ctx.slab is None:
+            b = migrate.slab_bounds(nx[IZ] - 1, world)
+            r = ctx.comm_info()[0]
+            ctx.set_slab(b[r], b[r + 1] + (1 if r == world - 1 else 0), SLAB_HALO)
+    elif ctx.slab is not None:
+        ctx.set_slab(0, 0)
+    rows = slab_rows(s)
+    own = (lambda f: f[rows[0]:rows[1]]) if rows is not None else (lambda f: f)
+    if rows is not None:
+        pass        # plb_trac2grid / plb_trac2grid_fused combine the slabs' boundary rows themselves
+    elif o.slab_reduce and o.marker_ownership == "slab" and ctx.comm_info()[1] > 1:
         slab_bounds = migrate.slab_bounds(nx[IZ] - 1, ctx.comm_info()[1])
 
         def t2g(ctx_, x_, cols_, schemes_, grid_, out_, mm_):
@@ -190,7 +236,7 @@ def timestep(s, o, want_kelem=True, phases=False):
         s.f_T[:, 0], s.f_T[:, -1] = s.newtemp[:, 0], s.newtemp[:, -1]
         s.f_T[0, :], s.f_T[-1, :] = s.newtemp[0, :], s.newtemp[-1, :]
     if o.do_heatdiff:                                                               # :339-343
-        diffusivity = markers.max_diffusivity2(s.f_k[IZ], s.f_rho, s.f_Cp)
+        diffusivity = _gmax(s, markers.max_diffusivity2(own(s.f_k[IZ]), own(s.f_rho), own(s.f_Cp)))
         tstep_temp = _clamp(o.tstep_modifier * min(s.dx) ** 2 / diffusivity, o.tstep_dif_min,
                             o.tstep_dif_max)
     ph.mark("dt_heat")
@@ -211,7 +257,7 @@ def timestep(s, o, want_kelem=True, phases=False):
     s.stats["stokes_status"], s.stats["stokes_rtol_eff"], s.stats["stokes_floor"] = st["status"], st["rtol_eff"], st["floor"]
     ph.mark("stokes_solve")
     s.newvel, s.newpres = pylamp_stokes.x2vp(x, nx)
-    vmax = max(markers.field_max(s.newvel[IZ]), markers.field_max(s.newvel[IX]))   # :364 (signed)
+    vmax = _gmax(s, max(markers.field_max(own(s.newvel[IZ])), markers.field_max(own(s.newvel[IX]))))   # :364 (signed)
     tstep_stokes = _clamp(o.tstep_modifier * min(s.dx) / vmax, o.tstep_adv_min, o.tstep_adv_max)
     if o.surfstab_tstep > 0:                                                        # :368-372
         tstep_stokes = o.surfstab_tstep
@@ -228,7 +274,7 @@ def timestep(s, o, want_kelem=True, phases=False):
             s.stats["stab_solves"] += 1
             s.stats["stokes_iters"] += s.stokes_op.iterations
             s.newvel, s.newpres = pylamp_stokes.x2vp(x, nx)
-            vmax = max(markers.field_max(s.newvel[IZ]), markers.field_max(s.newvel[IX]))
+            vmax = _gmax(s, max(markers.field_max(own(s.newvel[IZ])), markers.field_max(own(s.newvel[IX]))))
             check = o.tstep_modifier * min(s.dx) / vmax                            # :399 (not clamped)
             if check < tstep:
                 tstep, s.limiter = check, "Ss"
@@ -282,7 +328,6 @@ def timestep(s, o, want_kelem=True, phases=False):
     vzc, vxc = markers.centre_velocities(s.newvel[IZ], s.newvel[IX], o.bcstokes)
     pre = [gridmp[d][0] - (gridmp[d][1] - gridmp[d][0]) for d in range(DIM)]
     newgrid = [np.insert(gridmp[IZ], 0, pre[IZ]), np.insert(gridmp[IX], 0, pre[IX])]
-    world = ctx.comm_info()[1]
     slab = world > 1 and o.marker_ownership == "slab"
     s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep,
                                                 spare=slab)
@@ -312,8 +357,8 @@ def timestep(s, o, want_kelem=True, phases=False):
             b = migrate.slab_bounds(nx[IZ] - 1, world)
             rows = (b[ctx.comm_info()[0]], b[ctx.comm_info()[0] + 1])
         s.stats["injected"] = markers.inject_markers(s, o.tracdens, o.tracdens_min, cell_rows=rows)
-    if world > 1:
-        # per-cell counts of the whole cloud
+    if world > 1 and rows is None:
+        # per-cell counts of the whole cloud (slab-local fields: every rank keeps the counts of its own cells)
         import torch.distributed as dist
         dist.all_reduce(s.count)
     ph.mark("fence_count")

@@ -91,13 +91,15 @@ class DiffusionOperator:
             self._guess = _dev(guess, self.ctx)
             self.ctx.check(self.ctx.lib.plb_diff_set_initial_guess(self.h, self._guess.data_ptr()))
         rd = None if rhs is None else _dev(rhs, self.ctx).reshape(-1)
-        x = torch.empty(self.shape[0], dtype=torch.float64, device=self.ctx.torch_device)
+        # (slab-local fields: the solver writes the own rows and the halo rows only; the rest stays zero)
+        new = torch.zeros if self.ctx.slab is not None else torch.empty
+        x = new(self.shape[0], dtype=torch.float64, device=self.ctx.torch_device)
         it, rr = C.c_int(0), C.c_double(0)
         rc = self.ctx.lib.plb_diff_solve(self.h, None if rd is None else rd.data_ptr(), float(rtol),
                                          int(maxit), x.data_ptr(), C.byref(it), C.byref(rr))
         self.iterations, self.relres = it.value, rr.value
         self.ctx.check(rc)
-        if self.ctx.comm_info()[1] > 1:
+        if self.ctx.comm_info()[1] > 1 and self.ctx.slab is None:
             self.ctx.allreduce(x)       # every slab rank filled its own rows
         return x.cpu().numpy() if host else x
 

@@ -129,7 +129,9 @@ class StokesOperator:
         """x = A^-1 rhs on the GPU; same layout as the reference's spsolve result."""
         host = self.host if rhs is None else not isinstance(rhs, torch.Tensor)
         rd = None if rhs is None else _dev(rhs, self.ctx).reshape(-1)
-        x = torch.empty(self.shape[0], dtype=torch.float64, device=self.ctx.torch_device)
+        # (slab-local fields: the solver writes the own rows and the halo rows only; the rest stays zero)
+        new = torch.zeros if self.ctx.slab is not None else torch.empty
+        x = new(self.shape[0], dtype=torch.float64, device=self.ctx.torch_device)
         it, rr = C.c_int(0), C.c_double(0)
         rc = self.ctx.lib.plb_stokes_solve(self.h, None if rd is None else rd.data_ptr(), float(rtol),
                                            int(maxit), x.data_ptr(), C.byref(it), C.byref(rr))
@@ -141,7 +143,7 @@ class StokesOperator:
             import warnings
             warnings.warn("Stokes solve stopped at relres %.2e > rtol %.1e (fp64 residual floor or stagnation; "
                           "accepted below rtol_accept) -- see StokesOperator.stats" % (rr.value, rtol))
-        if self.ctx.comm_info()[1] > 1:
+        if self.ctx.comm_info()[1] > 1 and self.ctx.slab is None:
             self.ctx.allreduce(x)       # every slab rank filled its own rows: sum the pieces
         return x.cpu().numpy() if host else x
 

@@ -15,6 +15,7 @@ ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ownership = sys.argv[3] if len(sys.argv) > 3 else "index"
 slab_reduce = len(sys.argv) > 4 and sys.argv[4] == "reduce"      # slab only: slabgrid.py instead of the all-reduce
+slab_local = len(sys.argv) > 4 and sys.argv[4] == "local"        # slab only: slab-local grid fields (no full-plane collective)
 host_group = dist.new_group(backend="gloo")          # object gathers of the id-matched comparison
 ctx = _lib.default_context(local)
 ctx.init_comm()
@@ -28,7 +29,7 @@ if ownership == "slab":
 else:
     sel = np.arange((rank * M) // world, ((rank + 1) * M) // world)   # contiguous share of the markers
 sg = driver.State(nx, L, tr_x[sel], tr_f[sel], device=local)
-og = driver.Options(marker_ownership=ownership, slab_reduce=slab_reduce, **opts)
+og = driver.Options(marker_ownership=ownership, slab_reduce=slab_reduce, slab_local=slab_local, **opts)
 if rank == 0:
     so, oo = O.State(nx, L, tr_x.copy(), tr_f.copy()), O.Options(solve=O.solve_refined, **opts)
 ok = True
@@ -41,18 +42,32 @@ for it in range(nsteps):
                        dst=0, group=host_group)
     if ownership == "slab":
         ok = ok and migrate.check_ownership(sg) == 0
+    # slab-local fields: every rank holds its own rows (+ halo rows); put the pieces together for the comparison
+    F = {k: driver.full_field(sg, f) for k, f in (("vz", sg.newvel[0]), ("vx", sg.newvel[1]), ("P", sg.newpres),
+                                                  ("T", sg.newtemp), ("rho", sg.f_rho))}
+    count = sg.count.clone()
+    if slab_local:
+        dist.all_reduce(count)
+        # the halo rows must hold the neighbours' values: compare them with the assembled fields
+        i0, i1, h = sg.ctx.slab
+        lo, hi = max(i0 - h, 0), min(i1 + h, nx[0])
+        for k, f in (("vz", sg.newvel[0]), ("T", sg.newtemp), ("rho", sg.f_rho), ("etas", sg.f_etas)):
+            ref = F[k] if k in F else driver.full_field(sg, f)
+            if not torch.equal(f[lo:hi], ref[lo:hi]):
+                print("rank", rank, "halo rows of", k, "differ from the owners' rows", flush=True)
+                ok = False
     if rank == 0:
         O.timestep(so, oo)
         all_ids = np.concatenate([m[0] for m in mine])
         ok = ok and np.array_equal(np.sort(all_ids), np.arange(M))          # nobody lost, nobody duplicated
         gx, gT = np.concatenate([m[1] for m in mine]), np.concatenate([m[2] for m in mine])
         rel = lambda a, b: float(np.linalg.norm(a.cpu().numpy() - b) / np.linalg.norm(b))
-        e = {"vz": rel(sg.newvel[0], so.newvel[0]), "vx": rel(sg.newvel[1], so.newvel[1]),
-             "P": rel(sg.newpres, so.newpres), "T": rel(sg.newtemp, so.newtemp), "rho": rel(sg.f_rho, so.f_rho),
+        e = {"vz": rel(F["vz"], so.newvel[0]), "vx": rel(F["vx"], so.newvel[1]),
+             "P": rel(F["P"], so.newpres), "T": rel(F["T"], so.newtemp), "rho": rel(F["rho"], so.f_rho),
              "x": float(np.linalg.norm(gx - so.tr_x[all_ids]) / np.linalg.norm(so.tr_x)),
              "Tm": float(np.linalg.norm(gT - so.tr_f[all_ids, O.TR_TMP]) / np.linalg.norm(so.tr_f[:, O.TR_TMP])),
-             "count": int(np.abs(sg.count.cpu().numpy() - so.count).max())}
-        print("step", it + 1, "world", world, ownership, sg.stats, {k: ("%.1e" % v if k != "count" else v) for k, v in e.items()}, flush=True)
+             "count": int(np.abs(count.cpu().numpy() - so.count).max())}
+        print("step", it + 1, "world", world, ownership, "local" if slab_local else ("reduce" if slab_reduce else ""), sg.stats, {k: ("%.1e" % v if k != "count" else v) for k, v in e.items()}, flush=True)
         ok = ok and all(e[k] < 1e-8 for k in ("vz", "vx", "P", "T")) and e["x"] < 1e-10 and e["rho"] < 1e-10
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)        # rank 0 holds the parity verdict, every rank its ownership check

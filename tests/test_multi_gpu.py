@@ -14,16 +14,16 @@ from conftest import ROOT
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,port", [("index", 29533), ("slab", 29535), ("slab reduce", 29537)])
+@pytest.mark.parametrize("mode,port", [("index", 29533), ("slab", 29535), ("slab reduce", 29537), ("slab local", 29539)])
 def test_two_gpu_timestep_matches_oracle(mode, port):
-    """index: every rank keeps its markers (verified on 2 B200s in round 1).  slab / slab reduce: slab-owned
-    markers with migration, node sums by all-reduce / by boundary-row exchange + all-gather -- written after
-    round 1's GPU budget was spent, opt-in (PLB_RUN_UNVERIFIED=1) until they have passed once on GPUs."""
+    """index: every rank keeps its markers, fields replicated, raw node sums all-reduced.  slab / slab reduce:
+    slab-owned markers with migration, node sums by all-reduce / by boundary-row exchange + all-gather.
+    slab local (bench.py's multi-GPU default): slab-owned markers AND slab-local grid fields -- boundary-row
+    accumulate, halo rows, all-reduced scalars; no full-plane collective in the step.  The first three ran
+    green on 2 B200s in round 2 (profiles/r02_multi_gpu.log)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if mode != "index" and os.environ.get("PLB_RUN_UNVERIFIED") != "1":
-        pytest.skip("not yet verified on GPUs (set PLB_RUN_UNVERIFIED=1)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "scripts", "multi_gpu_driver_check.py"), "64", "3"] + mode.split()

@@ -87,3 +87,31 @@ def test_solcx_at_size(name):
     A.set_param("coarsen_wide", 0)
     x = A.solve(None, maxit=600)
     _check(name, _errors(x, nx, g), g, A)
+
+
+def test_solcx_converges_to_the_analytic_solution():
+    """BASELINE.json configs[1]: "Stokes solve only vs analytic and vs spsolve" at 256^2-1024^2 cells.  The GPU
+    solution of the reference's discrete system against the analytic SolCx-type solution (pylamp_b200/solcx.py;
+    pinned on the CPU against the oracle's direct solve in tests/test_solcx_cpu.py): the reference's scheme puts
+    the viscosity jump on a node line (the node takes the stiff value), so it converges at first order; the
+    errors must halve with the spacing and equal what the reference's own direct solve gives (the fixtures)."""
+    import torch
+    from pylamp_b200 import pylamp_stokes as S, setups, solcx
+    dev = torch.device("cuda")
+    errs = {}
+    for n in (257, 513, 1025):
+        nx, L, grid, gridmp, es, en, rho = setups.solcx_fields(n)
+        A = S.StokesOperator(nx, grid, *[torch.as_tensor(a).to(dev) for a in (es, en, rho)], [1, 1, 1, 1])
+        A.warn_unconverged = False
+        A.set_param("coarsen_wide", 0)
+        x = A.solve(None, maxit=600)
+        vel, p = S.x2vp(x, nx)
+        errs[n] = solcx.errors(nx, grid, gridmp, vel[0].cpu().numpy(), vel[1].cpu().numpy(), p.cpu().numpy(), A.scaling[0])
+        print("SolCx %d^2 nodes: iters %d, relative L2 error vs analytic (vz, vx, p) %s" %
+              (n, A.iterations, ["%.3e" % e for e in errs[n]]))
+        A.close()
+    for a, b in ((257, 513), (513, 1025)):
+        order = [float(np.log2(ea / eb)) for ea, eb in zip(errs[a], errs[b])]
+        print("order %d -> %d:" % (a, b), ["%.2f" % o for o in order])
+        assert all(0.9 < o < 1.2 for o in order), order
+    assert max(errs[1025]) < 8e-3
