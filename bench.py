@@ -27,9 +27,14 @@ sys.path.insert(0, ROOT)
 
 CLASS_NAMES = {0: "k_cheb (Chebyshev-Jacobi smoother sweep, finest level)",
                1: "k_stokes_op (coupled Stokes residual/apply)", 2: "k_multi_dot", 3: "k_multi_axpy2",
-               4: "k_t2g_chunk (trac2grid scatter)", 5: "k_rk4", 6: "k_grid2trac",
+               4: "k_t2g_fused + k_t2g_chunk (marker->grid sums: the step's 4-target pass + the subgrid call)", 5: "k_rk4", 6: "k_grid2trac",
                7: "coarse part of the V-cycle (levels >= 1, many launches)",
-               8: "finest-level residual+restrict+prolong", 9: "k_precond_rhs", 10: "k_diff", 11: "marker misc"}
+               8: "finest-level residual+restrict+prolong", 9: "k_precond_rhs", 10: "k_diff", 11: "marker misc",
+               12: "k_permute (marker-by-cell sort, when due)"}
+
+
+def class_name(k):
+    return CLASS_NAMES.get(k, "kernel class %d" % k)
 SINGLE_KERNEL_CLASSES = (0, 1, 2, 3, 4, 5, 6, 9)
 
 
@@ -232,9 +237,11 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e["ms"] = float(t.item())
 
+    if world > 1:
+        # nothing collective happens after this point: the other ranks must not wait for rank 0's report
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     peak, peak_src = peaks()
     single = {k: v for k, v in prof.items() if k in SINGLE_KERNEL_CLASSES}
@@ -251,7 +258,7 @@ def run_b200(args):
                 traffic = tr[key]["dram_bytes_per_launch"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": CLASS_NAMES[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": class_name(dom), "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "launches_timed": c, "avg_launch_ms": ms / c,
                     "algorithmic_bytes_per_launch": by / c, "peak_source": peak_src,
                     "share_of_step": ms / (ms_step * args.steps)}
@@ -260,9 +267,9 @@ def run_b200(args):
     if 0 in prof and prof[0][1] > 0:
         c, ms, by = prof[0]
         ach = by / (ms * 1e-3) / 1e9
-        roofline_stencil = {"bound": "hbm", "kernel": CLASS_NAMES[0], "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline_stencil = {"bound": "hbm", "kernel": class_name(0), "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "avg_launch_ms": ms / c, "share_of_step": ms / (ms_step * args.steps)}
-    breakdown = {CLASS_NAMES[k]: {"launch_groups": v[0], "ms_per_step": v[1] / args.steps,
+    breakdown = {class_name(k): {"launch_groups": v[0], "ms_per_step": v[1] / args.steps,
                                   "GBps": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 and v[2] > 0 else None}
                  for k, v in sorted(prof.items())}
     value = 1.0 / (ms_step * 1e-3)            # ONE global problem on all ranks (strong scaling)
@@ -304,8 +311,6 @@ def run_b200(args):
                                 "stokes_dof_per_s": 3.0 * cnx[0] * cnx[1] / sec,
                                 "phases_s": {k: v / 2 for k, v in timers.items()}}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def run_e2e(torch, driver, s, o, nsteps):

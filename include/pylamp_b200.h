@@ -91,6 +91,18 @@ int plb_allreduce(plb_ctx* ctx, double* d_buf, long long count, int op);
  * i1 <= i0 switches back to replicated fields.  plb_halo_rows: exchange `h` halo rows of narr full-size arrays
  * (h_row_doubles[a] doubles per row) with both z-neighbours, one NCCL group. */
 int plb_ctx_set_slab(plb_ctx* ctx, int i0, int i1, int halo);
+/* Marker migration between z-slabs after advection (north_star; replaces pylamp2.py:550-555's Allreduce of all
+ * positions): rank r owns the markers whose cell row floor((nz-1)*z/Lz) (pylamp2.py:588) lies in [c0, c1).
+ * plb_migrate_plan lists the leavers (one pass over the coordinates), swaps the counts with the two neighbours
+ * and returns h_counts[4] = {leavers down, leavers up, arrivals from below, arrivals from above}; a marker that
+ * moved beyond the neighbouring slab is an error (CFL 0.67 allows 0.45 cells per step).  plb_migrate_apply packs
+ * the leavers' rows of all arrays (coordinates first; rows of 1 or 2 doubles; capacity_rows rows allocated, M in
+ * use), exchanges them with one grouped ncclSend/ncclRecv pair per neighbour, writes the arrivals into the
+ * leavers' slots (surplus arrivals appended, surplus holes filled from the tail) and returns the new row count. */
+int plb_migrate_plan(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, double Lz, int c0, int c1,
+                     long long* h_counts);
+int plb_migrate_apply(plb_ctx* ctx, long long M, int narr, double* const* h_arrs, const int* h_width,
+                      long long capacity_rows, int nz, double Lz, int c0, int c1, long long* h_M_new);
 int plb_halo_rows(plb_ctx* ctx, int narr, double* const* h_ptrs, const long long* h_row_doubles, int i0, int i1, int h);
 void plb_comm_destroy(plb_ctx* ctx);
 
@@ -176,6 +188,13 @@ int plb_rk4(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_vz_
             const double* d_vx_c, const double* d_gc_z, int nzc, const double* d_gc_x, int nxc,
             int ld, double z0, double zlen, double x0, double xlen, double dt, double* d_x_out,
             double* d_v_out);
+/* plb_rk4 followed by plb_fence_count on the new positions in one pass over the markers (the positions are
+ * final after the RK update: pylamp2.py:550, then the fence :558-572 and the per-cell count :588-593).
+ * d_v_out holds (x_new - x_old)/dt of the UNfenced positions like the reference's trac_vel (pylamp_trac.py:386). */
+int plb_rk4_fence_count(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_vz_c, const double* d_vx_c,
+                        const double* d_gc_z, int nzc, const double* d_gc_x, int nxc, int ld, double z0, double zlen,
+                        double x0, double xlen, double dt, double* d_x_out, double* d_v_out, double Lz, double Lx,
+                        double eps, int nz, int nxx, long long* d_kelem, long long* d_count);
 
 /* ---- driver-inline marker steps of pylamp2.py ------------------------------------------ */
 /* fence, pylamp2.py:558-572 (fence enabled, no FLOWTHRU/CYCLIC): x<=0 -> eps, x>=L -> L-eps */

@@ -352,12 +352,19 @@ def makeStokesMatrix(nx, grid, f_etas, f_etan, f_rho, bc, surfstab=False, tstep=
             else:
                 T.add(g(i, nxx - 2, IZ), g(i, nxx - 2, IZ), Kc)
                 T.add(g(i, nxx - 2, IZ), g(i, nxx - 3, IZ), -Kc)
-        elif b & BC_TYPE_CYCLIC or b & BC_TYPE_FLOWTHRU:
-            raise NotImplementedError("CYCLIC/FLOWTHRU walls: SURVEY.md §8f-4 (next)")
+        elif b & BC_TYPE_CYCLIC:
+            raise NotImplementedError("CYCLIC walls: the reference's own matrix is singular (tests/test_reference_bc_probe.py)")
+        elif b & BC_TYPE_FLOWTHRU:
+            raise NotImplementedError("FLOWTHRU without FREESLIP leaves the vz wall rows empty in the reference (singular)")
         # (b == NOSLIP: the reference writes nothing here -> singular system, quirk 4)
-        i = np.arange(0, nz - 1)                        # vx = 0, :277-281, :322-326
+        i = np.arange(0, nz - 1)
         jw = 0 if wall == 0 else nxx - 1
-        T.add(g(i, jw, IX), g(i, jw, IX), Kc)
+        if b & BC_TYPE_FLOWTHRU:                        # dvx/dx = 0, :268-273, :314-319
+            jn, sgn = (1, -1.0) if wall == 0 else (nxx - 2, 1.0)
+            T.add(g(i, jw, IX), g(i, jw, IX), sgn * Kc)
+            T.add(g(i, jw, IX), g(i, jn, IX), -sgn * Kc)
+        else:                                           # vx = 0, :277-281, :322-326
+            T.add(g(i, jw, IX), g(i, jw, IX), Kc)
 
     # continuity: boundary cells without corners (:333-354) and interior (:496-518)
     ci, cj = np.meshgrid(np.arange(0, nz - 1), np.arange(0, nxx - 1), indexing="ij")
@@ -431,8 +438,15 @@ def makeStokesMatrix(nx, grid, f_etas, f_etan, f_rho, bc, surfstab=False, tstep=
     T.add(rows, g(i, j - 1, IP), 2 * Kc / dxc)
     rhs[rows] = -0.5 * (f_rho[i, j] + f_rho[i + 1, j]) * G[IX]
 
-    # pressure anchor, :525-551 (all-Dirichlet case only; FLOWTHRU is "next")
+    # pressure anchor, :525-551: cell (3,2), or mid-height on a flow-through x-wall (the last such wall in the
+    # reference's loop order wins; for the x = L wall that is the GHOST pressure column -- no real anchor)
+    if bz0 & BC_TYPE_FLOWTHRU or bz1 & BC_TYPE_FLOWTHRU:
+        raise Exception("flow bnd condition in IZ dir no implemented")       # :546
     anchor = g(3, 2, IP)
+    if bx1 & BC_TYPE_FLOWTHRU:
+        anchor = g(int(nz / 2), nxx - 1, IP)
+    elif bx0 & BC_TYPE_FLOWTHRU:
+        anchor = g(int(nz / 2), 0, IP)
     A = T.tocsr(dof, drop_rows=[anchor])
     A = A + scipy.sparse.csr_matrix(([Kc], ([anchor], [anchor])), shape=(dof, dof))
     return A.tocsr(), rhs

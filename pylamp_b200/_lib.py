@@ -35,6 +35,8 @@ _PROTOS = {
     "plb_allreduce": (I, [VP, VP, LL, I]),
     "plb_comm_destroy": (None, [VP]),
     "plb_ctx_set_slab": (I, [VP, I, I, I]),
+    "plb_migrate_plan": (I, [VP, LL, VP, I, D, I, I, C.POINTER(LL)]),
+    "plb_migrate_apply": (I, [VP, LL, I, PP, IP, LL, I, D, I, I, C.POINTER(LL)]),
     "plb_halo_rows": (I, [VP, I, PP, C.POINTER(LL), I, I, I]),
     "plb_marker_minmax": (I, [VP, LL, VP, DP]),
     "plb_sort_plan": (I, [VP, LL, VP, I, I, D, D, VP, VP]),
@@ -45,6 +47,7 @@ _PROTOS = {
     "plb_grid2trac": (I, [VP, LL, VP, I, I, PP, VP, I, VP, I, I, D, D, D, D, D, PP,
                           C.POINTER(LL)]),
     "plb_rk4": (I, [VP, LL, VP, VP, VP, VP, I, VP, I, I, D, D, D, D, D, VP, VP]),
+    "plb_rk4_fence_count": (I, [VP, LL, VP, VP, VP, VP, I, VP, I, I, D, D, D, D, D, VP, VP, D, D, D, I, I, VP, VP]),
     "plb_fence": (I, [VP, LL, VP, D, D, D]),
     "plb_cell_index_count": (I, [VP, LL, VP, I, I, D, D, VP, VP]),
     "plb_fence_count": (I, [VP, LL, VP, D, D, D, I, I, VP, VP]),

@@ -122,6 +122,20 @@ int plb_comm_halo_rows(plb_ctx* ctx, int narr, double* const* arrs, const long l
     return 0;
 }
 
+int plb_comm_neighbour_exchange(plb_ctx* ctx, const double* send_dn, size_t n_send_dn, double* recv_dn, size_t n_recv_dn,
+                                const double* send_up, size_t n_send_up, double* recv_up, size_t n_recv_up) {
+    plb_comm* c = ctx->comm;
+    if (!c || c->size == 1) return 0;
+    const bool has_dn = c->rank > 0, has_up = c->rank < c->size - 1;
+    PLB_NCCL(ctx, api.GroupStart());
+    if (has_dn && n_send_dn) PLB_NCCL(ctx, api.Send(send_dn, n_send_dn, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+    if (has_dn && n_recv_dn) PLB_NCCL(ctx, api.Recv(recv_dn, n_recv_dn, NCCL_DOUBLE, c->rank - 1, c->comm, ctx->stream));
+    if (has_up && n_send_up) PLB_NCCL(ctx, api.Send(send_up, n_send_up, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+    if (has_up && n_recv_up) PLB_NCCL(ctx, api.Recv(recv_up, n_recv_up, NCCL_DOUBLE, c->rank + 1, c->comm, ctx->stream));
+    PLB_NCCL(ctx, api.GroupEnd());
+    return 0;
+}
+
 namespace {
 __global__ void __launch_bounds__(256) k_add_rows(long long n, const double* __restrict__ src, double* __restrict__ dst) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)

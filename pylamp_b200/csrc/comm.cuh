@@ -22,3 +22,7 @@ int plb_comm_halo_rows(plb_ctx* ctx, int narr, double* const* arrs, const long l
 // rows and theirs to mine.  `scratch`: 2*h*sum(row_doubles) doubles of device memory.
 int plb_comm_accumulate_rows(plb_ctx* ctx, int narr, double* const* arrs, const long long* row_doubles,
                              const int* i0, const int* i1, const int* nrows, int h, double* scratch);
+// Exchange with the two z-neighbours in one NCCL group: send_dn -> rank-1, recv_dn <- rank-1, send_up -> rank+1,
+// recv_up <- rank+1 (counts in doubles; a count of 0 skips that transfer -- the peer's matching count is 0 too).
+int plb_comm_neighbour_exchange(plb_ctx* ctx, const double* send_dn, size_t n_send_dn, double* recv_dn, size_t n_recv_dn,
+                                const double* send_up, size_t n_send_up, double* recv_up, size_t n_recv_up);

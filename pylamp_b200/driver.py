@@ -73,6 +73,9 @@ class Options:
         # coarsen / solve / return their own rows, reductions are all-reduced scalars.  No full-plane collective
         # is left in the step.  Takes precedence over `slab_reduce`.
         self.slab_local = True
+        # migration by the library's kernels + ncclSend/ncclRecv to the two neighbours (csrc/migrate.cu) instead of
+        # the torch.distributed all-to-all of migrate.migrate (kept for the CPU/gloo tests of the host logic)
+        self.native_migration = True
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -329,20 +332,28 @@ def timestep(s, o, want_kelem=True, phases=False):
     pre = [gridmp[d][0] - (gridmp[d][1] - gridmp[d][0]) for d in range(DIM)]
     newgrid = [np.insert(gridmp[IZ], 0, pre[IZ]), np.insert(gridmp[IX], 0, pre[IX])]
     slab = world > 1 and o.marker_ownership == "slab"
-    s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep,
-                                                spare=slab)
+    need_kelem = want_kelem or o.tracdens_min > 0
+    fused_fence = o.tracs_fence_enabled and not slab
+    if fused_fence:
+        # RK4, fence and per-cell count in one pass over the markers (the new positions are final there)
+        s.trac_vel, s.tr_x, s.kelem, s.count = pylamp_trac.rk4_fence_count_device(
+            ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep, nx, s.L, EPS, want_kelem=need_kelem)
+    else:
+        s.trac_vel, s.tr_x = pylamp_trac.rk4_device(ctx, tr_x, newgrid, vzc, vxc, [nx[IZ] + 1, nx[IX] + 1], tstep,
+                                                    spare=slab)
     ph.mark("advect_rk4")
     # fence (or removal of the markers that left the box) + per-cell count, pylamp2.py:558-593
-    need_kelem = want_kelem or o.tracdens_min > 0
-    if not o.tracs_fence_enabled:
+    if fused_fence:
+        pass
+    elif not o.tracs_fence_enabled:
         s.stats["removed"] = markers.delete_outside(s)                              # :563-581
         if slab:
-            s.stats["migrated"] = migrate.migrate(s)
+            s.stats["migrated"] = (migrate.migrate_native if o.native_migration else migrate.migrate)(s)
         s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=need_kelem)
     elif slab:
         markers.fence(s.tr_x, s.L, EPS)
         # markers that crossed a slab boundary move to their new owner (positions are final here)
-        s.stats["migrated"] = migrate.migrate(s)
+        s.stats["migrated"] = (migrate.migrate_native if o.native_migration else migrate.migrate)(s)
         ph.mark("migrate")
         s.kelem, s.count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=need_kelem)
     else:
@@ -351,12 +362,12 @@ def timestep(s, o, want_kelem=True, phases=False):
         if world > 1 and not slab:
             raise NotImplementedError("marker injection needs marker_ownership='slab' on several ranks "
                                       "(a cell's markers must live on one rank)")
-        rows = None
+        cell_rows = None
         if slab:
             # a slab owns every marker of its cell rows: the local counts of those rows are complete
             b = migrate.slab_bounds(nx[IZ] - 1, world)
-            rows = (b[ctx.comm_info()[0]], b[ctx.comm_info()[0] + 1])
-        s.stats["injected"] = markers.inject_markers(s, o.tracdens, o.tracdens_min, cell_rows=rows)
+            cell_rows = (b[ctx.comm_info()[0]], b[ctx.comm_info()[0] + 1])
+        s.stats["injected"] = markers.inject_markers(s, o.tracdens, o.tracdens_min, cell_rows=cell_rows)
     if world > 1 and rows is None:
         # per-cell counts of the whole cloud (slab-local fields: every rank keeps the counts of its own cells)
         import torch.distributed as dist

@@ -157,6 +157,43 @@ def migrate(s, group=None, bounds=None):
     return {"sent": n_leave, "received": n_arr, "markers": M_new}
 
 
+def migrate_native(s, bounds=None):
+    """`migrate` on CUDA state with the library's kernels (csrc/migrate.cu: plb_migrate_plan + plb_migrate_apply):
+    the leavers are listed and packed by kernels and travel to the slab below / above with one grouped
+    ncclSend/ncclRecv pair per neighbour; arrivals fill the leavers' slots.  Same result as `migrate` up to the
+    order of the markers.  Returns {"sent": n, "received": n, "markers": M_new}."""
+    import ctypes as C
+    from . import _lib
+    ctx = s.ctx
+    rank, world = ctx.comm_info()
+    if bounds is None:
+        bounds = slab_bounds(s.nx[0] - 1, world)
+    M = int(s.tr_x.shape[0])
+    counts = (C.c_longlong * 4)()
+    ctx.call("plb_migrate_plan", M, s.tr_x.data_ptr(), int(s.nx[0]), float(s.L[0]), int(bounds[rank]),
+             int(bounds[rank + 1]), counts)
+    n_leave, n_arr = counts[0] + counts[1], counts[2] + counts[3]
+    uniq, where = _distinct(s.cols)
+    vel = getattr(s, "trac_vel", None)
+    if vel is not None and vel.shape[0] != M:
+        vel = None
+    arrays = [s.tr_x] + uniq + ([vel] if vel is not None else [])
+    need = max(M, M - n_leave + n_arr, M + max(0, n_arr - n_leave))
+    arrays = [resize_rows(t.contiguous() if not t.is_contiguous() else t, need) for t in arrays]   # capacity; keeps the data
+    widths = [1 if t.dim() == 1 else int(t.shape[1]) for t in arrays]
+    M_new = C.c_longlong(0)
+    ctx.call("plb_migrate_apply", M, len(arrays), _lib.ptr_array(arrays), _lib.int_array(widths), need, int(s.nx[0]),
+             float(s.L[0]), int(bounds[rank]), int(bounds[rank + 1]), C.byref(M_new))
+    n = int(M_new.value)
+    arrays = [t[:n] for t in arrays]
+    s.tr_x = arrays[0]
+    new_uniq = arrays[1:1 + len(uniq)]
+    s.cols = [new_uniq[w] for w in where]
+    if vel is not None:
+        s.trac_vel = arrays[-1]
+    return {"sent": int(n_leave), "received": int(n_arr), "markers": n}
+
+
 def check_ownership(s, group=None, bounds=None):
     """Number of local markers that lie outside this rank's slab (0 after `migrate`)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)

@@ -274,6 +274,23 @@ def rk4_device(ctx, tr_x_d, grids, vz_d, vx_d, nx1, tstep, want_vel=True, spare=
     return v_out, x_out
 
 
+def rk4_fence_count_device(ctx, tr_x_d, grids, vz_d, vx_d, nx1, tstep, nx, L, eps, want_kelem=True):
+    """`rk4_device` + fence + cell index + per-cell count of the new positions in one pass over the markers
+    (plb_rk4_fence_count; pylamp2.py:550, :558-572, :588-593).  Returns (trac_vel, tr_x_new, kelem, count)."""
+    gz, gx = _axis_np(grids[IZ]), _axis_np(grids[IX])
+    gz_d, gx_d = _to_dev(gz, ctx), _to_dev(gx, ctx)
+    M = tr_x_d.shape[0]
+    x_out, v_out = torch.empty_like(tr_x_d), torch.empty_like(tr_x_d)
+    nz, nxx = int(nx[IZ]), int(nx[IX])
+    kelem = torch.empty(M, dtype=torch.int64, device=tr_x_d.device) if want_kelem else None
+    count = torch.empty((nz - 1) * (nxx - 1), dtype=torch.int64, device=tr_x_d.device)
+    ctx.call("plb_rk4_fence_count", M, tr_x_d.data_ptr(), vz_d.data_ptr(), vx_d.data_ptr(), gz_d.data_ptr(),
+             int(nx1[IZ]), gx_d.data_ptr(), int(nx1[IX]), int(vz_d.shape[1]), float(gz[0]), float(gz[-1] - gz[0]),
+             float(gx[0]), float(gx[-1] - gx[0]), float(tstep), x_out.data_ptr(), v_out.data_ptr(), float(L[IZ]),
+             float(L[IX]), float(eps), nz, nxx, kelem.data_ptr() if want_kelem else None, count.data_ptr())
+    return v_out, x_out, kelem, count
+
+
 def RK(tr_x, grids, vels, nx, tstep, order=4):
     """Runge-Kutta marker advection with Meyer-Jenny velocity interpolation; returns
     (trac_vel, tr_x_final) as new arrays.  Reference: pylamp_trac.py:321-388 (the reference's

@@ -33,3 +33,16 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_other_ranks_silent():
     assert _run({"RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_every_profiled_kernel_class_has_a_name():
+    """bench.py names the kernel classes of csrc/common.cuh (PLB_K_*) in its breakdown; a class without a name
+    once made rank 0 raise after the timed region while the other ranks waited (round 2)."""
+    import re
+    import bench
+    src = open(os.path.join(ROOT, "pylamp_b200", "csrc", "common.cuh")).read()
+    ids = [int(v) for v in re.findall(r"PLB_K_[A-Z0-9_]+ = (\d+),", src) if int(v) < 16]
+    assert len(ids) >= 12
+    for k in ids:
+        assert k in bench.CLASS_NAMES, k
+    assert bench.class_name(15).startswith("kernel class")

@@ -103,11 +103,14 @@ def test_convection_small():
 
 
 def test_convection_257_bench_solver_settings():
-    """Larger grid (256^2 cells, 1.0e6 markers) with exactly bench.py's solver settings -- FGMRES(30),
-    V(2,2), extrapolated warm start, eigenvalue estimates reused, heat rtol 1e-11: every step within
-    1e-8 of the oracle's direct solve, positions within 1e-10."""
-    sg, so, errs = _run_both(setups.convection(ncell=256), 3, tol_fields=1e-8, heat_rtol=1e-11,
-                             stokes_params={"warm_start": 2, "gcr_m": 30, "nu": 2, "lmax_every": 8})
+    """Larger grid (256^2 cells, 1.0e6 markers) with bench.py's solver settings, imported from bench.py itself
+    (bench.DEFAULTS / bench.stokes_params: FGMRES(30), V(2,2), warm start extrapolated over 5 iterates, eigenvalue
+    estimates reused for 8 steps, Stokes rtol 1e-9, heat rtol 1e-11), 8 steps so that the warm-start
+    history fills: every step within 1e-8 of the oracle's direct solve, positions within 1e-10.  (Solver parity at
+    513^2 / 1025^2 with the same settings: tests/test_stokes_large_gpu.py.)"""
+    import bench
+    sg, so, errs = _run_both(setups.convection(ncell=256), 8, tol_fields=1e-8, heat_rtol=bench.DEFAULTS["heat_rtol"],
+                             stokes_rtol=bench.DEFAULTS["stokes_rtol"], stokes_params=bench.stokes_params())
     for e in errs:
         assert e["x"] <= 1e-10 and e["Tm"] <= 1e-10
 

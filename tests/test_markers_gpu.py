@@ -170,6 +170,61 @@ def test_large_random_cloud_vs_oracle(T):
     assert _rel(vg, vr) < 1e-9
 
 
+@pytest.mark.parametrize("cloud", ["sorted", "random", "faces"])
+def test_rk4_tile_kernel_and_fused_fence_count(T, cloud):
+    """RK4 on staged velocity tiles (rk4_variant 1, default) and the one-marker-per-thread kernel (0) against the
+    oracle's RK -- cell-ordered cloud (tiles), unordered cloud (bounding box too large: global reads), markers on and
+    within a few ulps of cell faces of the centre grid (the exact cell lookup decides) and a time step twice the
+    CFL one (stage positions leave the tile, some leave the grid) -- and plb_rk4_fence_count against the oracle's
+    RK + fence + cell_index_count, bit for bit in the indices."""
+    from pylamp_b200 import _lib, setups
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(31)
+    ncz, ncx, L = 40, 56, [1.0, 1.4]
+    nx = [ncz + 1, ncx + 1]
+    grid, mesh, gridmp, meshmp = O.make_grids(nx, L)
+    if cloud == "random":
+        x = rng.random((50000, 2)) * L
+    else:
+        x = setups.lattice_markers(ncz, ncx, L, 4, seed=8)[0]
+        if cloud == "faces":
+            m = x.shape[0] // 3
+            x[:m, 0] = np.round(x[:m, 0] * ncz / L[0] - 0.5) * L[0] / ncz + 0.5 * L[0] / ncz    # on centre-grid faces
+            x[:m:2, 0] = np.nextafter(x[:m:2, 0], 0)
+            x[m:2 * m, 1] = np.nextafter(np.round(x[m:2 * m, 1] * ncx / L[1]) * L[1] / ncx, 10)
+            x = np.clip(x, 1e-6, np.array(L) - 1e-6)
+    z, xx = np.meshgrid(grid[0], grid[1], indexing="ij")
+    newvel = [np.sin(np.pi * z / L[0]) * np.cos(np.pi * xx / L[1]) + 0.05 * rng.normal(size=nx),
+              -np.cos(np.pi * z / L[0]) * np.sin(np.pi * xx / L[1]) + 0.05 * rng.normal(size=nx)]
+    ng, vels = O.centre_velocities(newvel, gridmp, nx, [1, 1, 1, 1])
+    for cfl in (0.67, 1.5):
+        dt = cfl * (L[0] / ncz) / max(np.abs(newvel[0]).max(), np.abs(newvel[1]).max())
+        vr, xr = O.RK(x, ng, vels, nx, dt)
+        for variant in (1, 0):
+            ctx.set_param("rk4_variant", variant)
+            try:
+                vg, xg = T.RK(x, ng, vels, nx, dt)
+            finally:
+                ctx.set_param("rk4_variant", 1)
+            assert np.allclose(xg, xr, rtol=1e-12, atol=1e-15), (cloud, cfl, variant, np.abs(xg - xr).max())
+            assert np.allclose(vg, vr, rtol=1e-9, atol=1e-12 * np.abs(vr).max())
+        # fused RK4 + fence + count
+        xd = torch.as_tensor(x).cuda()
+        v, xn, kelem, count = T.rk4_fence_count_device(ctx, xd, ng, torch.as_tensor(vels[0]).cuda(), torch.as_tensor(vels[1]).cuda(),
+                                                       [nx[0] + 1, nx[1] + 1], dt, nx, L, 2.0 ** -10)
+        xf = xr.copy()
+        O.fence(xf, np.zeros((xf.shape[0], O.NFTRAC)), L, [1, 1, 1, 1])
+        kr, cr = O.cell_index_count(xf, nx, L)
+        assert np.allclose(xn.cpu().numpy(), xf, rtol=1e-12, atol=1e-15)
+        assert np.allclose(v.cpu().numpy(), vr, rtol=1e-9, atol=1e-12 * np.abs(vr).max())
+        same = kelem.cpu().numpy() == kr
+        assert same.mean() > 0.9999          # (a position that differs in the last bit may sit on the other side of a face)
+        if same.all():
+            assert np.array_equal(count.cpu().numpy(), cr)
+        kg, cg = O.cell_index_count(xn.cpu().numpy(), nx, L)       # ... but the indices of the positions returned are exact
+        assert np.array_equal(kelem.cpu().numpy(), kg) and np.array_equal(count.cpu().numpy(), cg)
+
+
 def test_sort_by_cell_keeps_results(T):
     """A shuffled cloud and its cell-sorted version give the same grids (order-independent sums)."""
     from pylamp_b200 import markers

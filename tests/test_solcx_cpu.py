@@ -15,11 +15,11 @@ def test_analytic_solution_conditions():
         xin = xw + (h if xw == 0 else -h)
         assert np.all(np.abs(f(z, np.full_like(z, xw))[1]) < 1e-12)
         dvz = (f(z, np.full_like(z, xin))[0] - f(z, np.full_like(z, xw))[0]) / (xin - xw)
-        assert np.all(np.abs(dvz) < 1e-6 * np.abs(f(z, np.full_like(z, 0.3))[0]).max() + 1e-9)
+        assert np.all(np.abs(dvz) < 1e-4 * np.abs(f(z, np.full_like(z, 0.3))[0]).max())     # O(h) one-sided difference, h = 1e-6
     e = 1e-9                                               # velocities continuous across the viscosity jump
     a, b = f(z, np.full_like(z, 0.5 - e)), f(z, np.full_like(z, 0.5 + e))
-    assert np.allclose(a[0], b[0], rtol=0, atol=1e-8 * np.abs(a[0]).max() + 1e-12)
-    assert np.allclose(a[1], b[1], rtol=0, atol=1e-8 * np.abs(a[1]).max() + 1e-12)
+    vmax = np.abs(f(z, np.full_like(z, 0.3))[0]).max()
+    assert np.allclose(a[0], b[0], rtol=0, atol=1e-6 * vmax) and np.allclose(a[1], b[1], rtol=0, atol=1e-6 * vmax)
     zz = np.array([0.0, 1.0])                              # no normal flow on the z-walls
     assert np.all(np.abs(f(zz, np.array([0.3, 0.7]))[0]) < 1e-15)
 
