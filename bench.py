@@ -275,12 +275,12 @@ def run_b200(args):
     value = 1.0 / (ms_step * 1e-3)            # ONE global problem on all ranks (strong scaling)
     line = {"metric": "timesteps_per_s", "value": value, "unit": "timesteps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C4 thermal convection Ra=1e6, Arrhenius viscosity clipped [1e17,1e23], "
                                    "%d^2 cells, %d markers/cell, Stokes+energy+MIC advection" % (ncell, args.per_side ** 2),
                        "grid_nodes": nx, "markers": M, "stokes_dof": 3 * N,
                        "parallelism": "1 GPU" if world == 1 else
-                       "%d GPUs, one 4096^2 problem in z-slabs: %s" %
+                       "%d GPUs, one problem in z-slabs: %s" %
                        (world, "slab-owned markers that migrate after every step, slab-local grid fields (boundary-row "
                         "accumulate + halo rows over NCCL send/recv, all-reduced scalars; no full-plane collective)"
                         if (args.marker_ownership == "slab" and args.slab_local) else
@@ -369,6 +369,9 @@ def main():
                     help="with --marker-ownership slab --slab-local 0: boundary-row exchange + all-gather instead of the all-reduce")
     ap.add_argument("--resort-every", type=int, default=DEFAULTS["resort_every"],
                     help="re-sort the markers by cell every n-th step (0: never)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="label of the JSON line: 'strong' = the 4096^2 problem on N GPUs (default); 'weak' when --ncell is "
+                         "chosen per N so that the work per GPU stays fixed (SURVEY 8d C5: 4096, 5632, 8192, 11264 cells)")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
     ap.add_argument("--ref-ncell", type=int, default=256, help="--impl reference sample size")
     args = ap.parse_args()

@@ -91,6 +91,22 @@ int plb_allreduce(plb_ctx* ctx, double* d_buf, long long count, int op);
  * i1 <= i0 switches back to replicated fields.  plb_halo_rows: exchange `h` halo rows of narr full-size arrays
  * (h_row_doubles[a] doubles per row) with both z-neighbours, one NCCL group. */
 int plb_ctx_set_slab(plb_ctx* ctx, int i0, int i1, int halo);
+/* Marker injection into under-populated cells, pylamp2.py:594-633 (the reference's Python loop with np.append per
+ * cell).  plb_inject_plan: among the cells [cell0, cell1) (a slab serves its own rows) those with fewer than
+ * tracdens_min markers receive tracdens - count new ones; h_out[3] = {deficient cells, markers to add, sum of
+ * (added - 1) = what these cells advance the marker ids by}.  plb_inject_apply appends the planned markers behind the
+ * M existing ones (d_tr_x and the ncols distinct columns need room for M + added rows): positions uniformly random
+ * inside the cell from a counter-based Philox4x32-10 stream (seed, stream0 + marker number) -- the reference's global
+ * Mersenne-Twister stream cannot be reproduced on a device, parity is at the level of counts, cells, properties
+ * and ids --, properties = mean of the cell's existing markers (0/0 = NaN for an empty cell, like the reference),
+ * ids continuing from id_start exactly as the reference's loop does (each cell's first new id repeats the running
+ * maximum, :614-615).  d_kelem / d_count: cell index per marker and markers per cell (plb_cell_index_count). */
+int plb_inject_plan(plb_ctx* ctx, long long ncell, const long long* d_count, int tracdens, int tracdens_min,
+                    long long cell0, long long cell1, long long* h_out);
+int plb_inject_apply(plb_ctx* ctx, long long M, const long long* d_kelem, const long long* d_count, double* d_tr_x,
+                     int ncols, double* const* h_cols, int id_col, double id_start, const double* d_grid_z,
+                     const double* d_grid_x, int nxx, unsigned long long seed, unsigned long long stream0);
+
 /* Marker migration between z-slabs after advection (north_star; replaces pylamp2.py:550-555's Allreduce of all
  * positions): rank r owns the markers whose cell row floor((nz-1)*z/Lz) (pylamp2.py:588) lies in [c0, c1).
  * plb_migrate_plan lists the leavers (one pass over the coordinates), swaps the counts with the two neighbours
@@ -199,6 +215,9 @@ int plb_rk4_fence_count(plb_ctx* ctx, long long M, const double* d_tr_x, const d
 /* ---- driver-inline marker steps of pylamp2.py ------------------------------------------ */
 /* fence, pylamp2.py:558-572 (fence enabled, no FLOWTHRU/CYCLIC): x<=0 -> eps, x>=L -> L-eps */
 int plb_fence(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps);
+/* the same with a set of walls (bit 0 z = 0, bit 1 x = 0, bit 2 z = L, bit 3 x = L): markers beyond a wall whose bit is
+ * clear -- a BC_TYPE_FLOWTHRU wall, pylamp2.py:565, :569 -- are left alone (the caller removes them, :573-581) */
+int plb_fence_walls(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps, int walls);
 /* cell index + per-cell count, pylamp2.py:588-593.  BIT-EXACT parity item: ielem =
  * floor((nz-1)*z/Lz) with IEEE mul then div, kelem = ielem*(nxx-1)+jelem (int64);
  * d_count[(nz-1)*(nxx-1)] int64.  d_kelem may be NULL. */

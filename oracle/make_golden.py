@@ -197,8 +197,49 @@ def driver_run(name, nsteps, seed, subs, stride):
     print(name, "steps", len(cap), "markers", [int(out["s%d_ntrac" % i]) for i in range(len(cap))])
 
 
+def flowthru_vectors():
+    """Flow-through x = 0 wall (BC_TYPE_FLOWTHRU|FREESLIP = 5, pylamp_stokes.py:268-273, anchor :525-551): the
+    reference's matrices on the non-uniform grid of kernels.npz, and its direct solve (spsolve + one refinement
+    step) of a 33 x 25 system whose density anomaly next to the wall drives flow through it."""
+    import scipy.sparse
+    import scipy.sparse.linalg
+    rt, rs, rd, rc = ref_shims.load()
+    g = np.load(os.path.join(OUT, "kernels.npz"))
+    nx = list(g["nx"])
+    g2 = [g["st_gz"], g["st_gx"]]
+    out = {}
+    combos = [[1, 5, 1, 1], [0, 5, 0, 1], [1, 5, 0, 1]]
+    out["ft_bc"] = np.array(combos)
+    for ic, bc in enumerate(combos):
+        A, r = rs.makeStokesMatrix(nx, g2, g["st_etas"], g["st_etan"], g["st_rho"], bc)
+        A = A.tocoo()
+        key = "ft_%d_" % ic
+        out[key + "row"], out[key + "col"], out[key + "val"], out[key + "rhs"] = A.row, A.col, A.data, r
+    rng = np.random.default_rng(3)
+    nx2, L2 = [33, 25], [1.0, 0.75]
+    grid = [np.linspace(0, L2[i], nx2[i]) for i in range(2)]
+    z, x = np.meshgrid(grid[0], grid[1], indexing="ij")
+    etas = 10 ** (1.5 * np.sin(3 * z) * np.cos(4 * x) + 0.2 * rng.normal(size=nx2))
+    etan = 10 ** (1.5 * np.sin(3 * (z + 0.5 / 32)) * np.cos(4 * (x + 0.375 / 24)) + 0.2 * rng.normal(size=nx2))
+    rho = 3000 + 200 * np.exp(-((z - 0.4) ** 2 + (x - 0.1) ** 2) / 0.02) + 20 * rng.normal(size=nx2)
+    A, r = rs.makeStokesMatrix(nx2, grid, etas, etan, rho, [1, 5, 1, 1])
+    A = scipy.sparse.csc_matrix(A)
+    lu = scipy.sparse.linalg.splu(A)
+    xs = lu.solve(r)
+    xs = xs + lu.solve(r - A @ xs)
+    out.update(fs_nx=np.array(nx2), fs_gz=grid[0], fs_gx=grid[1], fs_etas=etas, fs_etan=etan, fs_rho=rho, fs_x=xs,
+               fs_res=np.linalg.norm(r - A @ xs) / np.linalg.norm(r))
+    np.savez_compressed(os.path.join(OUT, "flowthru.npz"), **out)
+    vx = xs[1::3].reshape(nx2)
+    print("flowthru: residual %.1e, max |vx| on the x = 0 wall %.3e (of %.3e), P(anchor) %.1e" %
+          (out["fs_res"], np.abs(vx[:, 0]).max(), np.abs(xs[0::3]).max(), xs[2::3].reshape(nx2)[nx2[0] // 2, 0]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--only-flowthru" in sys.argv:
+        flowthru_vectors()
+        sys.exit(0)
     if "--only-fence-delete" in sys.argv:
         fence_delete_vectors()
         sys.exit(0)
@@ -211,3 +252,4 @@ if __name__ == "__main__":
     driver_run("c1_noinject", 3, SEED_C1, C1_NOINJECT_SUBS, 997)
     driver_run("thermo_variant", 4, SEED_THERMO, THERMO_SUBS, 53)
     driver_run("c1_surfstab", 3, SEED_C1, C1_SURFSTAB_SUBS, 997)
+    flowthru_vectors()

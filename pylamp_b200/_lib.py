@@ -35,6 +35,8 @@ _PROTOS = {
     "plb_allreduce": (I, [VP, VP, LL, I]),
     "plb_comm_destroy": (None, [VP]),
     "plb_ctx_set_slab": (I, [VP, I, I, I]),
+    "plb_inject_plan": (I, [VP, LL, VP, I, I, LL, LL, C.POINTER(LL)]),
+    "plb_inject_apply": (I, [VP, LL, VP, VP, VP, I, PP, I, D, VP, VP, I, C.c_ulonglong, C.c_ulonglong]),
     "plb_migrate_plan": (I, [VP, LL, VP, I, D, I, I, C.POINTER(LL)]),
     "plb_migrate_apply": (I, [VP, LL, I, PP, IP, LL, I, D, I, I, C.POINTER(LL)]),
     "plb_halo_rows": (I, [VP, I, PP, C.POINTER(LL), I, I, I]),
@@ -49,6 +51,7 @@ _PROTOS = {
     "plb_rk4": (I, [VP, LL, VP, VP, VP, VP, I, VP, I, I, D, D, D, D, D, VP, VP]),
     "plb_rk4_fence_count": (I, [VP, LL, VP, VP, VP, VP, I, VP, I, I, D, D, D, D, D, VP, VP, D, D, D, I, I, VP, VP]),
     "plb_fence": (I, [VP, LL, VP, D, D, D]),
+    "plb_fence_walls": (I, [VP, LL, VP, D, D, D, I]),
     "plb_cell_index_count": (I, [VP, LL, VP, I, I, D, D, VP, VP]),
     "plb_fence_count": (I, [VP, LL, VP, D, D, D, I, I, VP, VP]),
     "plb_update_properties": (I, [VP, LL, I, I, D, D, D, D, VP, VP, VP, VP, VP, VP, VP]),

@@ -9,6 +9,7 @@
 
 struct plb_comm;
 struct plb_migrate_ws;
+struct plb_inject_ws;
 
 struct plb_ctx {
     int device;
@@ -35,10 +36,10 @@ struct plb_ctx {
     int slab_i0, slab_i1, slab_halo;
     double* slab_scratch;  // receive buffer of the boundary-row accumulate (grown on demand)
     plb_migrate_ws* mig;   // marker migration scratch (migrate.cu)
+    plb_inject_ws* inj;    // marker injection scratch (inject.cu)
     size_t slab_scratch_dbl;
     // tuning knobs (plb_ctx_set_param)
     int t2g_variant;       // 1: wide-load chunk kernel for weighted schemes (default), 0: generic kernel only
-    int rk4_variant;       // 1: RK4 on staged velocity tiles (default), 0: one marker per thread on global memory
     int t2g_parts;         // fused step kernel: lanes per run (0 = 1; 1, 2, 4)
     int t2g_nm;            // fused step kernel: markers per CTA (960 default, 1024)
     int t2g_nfmax;         // fused step kernel: fields per node-target work item (default 6)

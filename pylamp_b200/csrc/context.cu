@@ -20,7 +20,6 @@ int plb_ctx_create(int device, plb_ctx** out) {
     }
     c->own_stream = true;
     c->t2g_variant = 1;
-    c->rk4_variant = 1;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->num_sms = prop.multiProcessorCount;
@@ -35,12 +34,14 @@ int plb_ctx_create(int device, plb_ctx** out) {
 
 extern "C" void plb_comm_destroy(plb_ctx* ctx);
 extern "C" void plb_migrate_free(plb_ctx* ctx);
+extern "C" void plb_inject_free(plb_ctx* ctx);
 
 void plb_ctx_destroy(plb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     plb_migrate_free(ctx);
+    plb_inject_free(ctx);
     plb_comm_destroy(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->slab_scratch) cudaFree(ctx->slab_scratch);
@@ -81,10 +82,6 @@ int plb_ctx_set_param(plb_ctx* ctx, const char* name, double value) {
     if (!ctx || !name) return 1;
     if (!strcmp(name, "t2g_variant")) {
         ctx->t2g_variant = (int)value;
-        return 0;
-    }
-    if (!strcmp(name, "rk4_variant")) {
-        ctx->rk4_variant = (int)value;
         return 0;
     }
     if (!strcmp(name, "t2g_parts")) {

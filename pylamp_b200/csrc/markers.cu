@@ -596,16 +596,25 @@ k_grid2trac(long long M, const double2* __restrict__ trx, int method, G2TGrid g,
 // RK4 with the reference's (1/6)(k1+k2+k3+k4) update, pylamp_trac.py:347-388
 // ---------------------------------------------------------------------------------------------
 // RK stage velocity: same arithmetic as locate() + veldiv() with the divisions hoisted -- the two
-// reciprocal cell sizes serve the local coordinates and both Meyer-Jenny coefficients, and the cell
-// lookup multiplies by (n-1)/len instead of dividing (a marker sitting exactly on a cell face may
-// then be assigned to the neighbouring cell, where the continuous interpolant has the same value).
-// fp64 division is what bounds this kernel: the two reciprocals come from per-axis tables filled
-// by k_axis_recip with the same IEEE division (bit-identical results, no division per stage).
+// reciprocal cell sizes serve the local coordinates and both Meyer-Jenny coefficients (per-axis tables filled
+// by k_axis_recip with the same IEEE division: bit-identical results, no fp64 division per stage, which is
+// what bounded this kernel).  The cell of a position is the reference's floor((n-1)(x-x0)/L)
+// (pylamp_trac.py:46-47): evaluated by a multiplication, and re-evaluated with the exact multiply-then-divide
+// whenever the position lies within 1e-7 cells of a face -- the Meyer-Jenny correction of the tangential
+// component is discontinuous across faces, so the cell choice matters there.
+__device__ __forceinline__ long long rk_cell(double v, double v0, double s, double len, int n) {
+    const double t = (v - v0) * s;
+    const double fl = floor(t);
+    const double f = t - fl;
+    if (f < 1e-7 || f > 1.0 - 1e-7) return cell_of(v, v0, len, n);
+    return (long long)fl;
+}
+
 __device__ __forceinline__ void vel_at(const double* __restrict__ fz, const double* __restrict__ fx,
                                        const G2TGrid& g, const double* __restrict__ riz,
                                        const double* __restrict__ rix, double sz, double sx, double z, double x,
                                        double& vz, double& vx) {
-    long long ie = (long long)floor((z - g.z0) * sz), je = (long long)floor((x - g.x0) * sx);
+    const long long ie = rk_cell(z, g.z0, sz, g.zlen, g.nz), je = rk_cell(x, g.x0, sx, g.xlen, g.nxx);
     if (ie < 0 || ie > g.nz - 2 || je < 0 || je > g.nxx - 2) {
         vz = 0, vx = 0;                                    // defval=0, :361
         return;
@@ -625,14 +634,25 @@ __device__ __forceinline__ void vel_at(const double* __restrict__ fz, const doub
     vz = w00 * z00 + w01 * z01 + w10 * z10 + w11 * z11 + dzn * (1 - dzn) * c20;
 }
 
+// FENCE: the fence of pylamp2.py:558-572 and the cell index / per-cell count of :588-593 in the same pass (the new
+// positions are final here) -- same operations as k_fence_count, one read of the coordinates less.
+struct FenceArgs {
+    double Lz, Lx, eps;
+    int nz, nxx;                 // NODE grid of the per-cell count
+    long long* kelem;
+    unsigned long long* count;
+};
+
+template <bool FENCE>
 __global__ void __launch_bounds__(256)
 k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ fz,
       const double* __restrict__ fx, G2TGrid g, const double* __restrict__ riz,
-      const double* __restrict__ rix, double dt, double2* __restrict__ xout, double2* __restrict__ vout) {
+      const double* __restrict__ rix, double dt, double2* __restrict__ xout, double2* __restrict__ vout, FenceArgs fa) {
     const double hdt = 0.5 * dt;
     const double sixth_dt = (1.0 / 6.0) * dt;
     const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
     const double rdt = 1.0 / dt;
+    const long long ncell = FENCE ? (long long)(fa.nz - 1) * (fa.nxx - 1) : 0;
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
          m += (long long)gridDim.x * blockDim.x) {
         double2 p = trx[m];
@@ -644,142 +664,12 @@ k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ f
         double2 q;
         q.x = p.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // :385 (unweighted sum)
         q.y = p.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
-        xout[m] = q;
         if (vout) {
             double2 v;
             v.x = (q.x - p.x) * rdt;                          // :386
             v.y = (q.y - p.y) * rdt;
             vout[m] = v;
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// RK4 on staged velocity tiles.  A CTA takes 1024 consecutive markers.  After the marker-by-cell sort they
-// occupy ~64 neighbouring cells, so the part of the two velocity fields that all four stages of all those
-// markers can read -- the bounding box of their cells plus the RK reach of one cell -- is a few hundred nodes:
-// it is loaded once (coalesced rows, both components interleaved as double2) into shared memory, and the
-// 4 x 8 corner reads per marker become 4 x 4 shared-memory reads of 16 bytes.  Chunks whose bounding box does
-// not fit (unordered clouds, chunks that wrap around a cell row) and stage positions that leave the tile read
-// global memory like k_rk4.  Same arithmetic as k_rk4 / vel_at; the cell of a position is the reference's
-// floor((n-1)(x-x0)/L) (pylamp_trac.py:46-47): evaluated by a multiplication, re-evaluated with the exact
-// multiply-then-divide whenever the position lies within 1e-7 cells of a face (the Meyer-Jenny correction of the
-// tangential component is discontinuous across faces, so the cell choice matters there).
-// FENCE: the fence of pylamp2.py:558-572 and the cell index / per-cell count of :588-593 in the same pass
-// (the new positions are final here) -- same operations as k_fence_count.
-// ---------------------------------------------------------------------------------------------
-constexpr int RK_NM = 1024, RK_THREADS = 256, RK_TILE_MAX = 2048;
-
-__device__ __forceinline__ int rk_cell(double v, double v0, double s, double len, int n) {
-    const double t = (v - v0) * s;
-    const double fl = floor(t);
-    const double f = t - fl;
-    if (f < 1e-7 || f > 1.0 - 1e-7) return (int)max(min(cell_of(v, v0, len, n), (long long)n), -1LL);
-    return (int)max(min(fl, (double)n), -1.0);
-}
-
-struct RKTile {
-    const double2* t;     // staged nodes [r0..r1] x [c0..c1], row length nc
-    int r0, r1, c0, c1, nc;
-    bool on;
-};
-
-__device__ __forceinline__ void rk_vel(const double* __restrict__ fz, const double* __restrict__ fx, const G2TGrid& g,
-                                       const double* __restrict__ riz, const double* __restrict__ rix, double sz,
-                                       double sx, const RKTile& T, double z, double x, double& vz, double& vx) {
-    const int ie = rk_cell(z, g.z0, sz, g.zlen, g.nz), je = rk_cell(x, g.x0, sx, g.xlen, g.nxx);
-    if (ie < 0 || ie > g.nz - 2 || je < 0 || je > g.nxx - 2) {
-        vz = 0, vx = 0;                                    // defval=0, pylamp_trac.py:361
-        return;
-    }
-    double z00, z01, z10, z11, x00, x01, x10, x11;
-    if (T.on && ie >= T.r0 && ie < T.r1 && je >= T.c0 && je < T.c1) {
-        const double2* p = T.t + (ie - T.r0) * T.nc + (je - T.c0);
-        const double2 a = p[0], b = p[1], c = p[T.nc], d = p[T.nc + 1];
-        z00 = a.x, x00 = a.y, z01 = b.x, x01 = b.y, z10 = c.x, x10 = c.y, z11 = d.x, x11 = d.y;
-    } else {
-        const double* pz = fz + (long long)ie * g.ld + je;
-        const double* px = fx + (long long)ie * g.ld + je;
-        z00 = __ldg(pz), z01 = __ldg(pz + 1), z10 = __ldg(pz + g.ld), z11 = __ldg(pz + g.ld + 1);
-        x00 = __ldg(px), x01 = __ldg(px + 1), x10 = __ldg(px + g.ld), x11 = __ldg(px + g.ld + 1);
-    }
-    const double gz0 = g.gz[ie], gz1 = g.gz[ie + 1], gx0 = g.gx[je], gx1 = g.gx[je + 1];
-    const double hz = gz1 - gz0, hx = gx1 - gx0;
-    const double rz = riz[ie], rx = rix[je];          // 1/hz, 1/hx
-    const double dzn = (z - gz0) * rz, dxn = (x - gx0) * rx;
-    const double c10 = (0.5 * hx * rz) * (z00 - z10 + z11 - z01);
-    const double c20 = (0.5 * hz * rx) * (x00 - x01 + x11 - x10);
-    const double w00 = (1 - dxn) * (1 - dzn), w01 = dxn * (1 - dzn), w10 = (1 - dxn) * dzn, w11 = dxn * dzn;
-    vx = w00 * x00 + w01 * x01 + w10 * x10 + w11 * x11 + dxn * (1 - dxn) * c10;
-    vz = w00 * z00 + w01 * z01 + w10 * z10 + w11 * z11 + dzn * (1 - dzn) * c20;
-}
-
-struct FenceArgs {
-    double Lz, Lx, eps;
-    int nz, nxx;                 // NODE grid of the per-cell count
-    long long* kelem;
-    unsigned long long* count;
-};
-
-template <bool FENCE>
-__global__ void __launch_bounds__(RK_THREADS)
-k_rk4_tile(long long M, const double2* __restrict__ trx, const double* __restrict__ fz, const double* __restrict__ fx,
-           G2TGrid g, const double* __restrict__ riz, const double* __restrict__ rix, double dt,
-           double2* __restrict__ xout, double2* __restrict__ vout, FenceArgs fa) {
-    __shared__ double2 tile[RK_TILE_MAX];
-    __shared__ int red[4][RK_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long m0 = (long long)blockIdx.x * RK_NM;
-    const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
-    int imin = 0x7fffffff, imax = -1, jmin = 0x7fffffff, jmax = -1;
-#pragma unroll
-    for (int r = 0; r < RK_NM / RK_THREADS; r++) {
-        const long long m = m0 + r * RK_THREADS + tid;
-        if (m < M) {
-            const double2 p = trx[m];
-            const int ie = __double2int_rd((p.x - g.z0) * sz), je = __double2int_rd((p.y - g.x0) * sx);
-            if (ie >= 0 && ie <= g.nz - 2 && je >= 0 && je <= g.nxx - 2)
-                imin = min(imin, ie), imax = max(imax, ie), jmin = min(jmin, je), jmax = max(jmax, je);
-        }
-    }
-    imin = __reduce_min_sync(0xffffffffu, imin), imax = __reduce_max_sync(0xffffffffu, imax);
-    jmin = __reduce_min_sync(0xffffffffu, jmin), jmax = __reduce_max_sync(0xffffffffu, jmax);
-    if (lane == 0) red[0][warp] = imin, red[1][warp] = imax, red[2][warp] = jmin, red[3][warp] = jmax;
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < RK_THREADS / 32; w++)
-        imin = min(imin, red[0][w]), imax = max(imax, red[1][w]), jmin = min(jmin, red[2][w]), jmax = max(jmax, red[3][w]);
-    RKTile T;
-    T.t = tile;
-    // nodes the four stages can touch: cells [imin-1, imax+1] x [jmin-1, jmax+1], i.e. nodes one further
-    T.r0 = max(imin - 1, 0), T.r1 = min(imax + 2, g.nz - 1), T.c0 = max(jmin - 1, 0), T.c1 = min(jmax + 2, g.nxx - 1);
-    T.nc = T.c1 - T.c0 + 1;
-    T.on = imax >= 0 && (long long)(T.r1 - T.r0 + 1) * T.nc <= RK_TILE_MAX;
-    if (T.on) {
-        const int n = (T.r1 - T.r0 + 1) * T.nc;
-        for (int e = tid; e < n; e += RK_THREADS) {
-            const int r = e / T.nc, c = e - r * T.nc;
-            const long long o = (long long)(T.r0 + r) * g.ld + T.c0 + c;
-            tile[e] = make_double2(__ldg(fz + o), __ldg(fx + o));
-        }
-    }
-    __syncthreads();
-    const double hdt = 0.5 * dt, sixth_dt = (1.0 / 6.0) * dt, rdt = 1.0 / dt;
-    const long long ncell = FENCE ? (long long)(fa.nz - 1) * (fa.nxx - 1) : 0;
-#pragma unroll 1
-    for (int r = 0; r < RK_NM / RK_THREADS; r++) {
-        const long long m = m0 + r * RK_THREADS + tid;
-        if (m >= M) break;
-        const double2 q0 = trx[m];              // (second read of the chunk: served by L1/L2)
-        double k1z, k1x, k2z, k2x, k3z, k3x, k4z, k4x;
-        rk_vel(fz, fx, g, riz, rix, sz, sx, T, q0.x, q0.y, k1z, k1x);
-        rk_vel(fz, fx, g, riz, rix, sz, sx, T, q0.x + hdt * k1z, q0.y + hdt * k1x, k2z, k2x);
-        rk_vel(fz, fx, g, riz, rix, sz, sx, T, q0.x + hdt * k2z, q0.y + hdt * k2x, k3z, k3x);
-        rk_vel(fz, fx, g, riz, rix, sz, sx, T, q0.x + dt * k3z, q0.y + dt * k3x, k4z, k4x);
-        double2 q;
-        q.x = q0.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // pylamp_trac.py:385 (unweighted sum)
-        q.y = q0.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
-        if (vout) vout[m] = make_double2((q.x - q0.x) * rdt, (q.y - q0.y) * rdt);      // :386
         if (FENCE) {
             if (q.x <= 0) q.x = fa.eps;                       // pylamp2.py:558-572
             if (q.x >= fa.Lz) q.x = fa.Lz - fa.eps;
@@ -798,16 +688,19 @@ k_rk4_tile(long long M, const double2* __restrict__ trx, const double* __restric
 // ---------------------------------------------------------------------------------------------
 // fence, cell index + count, property update, subgrid stages
 // ---------------------------------------------------------------------------------------------
+// walls: bit 0 z = 0, bit 1 x = 0, bit 2 z = L, bit 3 x = L (the order of the reference's bc lists); a wall
+// whose bit is clear is a flow-through wall: markers beyond it are left where they are (and removed by the caller,
+// pylamp2.py:563-581)
 __global__ void __launch_bounds__(256)
-k_fence(long long M, double2* __restrict__ trx, double Lz, double Lx, double eps) {
+k_fence(long long M, double2* __restrict__ trx, double Lz, double Lx, double eps, int walls) {
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
          m += (long long)gridDim.x * blockDim.x) {
         double2 p = trx[m];
         bool ch = false;
-        if (p.x <= 0) p.x = eps, ch = true;
-        if (p.x >= Lz) p.x = Lz - eps, ch = true;
-        if (p.y <= 0) p.y = eps, ch = true;
-        if (p.y >= Lx) p.y = Lx - eps, ch = true;
+        if (p.x <= 0 && (walls & 1)) p.x = eps, ch = true;
+        if (p.x >= Lz && (walls & 4)) p.x = Lz - eps, ch = true;
+        if (p.y <= 0 && (walls & 2)) p.y = eps, ch = true;
+        if (p.y >= Lx && (walls & 8)) p.y = Lx - eps, ch = true;
         if (ch) trx[m] = p;
     }
 }
@@ -1271,6 +1164,23 @@ k_t2g_fused(long long M, const double2* __restrict__ trx, const TFArgs a, int us
 // ---------------------------------------------------------------------------------------------
 constexpr int T2G_BOUNDARY_ROWS = 2;
 
+// zero `nplanes` accumulation planes of nze x nxe doubles; with slab-local fields only the rows this rank's markers
+// can reach (its own rows and the boundary rows either side)
+int t2g_zero_planes(plb_ctx* ctx, double* planes, size_t nplanes, int nze, int nxe, int crop_z0) {
+    const size_t plane = (size_t)nze * nxe;
+    if (!(plb_comm_size(ctx) > 1 && ctx->slab_on)) {
+        PLB_CUDA(ctx, cudaMemsetAsync(planes, 0, nplanes * plane * sizeof(double), ctx->stream));
+        return 0;
+    }
+    const int lo = std::max(ctx->slab_i0 + crop_z0 - T2G_BOUNDARY_ROWS - 1, 0);
+    const int hi = std::min(ctx->slab_i1 + crop_z0 + T2G_BOUNDARY_ROWS + 1, nze);
+    // (the first rank's markers can lie in the ghost rows below, the last rank's above: keep those)
+    const int a = plb_comm_rank(ctx) == 0 ? 0 : lo, b = plb_comm_rank(ctx) == plb_comm_size(ctx) - 1 ? nze : hi;
+    for (size_t p = 0; p < nplanes; p++)
+        PLB_CUDA(ctx, cudaMemsetAsync(planes + p * plane + (size_t)a * nxe, 0, (size_t)(b - a) * nxe * sizeof(double), ctx->stream));
+    return 0;
+}
+
 struct T2GFinish {
     T2GArgs a;
     int crop_z0, crop_x0;
@@ -1437,7 +1347,7 @@ int plb_trac2grid(plb_ctx* ctx, long long M, const double* d_tr_x, int k,
     if (any_c) a.cnt = w + (nxt++) * plane;
     a.axz = d_axis_z, a.axx = d_axis_x, a.nze = nze, a.nxe = nxe;
     a.z0 = z0, a.zlen = zlen, a.x0 = x0, a.xlen = xlen, a.k = k;
-    PLB_CUDA(ctx, cudaMemsetAsync(w, 0, nplanes * plane * sizeof(double), ctx->stream));
+    if (t2g_zero_planes(ctx, w, nplanes, nze, nxe, crop_z0)) return 2;
     if (M > 0) {
         plb_prof_scope prof_(ctx, PLB_K_T2G, (16.0 + 8.0 * k) * (double)M);
         const double2* x = (const double2*)d_tr_x;
@@ -1531,7 +1441,8 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
     if (plb_ws_reserve(ctx, ndbl * sizeof(double))) return 2;
     double* w = (double*)ctx->ws;
     // planes, tables
-    PLB_CUDA(ctx, cudaMemsetAsync(w, 0, nplane_dbl * sizeof(double), ctx->stream));
+    for (int i = 0; i < ntargets; i++)
+        if (t2g_zero_planes(ctx, w + plane_off[i], (size_t)(1 + tg[i].k), tg[i].nze, tg[i].nxe, tg[i].crop_z0)) return 2;
     int ti = 0;
     for (int i = 0; i < ntargets; i++) {
         const plb_t2g_target& T = tg[i];
@@ -1754,24 +1665,16 @@ int rk4_launch(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_
     k_axis_recip<<<plb_blocks(nxc, 256), 256, 0, ctx->stream>>>(nxc, d_gc_x, recip + nzc, nullptr);
     PLB_LAUNCHED(ctx);
     plb_prof_scope prof_(ctx, PLB_K_RK4, (d_v_out ? 48.0 : 32.0) * (double)M);
-    if (ctx->rk4_variant == 0 && !fence) {
-        k_rk4<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, recip,
-                                                                     recip + nzc, dt, (double2*)d_x_out, (double2*)d_v_out);
+    FenceArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    const int grid = plb_grid_for(ctx, M, 256, 8);
+    if (fence) {
+        fa = *fence;
+        k_rk4<true><<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, recip, recip + nzc, dt,
+                                                   (double2*)d_x_out, (double2*)d_v_out, fa);
     } else {
-        const long long nchunk = (M + RK_NM - 1) / RK_NM;
-        if (nchunk > 0x7fffffffLL) PLB_FAIL(ctx, "plb_rk4: too many markers");
-        FenceArgs fa;
-        memset(&fa, 0, sizeof(fa));
-        if (fence) {
-            fa = *fence;
-            k_rk4_tile<true><<<(unsigned)nchunk, RK_THREADS, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, recip,
-                                                                              recip + nzc, dt, (double2*)d_x_out,
-                                                                              (double2*)d_v_out, fa);
-        } else {
-            k_rk4_tile<false><<<(unsigned)nchunk, RK_THREADS, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, recip,
-                                                                               recip + nzc, dt, (double2*)d_x_out,
-                                                                               (double2*)d_v_out, fa);
-        }
+        k_rk4<false><<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, d_vz_c, d_vx_c, g, recip, recip + nzc, dt,
+                                                    (double2*)d_x_out, (double2*)d_v_out, fa);
     }
     PLB_LAUNCHED(ctx);
     return 0;
@@ -1797,14 +1700,18 @@ int plb_rk4_fence_count(plb_ctx* ctx, long long M, const double* d_tr_x, const d
     return rk4_launch(ctx, M, d_tr_x, d_vz_c, d_vx_c, d_gc_z, nzc, d_gc_x, nxc, ld, z0, zlen, x0, xlen, dt, d_x_out, d_v_out, &fa);
 }
 
-int plb_fence(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps) {
+int plb_fence_walls(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps, int walls) {
     if (!ctx) return 1;
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (M > 0) {
-        k_fence<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, (double2*)d_tr_x, Lz, Lx, eps);
+        k_fence<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, (double2*)d_tr_x, Lz, Lx, eps, walls);
         PLB_LAUNCHED(ctx);
     }
     return 0;
+}
+
+int plb_fence(plb_ctx* ctx, long long M, double* d_tr_x, double Lz, double Lx, double eps) {
+    return plb_fence_walls(ctx, M, d_tr_x, Lz, Lx, eps, 15);
 }
 
 int plb_cell_index_count(plb_ctx* ctx, long long M, const double* d_tr_x, int nz, int nxx,

@@ -116,6 +116,12 @@ k_scan_add(long long n, unsigned* __restrict__ out, const unsigned* __restrict__
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_scan_finish(long long n, unsigned* __restrict__ out, const unsigned* __restrict__ tile_sum) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t <= n; t += (long long)gridDim.x * blockDim.x)
+        out[t] = t == n ? tile_sum[(n + SCAN_TILE - 1) / SCAN_TILE] : out[t] + tile_sum[t / SCAN_TILE];
+}
+
 // slot = cursor[key]++ (warp-aggregated, ranks inside a warp follow the lane order)
 __global__ void __launch_bounds__(256)
 k_sort_slots(long long M, unsigned* __restrict__ key_dest, unsigned* __restrict__ cursor) {
@@ -140,6 +146,22 @@ k_permute(long long M, const unsigned* __restrict__ dest, const T* __restrict__ 
 }
 
 }  // namespace
+
+// out[t] = sum of in[0..t), t = 0..n (n + 1 entries); `tiles`: ceil(n / 4096) + 1 words of scratch
+int plb_exclusive_scan_u32(plb_ctx* ctx, long long n, const unsigned* in, unsigned* out, unsigned* tiles) {
+    const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    if (ntiles == 0) {
+        PLB_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(unsigned), ctx->stream));
+        return 0;
+    }
+    k_scan_tiles<<<ntiles, SCAN_T, 0, ctx->stream>>>(n, in, out, tiles);
+    PLB_LAUNCHED(ctx);
+    k_scan_tops<<<1, 1024, 0, ctx->stream>>>(ntiles + 1, tiles);       // tiles[ntiles] (zeroed by the caller) = grand total
+    PLB_LAUNCHED(ctx);
+    k_scan_finish<<<plb_grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(n, out, tiles);
+    PLB_LAUNCHED(ctx);
+    return 0;
+}
 
 extern "C" {
 

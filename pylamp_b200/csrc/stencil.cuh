@@ -25,6 +25,9 @@ struct LevelDev {
     int vx_i0, vx_i1, vx_j0, vx_j1;
     double sl_z0, sl_z1;              // vx(0,j) = sl_z0*vx(1,j), vx(nz-2,j) = sl_z1*vx(nz-3,j)
     int ns_z0, ns_z1;                 // proper levels: no-slip (instead of free-slip) z-walls
+    // reference closure only: flow-through wall at x = 0 (BC_TYPE_FLOWTHRU|FREESLIP, pylamp_stokes.py:268-273):
+    // vx(i,0) = vx(i,1) instead of vx(i,0) = 0
+    int ft_x0;
 };
 
 __device__ __forceinline__ bool is_vz_row(const LevelDev& L, int i, int j) {
@@ -134,6 +137,11 @@ __device__ __forceinline__ void store_vx(const LevelDev& L, double* __restrict__
     if (!L.proper) {
         if (i == L.vx_i0) vx[o - L.ld] = L.sl_z0 * v;   // :163-175
         if (i == L.vx_i1) vx[o + L.ld] = L.sl_z1 * v;   // :202-214
+        if (L.ft_x0 && j == L.vx_j0) {                  // dvx/dx = 0 on the x = 0 wall, rows i = 0 .. nz-2 (:268-273)
+            vx[o - 1] = v;
+            if (i == L.vx_i0) vx[o - L.ld - 1] = L.sl_z0 * v;
+            if (i == L.vx_i1) vx[o + L.ld - 1] = L.sl_z1 * v;
+        }
     }
 }
 

@@ -38,6 +38,7 @@ struct Level {
     int vz_i0, vz_i1, vz_j0, vz_j1, vx_i0, vx_i1, vx_j0, vx_j1;
     double sl_z0 = 1, sl_z1 = 1;
     int ns_z0 = 0, ns_z1 = 0;
+    int ft_x0 = 0;
     double *X = nullptr, *T = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;   // 2 local planes each
     double lmax = 0;
     LevelDev dev() const {
@@ -49,6 +50,7 @@ struct Level {
         L.vx_i0 = vx_i0, L.vx_i1 = vx_i1, L.vx_j0 = vx_j0, L.vx_j1 = vx_j1;
         L.sl_z0 = sl_z0, L.sl_z1 = sl_z1;
         L.ns_z0 = ns_z0, L.ns_z1 = ns_z1;
+        L.ft_x0 = ft_x0;
         return L;
     }
     // pointer to a local array as the kernels see it (global row indexing)
@@ -71,6 +73,7 @@ struct plb_stokes {
     // full-size planes of centred density gradients Dz | Dx the extra momentum-row terms are built from
     double surf = 0;
     double* surf_d = nullptr;
+    int ai = 3, aj = 2;           // pressure anchor cell (pylamp_stokes.py:525-551: (3,2), or (nz/2, 0) on a flow-through wall)
     double Kc = 0, Kb = 0;
     bool coeffs = false, hierarchy = false;
     bool slab_fields = false;     // coefficient fields and results are slab-local (plb_ctx_set_slab): own rows + halo rows
@@ -148,8 +151,9 @@ k_min2(long long n, const double* __restrict__ a, const double* __restrict__ b, 
 // -------------------------------------------------------------------------------------------
 struct FullArgs {
     const double *gz, *gx;
-    int bz0, bz1;          // z-wall types (NOSLIP / FREESLIP); x-walls are FREESLIP
+    int bz0, bz1;          // z-wall types (NOSLIP / FREESLIP); x-walls are FREESLIP (x = 0 optionally flow-through)
     double Kc, Kb;
+    int ft_x0, ai, aj;     // flow-through wall at x = 0; pressure anchor cell
 };
 
 // Free-surface stabilisation terms (SURF): with q = Dz*vz(i,j) + Dx*vx(i,j), the interior z-momentum row
@@ -202,7 +206,9 @@ k_stokes_full(LevelDev L, FullArgs a, SurfArgs sf, const double* __restrict__ vz
     }
     yz[o] = r;
     // ---- vx row
-    if (i == nz - 1 || j == 0 || j == nxx - 1) {
+    if (j == 0 && a.ft_x0 && i <= nz - 2) {
+        r = Kc * (vx[o + 1] - vx[o]);                                // flow-through wall: dvx/dx = 0, :268-273
+    } else if (i == nz - 1 || j == 0 || j == nxx - 1) {
         r = Kc * vx[o];
     } else if (i == 0) {
         if (a.bz0 == PLB_BC_FREESLIP) {
@@ -229,7 +235,7 @@ k_stokes_full(LevelDev L, FullArgs a, SurfArgs sf, const double* __restrict__ vz
         r = Kc * p[o];
     } else if ((i == 0 || i == nz - 2) && (j == 0 || j == nxx - 2)) {
         r = (j == 0) ? a.Kb * (p[o + 1] - p[o]) : a.Kb * (p[o - 1] - p[o]);      // :358-369
-    } else if (i == 3 && j == 2) {
+    } else if (i == a.ai && j == a.aj) {
         r = Kc * p[o];                                               // anchor, :525-551
     } else {
         r = Kc * (L.idx[j] * (vx[o + 1] - vx[o]) + L.idz[i] * (vz[o + ld] - vz[o]));
@@ -985,13 +991,13 @@ __global__ void __launch_bounds__(256) k_row_mean(LevelDev L, const double* __re
     }
 }
 // P_h per cell row with P_h(row 3) = 0 (the anchor row): -2 Kc idzc[i] (P_h[i] - P_h[i-1]) = m[i]
-__global__ void k_scan_ph(LevelDev L, double Kc, const double* __restrict__ m, double* __restrict__ ph) {
+__global__ void k_scan_ph(LevelDev L, double Kc, const double* __restrict__ m, double* __restrict__ ph, int ai) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int nz = L.nz;
     ph[0] = 0;
     for (int i = 1; i <= nz - 2; i++) ph[i] = ph[i - 1] - m[i] / (2 * Kc * L.idzc[i]);
     ph[nz - 1] = 0;
-    const double p3 = ph[3];
+    const double p3 = ph[ai];
     for (int i = 0; i <= nz - 2; i++) ph[i] -= p3;
 }
 __global__ void __launch_bounds__(BX* BY)
@@ -1018,8 +1024,8 @@ __global__ void __launch_bounds__(256) k_extrapolate(long long n, HistList H, do
 }
 
 // value of the iterate's pressure in the anchor cell (3,2) (zero on ranks that do not own row 3)
-__global__ void k_get_anchor(LevelDev L, const double* __restrict__ p, double* out) {
-    *out = (3 >= L.i0 && 3 < L.i1) ? p[3LL * L.ld + 2] : 0.0;
+__global__ void k_get_anchor(LevelDev L, const double* __restrict__ p, double* out, int ai, int aj) {
+    *out = (ai >= L.i0 && ai < L.i1) ? p[(long long)ai * L.ld + aj] : 0.0;
 }
 
 // final solution: planar -> interleaved with the slaved corner pressures filled in
@@ -1143,6 +1149,7 @@ int build_levels(plb_stokes* op, const double* h_gz, const double* h_gx) {
         if (l == 0) {
             L.vz_i0 = 1, L.vz_i1 = nz - 2, L.vz_j0 = 1, L.vz_j1 = nxx - 3;
             L.vx_i0 = 1, L.vx_i1 = nz - 3, L.vx_j0 = 1, L.vx_j1 = nxx - 2;
+            L.ft_x0 = (op->bc[1] & PLB_BC_FLOWTHRU) ? 1 : 0;
             // slave factors of the tangential wall rows (pylamp_stokes.py:163-175, :202-214)
             const std::vector<double>& gz = L.gz;
             if (op->bc[0] == PLB_BC_NOSLIP) {
@@ -1479,14 +1486,16 @@ int plb_stokes_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_gri
         bool zwall = (w % 2) == 0;
         if (zwall && b != PLB_BC_NOSLIP && b != PLB_BC_FREESLIP)
             PLB_FAIL(ctx, "plb_stokes_create: z-wall BC %d not supported (NOSLIP|FREESLIP; CYCLIC is SURVEY 8f-4)", b);
-        if (!zwall && b != PLB_BC_FREESLIP)
-            PLB_FAIL(ctx, "plb_stokes_create: x-wall BC %d not supported (the reference's matrix is singular "
-                          "for NOSLIP x-walls, pylamp_stokes.py:242; CYCLIC/FLOWTHRU are SURVEY 8f-4)", b);
+        if (!zwall && b != PLB_BC_FREESLIP && !(w == 1 && b == (PLB_BC_FREESLIP | PLB_BC_FLOWTHRU)))
+            PLB_FAIL(ctx, "plb_stokes_create: x-wall BC %d not supported (FREESLIP, or FLOWTHRU|FREESLIP on the x = 0 wall; "
+                          "the reference's own matrix is singular for NOSLIP, CYCLIC and pure FLOWTHRU x-walls and has "
+                          "no pressure anchor with a flow-through x = L wall: tests/test_reference_bc_probe.py)", b);
     }
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     plb_stokes* op = new plb_stokes();
     op->ctx = ctx, op->device = ctx->device, op->nz = nz, op->nxx = nxx, op->ld = ld;
     for (int w = 0; w < 4; w++) op->bc[w] = h_bc[w];
+    if (op->bc[1] & PLB_BC_FLOWTHRU) op->ai = nz / 2, op->aj = 0;      // pylamp_stokes.py:539-541
     if (plb_reduce_ws_init(ctx, &op->rws)) { delete op; return 2; }
     if (zalloc(ctx, &op->d_scal, 1024 + 2 * (size_t)nz)) { delete op; return 2; }
     if (build_levels(op, h_grid_z, h_grid_x)) { plb_stokes_destroy(op); return 2; }
@@ -1631,7 +1640,7 @@ int plb_stokes_apply(plb_stokes* op, const double* d_x, double* d_y) {
     double *in = op->t3, *outp = op->r3;
     k_deinterleave<<<plb_grid_for(ctx, (long long)P, 256, 8), 256, 0, ctx->stream>>>((long long)P, d_x, in, in + P, in + 2 * P);
     PLB_LAUNCHED(ctx);
-    FullArgs a = {op->gz_d, op->gx_d, op->bc[0], op->bc[2], op->Kc, op->Kb};
+    FullArgs a = {op->gz_d, op->gx_d, op->bc[0], op->bc[2], op->Kc, op->Kb, op->lv[0].ft_x0, op->ai, op->aj};
     const SurfArgs sf = surf_args(op);
     if (op->surf > 0)
         k_stokes_full<true><<<grid2d(L.nz, L.nxx), block2d(), 0, ctx->stream>>>(L.dev(), a, sf, in, in + P, in + 2 * P,
@@ -1714,7 +1723,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         k_row_mean<<<L.nz, 256, 0, ctx->stream>>>(D, C3(b, 0), m);
         PLB_LAUNCHED(ctx);
         if (L.dist && plb_comm_allreduce(ctx, m, (size_t)L.nz, PLB_OP_SUM)) return 2;   // rows of other slabs
-        k_scan_ph<<<1, 1, 0, ctx->stream>>>(D, Kc, m, ph);
+        k_scan_ph<<<1, 1, 0, ctx->stream>>>(D, Kc, m, ph, op->ai);
         PLB_LAUNCHED(ctx);
         k_sub_row_mean<<<g, blk, 0, ctx->stream>>>(D, m, V3(b, 0));
         PLB_LAUNCHED(ctx);
@@ -1853,7 +1862,7 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
     // and halo rows exchanged with the neighbours below
     if (L.dist && !op->slab_fields) PLB_CUDA(ctx, cudaMemsetAsync(d_x, 0, sizeof(double) * 3 * L.full, ctx->stream));
     double* panchor = op->d_scal + 930;
-    k_get_anchor<<<1, 1, 0, ctx->stream>>>(D, C3(x, 2), panchor);
+    k_get_anchor<<<1, 1, 0, ctx->stream>>>(D, C3(x, 2), panchor, op->ai, op->aj);
     PLB_LAUNCHED(ctx);
     if (L.dist && plb_comm_allreduce(ctx, panchor, 1, PLB_OP_SUM)) return 2;
     k_solution_out<<<g, blk, 0, ctx->stream>>>(D, C3(x, 0), C3(x, 1), C3(x, 2), ph, panchor, d_x);

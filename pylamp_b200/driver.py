@@ -333,7 +333,8 @@ def timestep(s, o, want_kelem=True, phases=False):
     newgrid = [np.insert(gridmp[IZ], 0, pre[IZ]), np.insert(gridmp[IX], 0, pre[IX])]
     slab = world > 1 and o.marker_ownership == "slab"
     need_kelem = want_kelem or o.tracdens_min > 0
-    fused_fence = o.tracs_fence_enabled and not slab
+    flowthru = any(int(b) & pylamp_stokes.BC_TYPE_FLOWTHRU for b in o.bcstokes)
+    fused_fence = o.tracs_fence_enabled and not slab and not flowthru
     if fused_fence:
         # RK4, fence and per-cell count in one pass over the markers (the new positions are final there)
         s.trac_vel, s.tr_x, s.kelem, s.count = pylamp_trac.rk4_fence_count_device(
@@ -345,7 +346,9 @@ def timestep(s, o, want_kelem=True, phases=False):
     # fence (or removal of the markers that left the box) + per-cell count, pylamp2.py:558-593
     if fused_fence:
         pass
-    elif not o.tracs_fence_enabled:
+    elif not o.tracs_fence_enabled or flowthru:
+        if o.tracs_fence_enabled:
+            markers.fence(s.tr_x, s.L, EPS, bc=o.bcstokes)                          # every wall but the flow-through ones
         s.stats["removed"] = markers.delete_outside(s)                              # :563-581
         if slab:
             s.stats["migrated"] = (migrate.migrate_native if o.native_migration else migrate.migrate)(s)

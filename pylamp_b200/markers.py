@@ -26,9 +26,13 @@ def cell_index_count(tr_x, nx, L, want_kelem=True):
     return kelem, count
 
 
-def fence(tr_x, L, eps=EPS):
-    """In-place fence to [eps, L-eps] -- pylamp2.py:558-572 (no FLOWTHRU / CYCLIC walls)."""
-    _ctx(tr_x).call("plb_fence", tr_x.shape[0], tr_x.data_ptr(), float(L[IZ]), float(L[IX]), float(eps))
+def fence(tr_x, L, eps=EPS, bc=None):
+    """In-place fence to [eps, L-eps] -- pylamp2.py:558-572.  `bc`: the Stokes wall types [z=0, x=0, z=L, x=L];
+    markers beyond a BC_TYPE_FLOWTHRU wall are not fenced (they are removed afterwards, :573-581)."""
+    walls = 15
+    if bc is not None:
+        walls = sum(1 << w for w in range(4) if not (int(bc[w]) & 4))
+    _ctx(tr_x).call("plb_fence_walls", tr_x.shape[0], tr_x.data_ptr(), float(L[IZ]), float(L[IX]), float(eps), walls)
 
 
 def fence_count(tr_x, nx, L, eps=EPS, want_kelem=True):
@@ -194,7 +198,60 @@ def subgrid_fused(stage, tr_x, grid, field, T, dt=0.0, dz=1.0, dx=1.0, cp=None, 
     return Tsg, dT
 
 
-def inject_markers(s, tracdens, tracdens_min, generator=None, cell_rows=None, group=None):
+def inject_markers(s, tracdens, tracdens_min, generator=None, cell_rows=None, group=None, seed=None):
+    """Marker injection into under-populated cells -- pylamp2.py:594-633.  CUDA state: the library's kernels
+    (csrc/inject.cu: plan by scans over the cells, cell means by one pass over the markers, positions from a
+    counter-based Philox stream); CPU tensors (gloo tests of the multi-rank host logic): `inject_markers_torch`.
+    Same counts, cells, cell-mean properties and ids as the reference's loop; positions are random inside the same
+    cells.  Returns the number of markers injected on this rank."""
+    if not s.tr_x.is_cuda:
+        return inject_markers_torch(s, tracdens, tracdens_min, generator=generator, cell_rows=cell_rows, group=group)
+    from .migrate import _distinct, resize_rows
+    from .pylamp_const import TR__ID
+    ctx = s.ctx
+    nz, nxx = int(s.nx[IZ]), int(s.nx[IX])
+    ncx, ncell = nxx - 1, (nz - 1) * (nxx - 1)
+    dev = s.tr_x.device
+    c0, c1 = (0, ncell) if cell_rows is None else (cell_rows[0] * ncx, cell_rows[1] * ncx)
+    plan = (C.c_longlong * 3)()
+    ctx.call("plb_inject_plan", ncell, s.count.data_ptr(), int(tracdens), int(tracdens_min), int(c0), int(c1), plan)
+    n_def, n_new, id_adv = int(plan[0]), int(plan[1]), int(plan[2])
+    M0 = int(s.tr_x.shape[0])
+    max0 = s.cols[TR__ID].max() if M0 else torch.tensor(-1.0, dtype=torch.float64, device=dev)
+    id_offset = 0.0
+    if cell_rows is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        max0 = max0.clone()
+        dist.all_reduce(max0, op=dist.ReduceOp.MAX, group=group)
+        adv = torch.zeros(world, dtype=torch.float64, device=dev)
+        adv[rank] = float(id_adv)
+        dist.all_reduce(adv, group=group)
+        id_offset = float(adv[:rank].sum().item())      # ids continue over the ranks in cell order
+    if n_new == 0:
+        return 0
+    # the id column must not share storage with another column once new ids are written
+    id_aliased = any(k != TR__ID and s.cols[k].data_ptr() == s.cols[TR__ID].data_ptr() for k in range(len(s.cols)))
+    if id_aliased:
+        s.cols = list(s.cols)
+        s.cols[TR__ID] = s.cols[TR__ID].clone()
+    uniq, where = _distinct(s.cols)
+    uniq = [resize_rows(c if c.is_contiguous() else c.contiguous(), M0 + n_new) for c in uniq]
+    s.tr_x = resize_rows(s.tr_x, M0 + n_new)
+    gz = torch.as_tensor(np.asarray(s.grid[IZ], dtype=np.float64)).to(dev)
+    gx = torch.as_tensor(np.asarray(s.grid[IX], dtype=np.float64)).to(dev)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device="cpu" if generator is None or generator.device.type == "cpu" else dev).item())
+    s._inject_stream = getattr(s, "_inject_stream", 0)
+    ctx.call("plb_inject_apply", M0, s.kelem.data_ptr(), s.count.data_ptr(), s.tr_x.data_ptr(), len(uniq),
+             _lib.ptr_array(uniq), int(where[TR__ID]), float(max0.item()) + id_offset, gz.data_ptr(), gx.data_ptr(), nxx,
+             C.c_ulonglong(seed), C.c_ulonglong(s._inject_stream))
+    s._inject_stream += n_new
+    s.cols = [uniq[w] for w in where]
+    return n_new
+
+
+def inject_markers_torch(s, tracdens, tracdens_min, generator=None, cell_rows=None, group=None):
     """Marker injection into under-populated cells on the device -- pylamp2.py:594-633.
 
     Every cell with fewer than `tracdens_min` markers receives `tracdens - count` new markers at

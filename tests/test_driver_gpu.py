@@ -146,3 +146,74 @@ def test_injection_matches_reference_counts_and_properties(tmp_path):
     t = np.load(str(tmp_path) + "/tracs.1.npz")
     assert set(g.files) == {"gridz", "gridx", "velz", "velx", "pres", "rho", "temp", "tstep", "time"}
     assert set(t.files) == {"tr_x", "tr_f", "tr_v"} and t["tr_f"].shape[1] == 13
+
+
+def test_fence_disabled_loop_removes_leavers_like_the_reference():
+    """`tracs_fence_enabled = False` (pylamp2.py:563-581): markers beyond the walls are removed, not fenced.  A closed
+    free-slip box does not push markers out by itself, so a few start beyond each wall: they take part in the first
+    marker->grid pass through the ghost-node extension (pylamp_trac.py:207-217; the fused kernel declines, the per-target
+    path runs), get zero velocity from RK (defval 0) and are removed at the end of the step -- the same ids as in the
+    oracle's loop survive."""
+    from pylamp_b200 import driver
+    nx, L, tr_x, tr_f, opts = setups.rayleigh_taylor(ncell=32)
+    d = L[0] / 32
+    tr_x[10:20, 0] = -0.3 * d
+    tr_x[500:507, 1] = L[1] + 0.2 * d
+    tr_x[9000:9005, 0] = L[0] + 0.4 * d
+    tr_x[12000:12003, 1] = -0.1 * d
+    so = O.State(nx, L, tr_x.copy(), tr_f.copy())
+    oo = O.Options(solve=O.solve_refined, tracs_fence_enabled=False, **opts)
+    sg, og = driver.State(nx, L, tr_x, tr_f), driver.Options(tracs_fence_enabled=False, **opts)
+    removed = 0
+    for it in range(2):
+        O.timestep(so, oo)
+        driver.timestep(sg, og)
+        assert sg.ntrac == so.tr_x.shape[0]
+        assert _rel(sg.newvel[0], so.newvel[0]) < 1e-8 and _rel(sg.f_rho, so.f_rho) < 1e-12
+        ids_g, ids_o = sg.cols[O.TR__ID].cpu().numpy().astype(np.int64), so.tr_f[:, O.TR__ID].astype(np.int64)
+        assert np.array_equal(np.sort(ids_g), np.sort(ids_o))
+        removed += sg.stats["removed"]
+        print("step", it + 1, "removed", sg.stats["removed"], "markers", sg.ntrac)
+    assert removed == 25
+
+
+def test_injection_kernels_fill_empty_and_thin_cells():
+    """csrc/inject.cu on a cloud with emptied and thinned cells: every cell below tracdens_min ends with exactly
+    tracdens markers, new markers lie inside their cells, carry the cell mean of the existing markers (NaN for an
+    empty cell, like the reference's 0/0) and ids that continue the reference's way; the same seed reproduces the
+    positions, another seed changes them."""
+    from pylamp_b200 import driver, markers
+    rng = np.random.default_rng(17)
+    ncz, ncx, L = 24, 20, [1.0, 0.8]
+    nx = [ncz + 1, ncx + 1]
+    x, f = setups.lattice_markers(ncz, ncx, L, 4, seed=2)
+    f[:, O.TR_TMP] = rng.uniform(300, 1600, x.shape[0])
+    f[:, O.TR_RH0] = rng.uniform(2000, 3000, x.shape[0])
+    ie = np.floor(ncz * x[:, 0] / L[0]).astype(int)
+    je = np.floor(ncx * x[:, 1] / L[1]).astype(int)
+    kel = ie * ncx + je
+    keep = ~np.isin(kel, [5, 6, 130]) & ~(np.isin(kel, [40, 41, 250, 479]) & (rng.random(x.shape[0]) < 0.7))
+    x, f = x[keep], f[keep]
+    outs = []
+    for seed in (11, 11, 12):
+        so = O.State(nx, L, x.copy(), f.copy())
+        so.kelem, so.count = O.cell_index_count(so.tr_x, nx, L)
+        sg = driver.State(nx, L, x.copy(), f.copy())
+        sg.kelem, sg.count = markers.cell_index_count(sg.tr_x, nx, L)
+        M0 = sg.ntrac
+        np.random.seed(0)
+        n_ref = O.inject_markers(so, 16, 10)
+        n = markers.inject_markers(sg, 16, 10, seed=seed)
+        assert n == n_ref and sg.ntrac == M0 + n == so.tr_x.shape[0]
+        k2, c2 = markers.cell_index_count(sg.tr_x, nx, L)
+        kr, cr = O.cell_index_count(so.tr_x, nx, L)
+        assert np.array_equal(c2.cpu().numpy(), cr)                       # same population per cell
+        newk = k2[M0:].cpu().numpy()
+        assert np.array_equal(np.sort(newk), np.sort(kr[M0:]))
+        # properties and ids of the new markers, cell by cell (the reference appends cell after cell in ascending order)
+        tg, tr = sg.tr_f_host()[M0:], so.tr_f[M0:]
+        og_, or_ = np.lexsort((tg[:, O.TR__ID], newk)), np.lexsort((tr[:, O.TR__ID], kr[M0:]))
+        assert np.allclose(tg[og_], tr[or_], rtol=1e-13, atol=0, equal_nan=True)
+        assert np.isnan(tg[np.isin(newk, [5, 6, 130])][:, O.TR_TMP]).all()
+        outs.append(sg.tr_x[M0:].cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])

@@ -171,12 +171,11 @@ def test_large_random_cloud_vs_oracle(T):
 
 
 @pytest.mark.parametrize("cloud", ["sorted", "random", "faces"])
-def test_rk4_tile_kernel_and_fused_fence_count(T, cloud):
-    """RK4 on staged velocity tiles (rk4_variant 1, default) and the one-marker-per-thread kernel (0) against the
-    oracle's RK -- cell-ordered cloud (tiles), unordered cloud (bounding box too large: global reads), markers on and
-    within a few ulps of cell faces of the centre grid (the exact cell lookup decides) and a time step twice the
-    CFL one (stage positions leave the tile, some leave the grid) -- and plb_rk4_fence_count against the oracle's
-    RK + fence + cell_index_count, bit for bit in the indices."""
+def test_rk4_cell_lookup_on_faces_and_fused_fence_count(T, cloud):
+    """RK4 against the oracle's RK -- cell-ordered and unordered clouds, markers on and within a few ulps of cell
+    faces of the centre grid (the Meyer-Jenny term is discontinuous there: the reference's exact multiply-then-divide
+    cell lookup decides), a time step twice the CFL one (some stage positions leave the grid) -- and
+    plb_rk4_fence_count against the oracle's RK + fence + cell_index_count, bit for bit in the indices."""
     from pylamp_b200 import _lib, setups
     ctx = _lib.default_context()
     rng = np.random.default_rng(31)
@@ -200,14 +199,9 @@ def test_rk4_tile_kernel_and_fused_fence_count(T, cloud):
     for cfl in (0.67, 1.5):
         dt = cfl * (L[0] / ncz) / max(np.abs(newvel[0]).max(), np.abs(newvel[1]).max())
         vr, xr = O.RK(x, ng, vels, nx, dt)
-        for variant in (1, 0):
-            ctx.set_param("rk4_variant", variant)
-            try:
-                vg, xg = T.RK(x, ng, vels, nx, dt)
-            finally:
-                ctx.set_param("rk4_variant", 1)
-            assert np.allclose(xg, xr, rtol=1e-12, atol=1e-15), (cloud, cfl, variant, np.abs(xg - xr).max())
-            assert np.allclose(vg, vr, rtol=1e-9, atol=1e-12 * np.abs(vr).max())
+        vg, xg = T.RK(x, ng, vels, nx, dt)
+        assert np.allclose(xg, xr, rtol=1e-12, atol=1e-15), (cloud, cfl, np.abs(xg - xr).max())
+        assert np.allclose(vg, vr, rtol=1e-9, atol=1e-12 * np.abs(vr).max())
         # fused RK4 + fence + count
         xd = torch.as_tensor(x).cuda()
         v, xn, kelem, count = T.rk4_fence_count_device(ctx, xd, ng, torch.as_tensor(vels[0]).cuda(), torch.as_tensor(vels[1]).cuda(),
