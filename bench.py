@@ -177,6 +177,7 @@ def run_b200(args):
     o.slab_reduce = bool(args.slab_reduce)
     o.slab_local = bool(args.slab_local)
     o.resort_every = args.resort_every
+    o.fused_rk4_fence = bool(args.fused_rk4_fence)
     o.stokes_rtol = args.stokes_rtol
     o.stokes_params = stokes_params(args.warm_start, args.nu, args.gmres_m)
     M = s.ntrac
@@ -369,6 +370,7 @@ def main():
                     help="with --marker-ownership slab --slab-local 0: boundary-row exchange + all-gather instead of the all-reduce")
     ap.add_argument("--resort-every", type=int, default=DEFAULTS["resort_every"],
                     help="re-sort the markers by cell every n-th step (0: never)")
+    ap.add_argument("--fused-rk4-fence", type=int, default=0, help="RK4 + fence + per-cell count in one kernel (1 GPU)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="label of the JSON line: 'strong' = the 4096^2 problem on N GPUs (default); 'weak' when --ncell is "
                          "chosen per N so that the work per GPU stays fixed (SURVEY 8d C5: 4096, 5632, 8192, 11264 cells)")

@@ -602,22 +602,46 @@ k_grid2trac(long long M, const double2* __restrict__ trx, int method, G2TGrid g,
 // (pylamp_trac.py:46-47): evaluated by a multiplication, and re-evaluated with the exact multiply-then-divide
 // whenever the position lies within 1e-7 cells of a face -- the Meyer-Jenny correction of the tangential
 // component is discontinuous across faces, so the cell choice matters there.
-__device__ __forceinline__ long long rk_cell(double v, double v0, double s, double len, int n) {
-    const double t = (v - v0) * s;
-    const double fl = floor(t);
-    const double f = t - fl;
-    if (f < 1e-7 || f > 1.0 - 1e-7) return cell_of(v, v0, len, n);
-    return (long long)fl;
+
+// locate() for the marker-temperature kernels of the time loop: the cell by multiplication (exact re-evaluation
+// within 1e-7 cells of a face, like RK4 -- bilinear interpolation is continuous across faces, so the choice does
+// not even matter here) and the local coordinates by a multiplication with the tabulated reciprocal cell size
+// instead of the reference's (x - g0)/((x - g0) + (g1 - x)) (pylamp_trac.py:74-75): four fp64 divisions per marker
+// less; the two forms differ by a rounding error (1e-16 relative), the public plb_grid2trac keeps the reference's.
+__device__ __forceinline__ Cell locate_fast(const G2TGrid& g, const double* __restrict__ riz, const double* __restrict__ rix,
+                                            double sz, double sx, double z, double x) {
+    Cell c;
+    c.ie = (long long)floor((z - g.z0) * sz);
+    c.je = (long long)floor((x - g.x0) * sx);
+    c.bad = (c.ie < 0) || (c.ie > g.nz - 2) || (c.je < 0) || (c.je > g.nxx - 2);
+    if (c.bad) {                                     // (rare: let the reference's formula decide what is outside)
+        c.ie = cell_of(z, g.z0, g.zlen, g.nz), c.je = cell_of(x, g.x0, g.xlen, g.nxx);
+        c.bad = (c.ie < 0) || (c.ie > g.nz - 2) || (c.je < 0) || (c.je > g.nxx - 2);
+        if (c.bad) c.ie = 0, c.je = 0;
+    }
+    c.dz0 = z - g.gz[c.ie], c.dx0 = x - g.gx[c.je];
+    c.dz1 = 0, c.dx1 = 0;
+    c.dzn = c.dz0 * riz[c.ie];
+    c.dxn = c.dx0 * rix[c.je];
+    return c;
 }
 
-__device__ __forceinline__ void vel_at(const double* __restrict__ fz, const double* __restrict__ fx,
+// EXACT = false: the cell by a multiplication; returns true when the position lies within 1e-7 cells of a face (or
+// outside the grid), where the multiplication may have picked the neighbour of the reference's cell -- and the
+// Meyer-Jenny term is discontinuous across faces.  EXACT = true: the reference's own formula (multiply, then divide,
+// pylamp_trac.py:46-47).  k_rk4 runs the four stages with EXACT = false and repeats the (rare) markers that
+// reported a face with EXACT = true.
+template <bool EXACT>
+__device__ __forceinline__ bool vel_at(const double* __restrict__ fz, const double* __restrict__ fx,
                                        const G2TGrid& g, const double* __restrict__ riz,
                                        const double* __restrict__ rix, double sz, double sx, double z, double x,
                                        double& vz, double& vx) {
-    const long long ie = rk_cell(z, g.z0, sz, g.zlen, g.nz), je = rk_cell(x, g.x0, sx, g.xlen, g.nxx);
+    long long ie, je;
+    if (EXACT) ie = cell_of(z, g.z0, g.zlen, g.nz), je = cell_of(x, g.x0, g.xlen, g.nxx);
+    else ie = (long long)floor((z - g.z0) * sz), je = (long long)floor((x - g.x0) * sx);
     if (ie < 0 || ie > g.nz - 2 || je < 0 || je > g.nxx - 2) {
         vz = 0, vx = 0;                                    // defval=0, :361
-        return;
+        return true;
     }
     const double gz0 = g.gz[ie], gz1 = g.gz[ie + 1], gx0 = g.gx[je], gx1 = g.gx[je + 1];
     const double hz = gz1 - gz0, hx = gx1 - gx0;
@@ -632,6 +656,22 @@ __device__ __forceinline__ void vel_at(const double* __restrict__ fz, const doub
     const double w00 = (1 - dxn) * (1 - dzn), w01 = dxn * (1 - dzn), w10 = (1 - dxn) * dzn, w11 = dxn * dzn;
     vx = w00 * x00 + w01 * x01 + w10 * x10 + w11 * x11 + dxn * (1 - dxn) * c10;
     vz = w00 * z00 + w01 * z01 + w10 * z10 + w11 * z11 + dzn * (1 - dzn) * c20;
+    return fmin(fmin(dzn, 1.0 - dzn), fmin(dxn, 1.0 - dxn)) < 1e-7;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ bool rk4_stages(const double* __restrict__ fz, const double* __restrict__ fx, const G2TGrid& g,
+                                           const double* __restrict__ riz, const double* __restrict__ rix, double sz,
+                                           double sx, double dt, const double2& p, double2& q) {
+    const double hdt = 0.5 * dt, sixth_dt = (1.0 / 6.0) * dt;
+    double k1z, k1x, k2z, k2x, k3z, k3x, k4z, k4x;
+    bool face = vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x, p.y, k1z, k1x);
+    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
+    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
+    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
+    q.x = p.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // :385 (unweighted sum)
+    q.y = p.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
+    return face;
 }
 
 // FENCE: the fence of pylamp2.py:558-572 and the cell index / per-cell count of :588-593 in the same pass (the new
@@ -648,22 +688,14 @@ __global__ void __launch_bounds__(256)
 k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ fz,
       const double* __restrict__ fx, G2TGrid g, const double* __restrict__ riz,
       const double* __restrict__ rix, double dt, double2* __restrict__ xout, double2* __restrict__ vout, FenceArgs fa) {
-    const double hdt = 0.5 * dt;
-    const double sixth_dt = (1.0 / 6.0) * dt;
     const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
     const double rdt = 1.0 / dt;
     const long long ncell = FENCE ? (long long)(fa.nz - 1) * (fa.nxx - 1) : 0;
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
          m += (long long)gridDim.x * blockDim.x) {
-        double2 p = trx[m];
-        double k1z, k1x, k2z, k2x, k3z, k3x, k4z, k4x;
-        vel_at(fz, fx, g, riz, rix, sz, sx, p.x, p.y, k1z, k1x);
-        vel_at(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
-        vel_at(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
-        vel_at(fz, fx, g, riz, rix, sz, sx, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
+        const double2 p = trx[m];
         double2 q;
-        q.x = p.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // :385 (unweighted sum)
-        q.y = p.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
+        if (rk4_stages<false>(fz, fx, g, riz, rix, sz, sx, dt, p, q)) rk4_stages<true>(fz, fx, g, riz, rix, sz, sx, dt, p, q);
         if (vout) {
             double2 v;
             v.x = (q.x - p.x) * rdt;                          // :386
@@ -795,16 +827,18 @@ k_sub(long long M, const double* __restrict__ a, const double* __restrict__ b,
 // subgrid relaxation Tsg = Told - (Told - T1) exp(-d dt / tau), dT = Tsg - T1 (:472-475) with Told = T.
 // One pass over the markers instead of clone + grid2trac + add + stage 1 (same arithmetic).
 __global__ void __launch_bounds__(256)
-k_subgrid_fused1(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ dTg,
+k_subgrid_fused1(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ riz,
+                 const double* __restrict__ rix, const double* __restrict__ dTg,
                  double dt, double fac, const double* __restrict__ T, const double* __restrict__ cp,
                  const double* __restrict__ rho, const double* __restrict__ k, double* __restrict__ Tsg,
                  double* __restrict__ dT, unsigned long long* n_outside) {
     const double d = 0.5;
+    const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
     unsigned bad_local = 0;
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
          m += (long long)gridDim.x * blockDim.x) {
         const double2 p = trx[m];
-        const Cell c = locate(g, p.x, p.y);
+        const Cell c = locate_fast(g, riz, rix, sz, sx, p.x, p.y);
         if (c.bad) {
             bad_local++;
             continue;
@@ -822,13 +856,15 @@ k_subgrid_fused1(long long M, const double2* __restrict__ trx, G2TGrid g, const 
 
 // T = Tsg - interp(f_sgc), pylamp2.py:479-480
 __global__ void __launch_bounds__(256)
-k_subgrid_fused2(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ sgc,
+k_subgrid_fused2(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ riz,
+                 const double* __restrict__ rix, const double* __restrict__ sgc,
                  const double* __restrict__ Tsg, double* __restrict__ T, unsigned long long* n_outside) {
+    const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
     unsigned bad_local = 0;
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
          m += (long long)gridDim.x * blockDim.x) {
         const double2 p = trx[m];
-        const Cell c = locate(g, p.x, p.y);
+        const Cell c = locate_fast(g, riz, rix, sz, sx, p.x, p.y);
         if (c.bad) {
             bad_local++;
             continue;
@@ -1791,19 +1827,25 @@ int plb_subgrid_fused(plb_ctx* ctx, int stage, long long M, const double* d_tr_x
                       long long* h_n_outside) {
     if (!ctx) return 1;
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (plb_ws_reserve(ctx, 64)) return 2;
+    if (plb_ws_reserve(ctx, 64 + (size_t)(nz + nxx) * sizeof(double))) return 2;
     unsigned long long* d_bad = (unsigned long long*)ctx->ws;
+    double* recip = (double*)ctx->ws + 8;
     PLB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->stream));
     G2TGrid g = {d_grid_z, d_grid_x, nz, nxx, ld, z0, zlen, x0, xlen};
     if (M > 0) {
+        k_axis_recip<<<plb_blocks(nz, 256), 256, 0, ctx->stream>>>(nz, d_grid_z, recip, nullptr);
+        PLB_LAUNCHED(ctx);
+        k_axis_recip<<<plb_blocks(nxx, 256), 256, 0, ctx->stream>>>(nxx, d_grid_x, recip + nz, nullptr);
+        PLB_LAUNCHED(ctx);
         plb_prof_scope prof_(ctx, PLB_K_G2T, (stage == 1 ? 64.0 : 32.0) * (double)M);
         const int grid = plb_grid_for(ctx, M, 256, 8);
         if (stage == 1) {
             const double fac = (2 / dx) * (2 / dx) + (2 / dz) * (2 / dz);        // pylamp2.py:473
-            k_subgrid_fused1<<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, g, d_field, dt, fac, d_T, d_cp,
-                                                            d_rho, d_k, d_Tsg, d_dT, d_bad);
+            k_subgrid_fused1<<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, g, recip, recip + nz, d_field, dt, fac,
+                                                            d_T, d_cp, d_rho, d_k, d_Tsg, d_dT, d_bad);
         } else {
-            k_subgrid_fused2<<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, g, d_field, d_Tsg, d_T, d_bad);
+            k_subgrid_fused2<<<grid, 256, 0, ctx->stream>>>(M, (const double2*)d_tr_x, g, recip, recip + nz, d_field, d_Tsg, d_T,
+                                                            d_bad);
         }
         PLB_LAUNCHED(ctx);
     }

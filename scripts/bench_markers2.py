@@ -95,4 +95,9 @@ dt = 0.67 * dz / 1e-9
 for name, x in (("ordered", tr_x), ("displaced", moved)):
     ms = timed(lambda: T.rk4_device(ctx, x, newgrid, vz, vx, [nx[0] + 1, nx[1] + 1], dt))
     res["rk4_" + name] = {"ms": ms, "GBps": 48 * M / ms / 1e6}
+    ms_f = timed(lambda: T.rk4_fence_count_device(ctx, x, newgrid, vz, vx, [nx[0] + 1, nx[1] + 1], dt, nx, L, 2.0 ** -10,
+                                                   want_kelem=False))
+    xq = x.clone()
+    ms_s = timed(lambda: markers.fence_count(xq, nx, L, want_kelem=False))
+    res["rk4_fence_count_" + name] = {"fused_ms": ms_f, "separate_ms": ms + ms_s}
 print(json.dumps(res))

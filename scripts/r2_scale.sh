@@ -1,0 +1,16 @@
+#!/bin/bash
+# strong (4096^2) and weak (4096*sqrt(N) cells, rounded to a multigrid-friendly size) scaling points on N GPUs
+N=$1; WEAK=$2; PORT=${3:-29571}
+run() {  # name, extra args
+  timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 0 --cpu-ncell 0 $2 > gpurun_out/r2_scale_$1_n$N.json 2> gpurun_out/r2_scale_$1_n$N.err
+  python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/r2_scale_$1_n$N.json'))
+    print('$1 N=$N ncell',d['config']['grid_nodes'][0]-1,'value',round(d['value'],2),'ms',round(d['ms_per_step'],2), {k:round(v,2) for k,v in d['phases_ms_per_step'].items()}, d['solver_iterations'][-1])
+except Exception as e:
+    print('$1 N=$N FAILED', e); print(open('gpurun_out/r2_scale_$1_n$N.err').read()[-1500:])
+PY
+}
+run strong ""
+if [ -n "$WEAK" ] && [ "$WEAK" != "0" ]; then PORT=$((PORT+2)); run weak "--ncell $WEAK --scaling weak"; fi
