@@ -319,8 +319,10 @@ def run_e2e(torch, driver, s, o, nsteps):
     marker coordinates and marker temperature go from pinned host memory to the device, the step runs, and the new
     coordinates, marker temperature, marker velocities and the velocity / pressure / temperature grids come back
     (the constant material columns -- rho0, alpha, Ea, eta0, k, Cp, H, material id -- are uploaded once with the
-    set-up, like the grids' axes).  The download of step n's grids overlaps nothing: everything is inside the
-    timed region, one stream, synchronised per step."""
+    set-up, like the grids' axes).  Step n+1 can only start from what step n returned, so upload -> step ->
+    download of (coordinates, temperature) is a serial chain; the outputs that are not fed back (marker velocities,
+    grids) are downloaded on a second stream while the next step's upload runs (PCIe is full duplex).  Everything
+    is inside the timed region; both streams are drained before the clock stops."""
     from pylamp_b200.pylamp_const import TR_TMP
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
     h_x, h_T = pin(s.tr_x), pin(s.cols[TR_TMP])
@@ -328,6 +330,8 @@ def run_e2e(torch, driver, s, o, nsteps):
     h_grids = [torch.empty(tuple(s.nx), dtype=torch.float64, pin_memory=True) for _ in range(4)]
     h2d = (h_x.numel() + h_T.numel()) * 8
     d2h = (h_x.numel() + h_T.numel() + h_v.numel() + 4 * h_grids[0].numel()) * 8
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -335,12 +339,18 @@ def run_e2e(torch, driver, s, o, nsteps):
         s.tr_x.copy_(h_x, non_blocking=True)
         s.cols[TR_TMP].copy_(h_T, non_blocking=True)
         driver.timestep(s, o, want_kelem=False)
+        done = torch.cuda.Event()
+        done.record(main)
+        outs = (s.trac_vel, s.newvel[0], s.newvel[1], s.newpres, s.newtemp)
+        with torch.cuda.stream(side):
+            side.wait_event(done)
+            for h, d in zip([h_v] + h_grids, outs):
+                d.record_stream(side)            # the next step replaces these tensors while the copy may still run
+                h.copy_(d, non_blocking=True)
         h_x.copy_(s.tr_x, non_blocking=True)
         h_T.copy_(s.cols[TR_TMP], non_blocking=True)
-        h_v.copy_(s.trac_vel, non_blocking=True)
-        for h, d in zip(h_grids, (s.newvel[0], s.newvel[1], s.newpres, s.newtemp)):
-            h.copy_(d, non_blocking=True)
-        torch.cuda.synchronize()
+        main.synchronize()                       # the next step starts from h_x, h_T
+    side.synchronize()
     ev1.record()
     torch.cuda.synchronize()
     return {"ms": ev0.elapsed_time(ev1) / nsteps, "h2d": int(h2d), "d2h": int(d2h)}
@@ -370,7 +380,7 @@ def main():
                     help="with --marker-ownership slab --slab-local 0: boundary-row exchange + all-gather instead of the all-reduce")
     ap.add_argument("--resort-every", type=int, default=DEFAULTS["resort_every"],
                     help="re-sort the markers by cell every n-th step (0: never)")
-    ap.add_argument("--fused-rk4-fence", type=int, default=0, help="RK4 + fence + per-cell count in one kernel (1 GPU)")
+    ap.add_argument("--fused-rk4-fence", type=int, default=1, help="RK4 + fence + per-cell count in one kernel (1 GPU)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="label of the JSON line: 'strong' = the 4096^2 problem on N GPUs (default); 'weak' when --ncell is "
                          "chosen per N so that the work per GPU stays fixed (SURVEY 8d C5: 4096, 5632, 8192, 11264 cells)")

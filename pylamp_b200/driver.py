@@ -59,7 +59,7 @@ class Options:
         self.heat_extrapolate = True  # heat solve starts from T + the previous step's increment
         self.resort_every = 0         # > 0: re-order the markers by cell every n-th step (device counting sort)
         self.fused_t2g = True         # the step's marker->grid targets in one pass (plb_trac2grid_fused)
-        self.fused_rk4_fence = False  # RK4 + fence + per-cell count in one pass (plb_rk4_fence_count)
+        self.fused_rk4_fence = True   # RK4 + fence + per-cell count in one pass (plb_rk4_fence_count)
         self.tracdens, self.tracdens_min = 45, 0   # marker injection (pylamp2.py:594-633); 0 = off
         # several ranks: "index" = every rank keeps the markers it started with (any marker may be
         # processed by any rank); "slab" = rank r owns the markers in its cell rows, markers that
@@ -335,8 +335,7 @@ def timestep(s, o, want_kelem=True, phases=False):
     slab = world > 1 and o.marker_ownership == "slab"
     need_kelem = want_kelem or o.tracdens_min > 0
     flowthru = any(int(b) & pylamp_stokes.BC_TYPE_FLOWTHRU for b in o.bcstokes)
-    # (plb_rk4_fence_count -- RK4, fence and per-cell count in one pass -- measured slower on the B200 than the two
-    # kernels, 8.6 vs 8.0 ms at 2.7e8 markers: the fused kernel needs 80 registers instead of 64)
+    # (plb_rk4_fence_count: RK4, fence and per-cell count in one pass -- 8.0 vs 7.2 + 1.5 ms at 2.7e8 markers)
     fused_fence = o.fused_rk4_fence and o.tracs_fence_enabled and not slab and not flowthru
     if fused_fence:
         # RK4, fence and per-cell count in one pass over the markers (the new positions are final there)
