@@ -8,6 +8,9 @@
 // restarted GMRES on the row-scaled system converges in a few tens of iterations independent of
 // the grid size, so no multigrid is needed here.
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include <vector>
 
@@ -108,6 +111,108 @@ k_diff(DiffDev D, const double* __restrict__ x, const double* __restrict__ b, do
     else y[o] = a / r.cC;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Chebyshev-Jacobi iteration for the heat system (the default path of plb_diff_solve).
+//
+// Every wall row is an explicit relation between a wall node and its normal neighbour (FIXTEMP: T_w = value;
+// FIXFLOW: k (T_1 - T_0)/d = value; the z-walls own the corners, pylamp_diff.py:99-152), so the wall nodes are
+// eliminated: they are kept consistent with their interior neighbours ("slaves"), and the iteration runs on the
+// interior rows, whose eliminated diagonal is diag' = cC + sum over FIXFLOW wall neighbours of their coefficient.
+// Row-scaled by diag' the eliminated operator is I + N with ||N||_inf = rho = max_i S_i / (S_i + 1) < 1, S_i = the
+// row's sum of interior off-diagonal coefficients (dt <= 0.67 dx^2 / max(2 kappa) in the time loop gives
+// rho ~ 0.57): the spectrum lies in [1 - rho, 1 + rho], which is all a Chebyshev iteration needs -- no inner
+// products, no host read-back per iteration, one halo exchange per sweep on several GPUs.
+// ---------------------------------------------------------------------------------------------
+struct WallRel {       // T_wall = a + b * T_neighbour
+    double a, b;
+};
+
+// relation of wall node (iw, jw) to its normal neighbour (from the wall row)
+__device__ __forceinline__ WallRel wall_rel(const DiffDev& D, int iw, int jw) {
+    const Row r = diff_row(D, iw, jw);
+    const double off = r.cE + r.cW + r.cS + r.cN;      // a wall row has at most one off-diagonal entry
+    WallRel w;
+    w.a = r.rhs / r.cC, w.b = -off / r.cC;
+    return w;
+}
+
+__device__ __forceinline__ bool is_wall(const DiffDev& D, int i, int j) {
+    return i == 0 || i == D.nz - 1 || j == 0 || j == D.nxx - 1;
+}
+
+// eliminated diagonal and Gershgorin radius of interior row (i,j)
+__device__ __forceinline__ void elim_row(const DiffDev& D, const Row& r, int i, int j, double& diag, double& offsum) {
+    diag = r.cC, offsum = 0;
+    if (j == 1) diag += r.cW * wall_rel(D, i, 0).b; else offsum += fabs(r.cW);
+    if (j == D.nxx - 2) diag += r.cE * wall_rel(D, i, D.nxx - 1).b; else offsum += fabs(r.cE);
+    if (i == 1) diag += r.cN * wall_rel(D, 0, j).b; else offsum += fabs(r.cN);
+    if (i == D.nz - 2) diag += r.cS * wall_rel(D, D.nz - 1, j).b; else offsum += fabs(r.cS);
+}
+
+// the wall nodes next to interior node (i,j), from its value v: x-wall nodes first, then the z-wall nodes incl. the
+// corners (a corner's z-wall row refers to the x-wall node of the row next to it)
+__device__ __forceinline__ void write_slaves(const DiffDev& D, double* __restrict__ x, int i, int j, double v) {
+    const int nz = D.nz, nxx = D.nxx, ld = D.ld;
+    const long long o = (long long)i * ld + j;
+    double vl = 0, vr = 0;
+    if (j == 1) { const WallRel w = wall_rel(D, i, 0); vl = w.a + w.b * v; x[o - 1] = vl; }
+    if (j == nxx - 2) { const WallRel w = wall_rel(D, i, nxx - 1); vr = w.a + w.b * v; x[o + 1] = vr; }
+    if (i == 1) {
+        const WallRel w = wall_rel(D, 0, j);
+        x[o - ld] = w.a + w.b * v;
+        if (j == 1) { const WallRel c = wall_rel(D, 0, 0); x[o - ld - 1] = c.a + c.b * vl; }
+        if (j == nxx - 2) { const WallRel c = wall_rel(D, 0, nxx - 1); x[o - ld + 1] = c.a + c.b * vr; }
+    }
+    if (i == nz - 2) {
+        const WallRel w = wall_rel(D, nz - 1, j);
+        x[o + ld] = w.a + w.b * v;
+        if (j == 1) { const WallRel c = wall_rel(D, nz - 1, 0); x[o + ld - 1] = c.a + c.b * vl; }
+        if (j == nxx - 2) { const WallRel c = wall_rel(D, nz - 1, nxx - 1); x[o + ld + 1] = c.a + c.b * vr; }
+    }
+}
+
+// MODE 0: make the wall nodes of x consistent with its interior values.  MODE 1: one Chebyshev-Jacobi step
+// d = cd d + cr diag'^-1 (b - A x), xout = x + d (FIRST: d = cr ...).  MODE 2: rho = max radius (atomic max into out).
+template <int MODE>
+__global__ void __launch_bounds__(BX* BY)
+k_diff_cheb(DiffDev D, const double* x, const double* __restrict__ b, double* __restrict__ d,
+            double* xout, double cd, double cr, int first, double* __restrict__ out) {      // (MODE 0: xout == x)
+    const int j = blockIdx.x * BX + threadIdx.x, i = D.i0 + blockIdx.y * BY + threadIdx.y;
+    double rad = 0;
+    if (i < D.i1 && j < D.nxx && !is_wall(D, i, j)) {
+        const long long o = (long long)i * D.ld + j;
+        if (MODE == 0) {
+            write_slaves(D, xout, i, j, x[o]);
+        } else {
+            const Row r = diff_row(D, i, j);
+            double diag, offsum;
+            elim_row(D, r, i, j, diag, offsum);
+            if (MODE == 2) {
+                rad = offsum / fabs(diag);
+            } else {
+                const double res = ((b ? b[o] : r.rhs) - row_apply(D, r, x, i, j)) / diag;
+                const double dn = first ? cr * res : cd * d[o] + cr * res;
+                d[o] = dn;
+                const double v = x[o] + dn;
+                xout[o] = v;
+                write_slaves(D, xout, i, j, v);
+            }
+        }
+    }
+    if (MODE == 2) {
+        rad = warp_max(rad);
+        __shared__ double sm[BX * BY / 32];
+        const int t = threadIdx.y * BX + threadIdx.x;
+        if ((t & 31) == 0) sm[t >> 5] = rad;
+        __syncthreads();
+        if (t == 0) {
+            for (int q = 1; q < BX * BY / 32; q++) rad = fmax(rad, sm[q]);
+            atomic_max_double(out, rad);
+        }
+    }
+}
+
 }  // namespace
 
 struct plb_diff {
@@ -128,6 +233,10 @@ struct plb_diff {
     size_t plane = 0;                      // local plane size
     long long shift = 0;
     int m = 40;
+    int use_cheb = 1;                      // Chebyshev-Jacobi on the wall-eliminated system (fallback: GMRES)
+    double *cd_ = nullptr, *cx2 = nullptr; // Chebyshev direction and second iterate (local planes)
+    int last_sweeps = 0;
+    double last_rho = 0;
     const double* guess = nullptr;         // full-size initial guess for the next solve (NULL: T)
     int last_iters = 0;
     double last_relres = 0;
@@ -169,6 +278,7 @@ int plb_diff_create(plb_ctx* ctx, int nz, int nxx, int ld, const double* h_grid_
     }
     PLB_CUDA(ctx, cudaMalloc(&op->d_scal, sizeof(double) * 1024));
     const int R = plb_comm_size(ctx), rank = plb_comm_rank(ctx);
+    if (const char* e = getenv("PLB_DIFF_GMRES")) op->use_cheb = atoi(e) ? 0 : 1;     // A/B switch: GMRES only
     op->dist = R > 1 && nz >= 4 * R;
     op->slab_fields = op->dist && ctx->slab_on;
     if (op->slab_fields) {
@@ -198,7 +308,7 @@ void plb_diff_destroy(plb_diff* op) {
     if (!op) return;
     cudaSetDevice(op->device);
     cudaDeviceSynchronize();
-    double* ptrs[] = {op->idz, op->idx, op->idzm, op->idxm, op->d_scal, op->xs, op->xl};
+    double* ptrs[] = {op->idz, op->idx, op->idzm, op->idxm, op->d_scal, op->xs, op->xl, op->cd_, op->cx2};
     for (double* p : ptrs) if (p) cudaFree(p);
     plb_fgmres_free(&op->kry);
     plb_reduce_ws_free(&op->rws);
@@ -282,6 +392,69 @@ int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, do
     PLB_CUDA(ctx, cudaMemcpyAsync(x, (op->guess ? op->guess : D.T) + sh, sizeof(double) * n,
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     op->guess = nullptr;
+    plb_fgmres_result res;
+    bool done = false;
+    op->last_sweeps = 0;
+    // wall rows with a dependent right-hand side (a caller-supplied b) keep the general path
+    if (op->use_cheb && bnorm > 0 && !d_rhs) {
+        if (!op->cd_) {
+            PLB_CUDA(ctx, cudaMalloc(&op->cd_, sizeof(double) * op->plane));
+            PLB_CUDA(ctx, cudaMalloc(&op->cx2, sizeof(double) * op->plane));
+        }
+        // the rows whose unknown this rank iterates on: its own rows; wall rows are written by their neighbours
+        double* s2 = op->d_scal + 910;
+        PLB_CUDA(ctx, cudaMemsetAsync(s2, 0, sizeof(double), ctx->stream));
+        k_diff_cheb<2><<<g, blk, 0, ctx->stream>>>(D, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, s2);
+        PLB_LAUNCHED(ctx);
+        if (plb_comm_allreduce(ctx, s2, 1, PLB_OP_MAX)) return 2;
+        // consistent wall values for the start vector, then its residual
+        k_diff_cheb<0><<<g, blk, 0, ctx->stream>>>(D, x - sh, nullptr, nullptr, x - sh, 0, 0, 0, nullptr);
+        PLB_LAUNCHED(ctx);
+        if (resid_of(x, op->xs)) return 2;
+        if (plb_dot(ctx, &op->rws, n, op->xs, op->xs, op->d_scal + 911)) return 2;
+        double h[2];
+        if (plb_read_scalars(ctx, op->d_scal + 910, 2, h)) return 2;
+        const double rho = h[0];
+        double rel = sqrt(h[1]) / bnorm;
+        op->last_rho = rho;
+        if (rho < 0.97 && rel == rel) {
+            const double lmin = 1 - rho, lmax = 1 + rho;
+            const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+            const double sigma1 = theta / delta;                       // > 1
+            const double conv = sigma1 - sqrt(sigma1 * sigma1 - 1);    // asymptotic factor per sweep
+            double* cur = x;
+            double* oth = op->cx2;
+            for (int round = 0; round < 4 && rel > rtol && res.iters < maxit; round++) {
+                // sweeps for the reduction still needed (Chebyshev bound 2 conv^n), a few to spare
+                int nsw = rho > 1e-14 ? (int)ceil(log(2.0 * rel / (0.5 * rtol)) / -log(conv)) + 1 : 2;
+                nsw = std::max(2, std::min(nsw, maxit - res.iters));
+                double rk = 1.0 / sigma1;
+                for (int k = 0; k < nsw; k++) {
+                    double cd, cr;
+                    if (k == 0) cd = 0, cr = 1.0 / theta;
+                    else {
+                        const double rn = 1.0 / (2 * sigma1 - rk);
+                        cd = rn * rk, cr = 2 * rn / delta, rk = rn;
+                    }
+                    if (halo(cur)) return 2;
+                    // (the other buffer's wall rows not adjacent to this rank's rows are never read)
+                    k_diff_cheb<1><<<g, blk, 0, ctx->stream>>>(D, cur - sh, nullptr, op->cd_ - sh, oth - sh, cd, cr, k == 0, nullptr);
+                    PLB_LAUNCHED(ctx);
+                    std::swap(cur, oth);
+                }
+                res.iters += nsw;
+                if (resid_of(cur, op->xs)) return 2;
+                if (plb_dot(ctx, &op->rws, n, op->xs, op->xs, op->d_scal + 911)) return 2;
+                if (plb_read_scalars(ctx, op->d_scal + 911, 1, h)) return 2;
+                rel = sqrt(h[0]) / bnorm;
+            }
+            if (cur != x) PLB_CUDA(ctx, cudaMemcpyAsync(x, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+            op->last_sweeps = res.iters;
+            res.relres = rel;
+            res.converged = rel <= rtol;
+            done = res.converged;
+        }
+    }
     auto apply = [&](const double* z, double* w) -> int {
         if (halo(const_cast<double*>(z))) return 2;
         k_diff<3><<<g, blk, 0, ctx->stream>>>(D, z - sh, nullptr, w - sh);
@@ -289,10 +462,13 @@ int plb_diff_solve(plb_diff* op, const double* d_rhs, double rtol, int maxit, do
         return 0;
     };
     auto precond = [&](const double* v, double* z) -> int { return plb_copy(ctx, n, v, z); };
-    plb_fgmres_result res;
     op->kry.pyth_thresh = 0.5;      // rtol is near the fp64 limit here: keep the Arnoldi norms exact
-    if (bnorm > 0) {
+    if (done) {
+        // converged by the Chebyshev iteration
+    } else if (bnorm > 0) {
+        const int spent = res.iters;
         if (plb_fgmres(ctx, &op->rws, &op->kry, residual, apply, precond, x, bnorm, rtol, maxit, &res)) return 2;
+        res.iters += spent;
     } else {
         PLB_CUDA(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
         res.converged = true;

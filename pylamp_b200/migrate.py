@@ -25,6 +25,14 @@ import torch
 import torch.distributed as dist
 
 SLACK = 0.02      # spare capacity kept when a marker array has to grow
+GRANULE = 1 << 20  # capacities are rounded up to this many rows: a slab's marker count changes by a few rows every step,
+                   # and allocations of ever-changing sizes defeat the caching allocator (measured on 4 GPUs: 12 ms per
+                   # step of cudaMalloc/cudaFree in the RK4 phase)
+
+
+def _capacity(n, slack=SLACK):
+    cap = int(n) + int(n * slack) + 1024
+    return ((cap + GRANULE - 1) // GRANULE) * GRANULE if cap > GRANULE else cap
 
 
 def slab_bounds(ncell_z, world):
@@ -56,7 +64,7 @@ def resize_rows(t, n, slack=SLACK):
     need = (t.storage_offset() + n * row) * t.element_size()
     if t.is_contiguous() and st.nbytes() >= need:
         return t.new_empty(0).set_(st, t.storage_offset(), (n,) + tuple(t.shape[1:]))
-    cap = n + int(n * slack) + 1024
+    cap = _capacity(n, slack)
     new = torch.empty((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     new[:t.shape[0]] = t
     return new[:n]
@@ -64,7 +72,7 @@ def resize_rows(t, n, slack=SLACK):
 
 def empty_rows(n, tail_shape, dtype, device, slack=SLACK):
     """Uninitialised (n, *tail_shape) view of an allocation with spare capacity."""
-    cap = int(n) + int(n * slack) + 1024
+    cap = _capacity(n, slack)
     return torch.empty((cap,) + tuple(tail_shape), dtype=dtype, device=device)[:int(n)]
 
 
