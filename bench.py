@@ -207,11 +207,14 @@ def run_b200(args):
     iters = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    phase_ms = {}
+    phase_ms, step_ms, step_rk4 = {}, [], []
     for _ in range(args.steps):
         driver.timestep(s, o, want_kelem=False, phases=True)
         iters.append(dict(s.stats))
-        for k, v in s.phases.result().items():
+        pr = s.phases.result()
+        step_ms.append(round(sum(pr.values()), 2))
+        step_rk4.append(round(pr.get("advect_rk4", 0.0), 2))
+        for k, v in pr.items():
             phase_ms[k] = phase_ms.get(k, 0.0) + v / args.steps
         for k, (c, ms, by) in ctx.profile_read().items():
             a = prof.setdefault(k, [0, 0.0, 0.0])
@@ -298,6 +301,7 @@ def run_b200(args):
             "stokes_dof_per_s": 3.0 * N / (ms_step * 1e-3),
             "solver_iterations": iters, "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_stencil": roofline_stencil, "phases_ms_per_step": phase_ms,
+            "ms_of_each_timed_step": step_ms, "advect_rk4_ms_of_each_timed_step": step_rk4,
             "kernel_breakdown": breakdown}
     if e2e is not None:
         line["e2e"] = {"value": 1.0 / (e2e["ms"] * 1e-3), "unit": "timesteps/s",

@@ -91,6 +91,13 @@ int plb_allreduce(plb_ctx* ctx, double* d_buf, long long count, int op);
  * i1 <= i0 switches back to replicated fields.  plb_halo_rows: exchange `h` halo rows of narr full-size arrays
  * (h_row_doubles[a] doubles per row) with both z-neighbours, one NCCL group. */
 int plb_ctx_set_slab(plb_ctx* ctx, int i0, int i1, int halo);
+/* Removal of the markers beyond the box, pylamp2.py:563-581 (fence disabled, or a flow-through wall: the reference
+ * flags them TR__ID = -1 and np.delete's their rows from tr_x, tr_f, trac_vel).  All arrays (coordinates first; rows of
+ * 1 or 2 doubles) lose the same rows: survivors of the tail move into the holes -- marker order is free --, *h_M_new
+ * rows remain in use. */
+int plb_delete_outside(plb_ctx* ctx, long long M, int narr, double* const* h_arrs, const int* h_width, double Lz, double Lx,
+                       long long* h_M_new);
+
 /* Marker injection into under-populated cells, pylamp2.py:594-633 (the reference's Python loop with np.append per
  * cell).  plb_inject_plan: among the cells [cell0, cell1) (a slab serves its own rows) those with fewer than
  * tracdens_min markers receive tracdens - count new ones; h_out[3] = {deficient cells, markers to add, sum of

@@ -37,6 +37,7 @@ _PROTOS = {
     "plb_ctx_set_slab": (I, [VP, I, I, I]),
     "plb_inject_plan": (I, [VP, LL, VP, I, I, LL, LL, C.POINTER(LL)]),
     "plb_inject_apply": (I, [VP, LL, VP, VP, VP, I, PP, I, D, VP, VP, I, C.c_ulonglong, C.c_ulonglong]),
+    "plb_delete_outside": (I, [VP, LL, I, PP, IP, D, D, C.POINTER(LL)]),
     "plb_migrate_plan": (I, [VP, LL, VP, I, D, I, I, C.POINTER(LL)]),
     "plb_migrate_apply": (I, [VP, LL, I, PP, IP, LL, I, D, I, I, C.POINTER(LL)]),
     "plb_halo_rows": (I, [VP, I, PP, C.POINTER(LL), I, I, I]),

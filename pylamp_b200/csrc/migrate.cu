@@ -109,6 +109,28 @@ k_mig_fill(int n, const int* __restrict__ dst, const int* __restrict__ src, MigA
     }
 }
 
+// markers beyond the box (pylamp2.py:563-571: x <= 0 or x >= L in either direction)
+__device__ __forceinline__ bool outside_box(const double2 p, double Lz, double Lx) {
+    return p.x <= 0 || p.x >= Lz || p.y <= 0 || p.y >= Lx;
+}
+
+__global__ void __launch_bounds__(256)
+k_del_list(long long M, const double2* __restrict__ trx, double Lz, double Lx, int* __restrict__ idx, long long cap,
+           int* __restrict__ counts) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x)
+        if (outside_box(trx[m], Lz, Lx)) {
+            const int slot = atomicAdd(counts, 1);
+            if (slot < cap) idx[slot] = (int)m;
+        }
+}
+
+__global__ void __launch_bounds__(256)
+k_del_tail(long long M_new, long long M, const double2* __restrict__ trx, double Lz, double Lx, int* __restrict__ tail,
+           int* __restrict__ counts) {
+    for (long long m = M_new + blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x)
+        if (!outside_box(trx[m], Lz, Lx)) tail[atomicAdd(counts + 4, 1)] = (int)m;
+}
+
 template <typename T>
 int grow(plb_ctx* ctx, T** p, size_t* cap, size_t need) {
     if (need <= *cap) return 0;
@@ -255,6 +277,90 @@ int plb_migrate_apply(plb_ctx* ctx, long long M, int narr, double* const* h_arrs
         k_mig_fill<<<plb_grid_for(ctx, n_tail, 256, 4), 256, 0, ctx->stream>>>(n_tail, w->low + n_arr, w->tail, A);
         PLB_LAUNCHED(ctx);
     }
+    return 0;
+}
+
+// Removes the markers beyond the box from all arrays (pylamp2.py:563-581: with the fence disabled, or beyond a
+// flow-through wall, the reference flags them TR__ID = -1 and np.delete's their rows): the survivors of the tail move
+// into the holes (marker order is free), *h_M_new rows remain.  Coordinates first in h_arrs.  Synchronises twice.
+int plb_delete_outside(plb_ctx* ctx, long long M, int narr, double* const* h_arrs, const int* h_width, double Lz, double Lx,
+                       long long* h_M_new) {
+    if (!ctx || !h_M_new) return 1;
+    if (M >= (1LL << 31)) PLB_FAIL(ctx, "plb_delete_outside: too many markers for the 32-bit index lists");
+    if (narr < 1 || narr > 20 || h_width[0] != 2) PLB_FAIL(ctx, "plb_delete_outside: 1..20 arrays, coordinates first");
+    PLB_CUDA(ctx, cudaSetDevice(ctx->device));
+    *h_M_new = M;
+    if (M <= 0) return 0;
+    if (!ctx->mig) ctx->mig = new plb_migrate_ws();
+    plb_migrate_ws* w = ctx->mig;
+    if (!w->counts) {
+        PLB_CUDA(ctx, cudaMalloc(&w->counts, 8 * sizeof(int)));
+        PLB_CUDA(ctx, cudaMalloc(&w->xcnt, 8 * sizeof(double)));
+    }
+    const long long cap = M / 8 + 4096;
+    if (cap > w->cap_idx) {
+        PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int d = 0; d < 2; d++) {
+            if (w->idx[d]) cudaFree(w->idx[d]);
+            w->idx[d] = nullptr;
+            PLB_CUDA(ctx, cudaMalloc(&w->idx[d], (size_t)cap * sizeof(int)));
+        }
+        w->cap_idx = cap;
+    }
+    MigArrays A;
+    A.n = narr, A.W = 0;
+    for (int a = 0; a < narr; a++) {
+        if (h_width[a] != 1 && h_width[a] != 2) PLB_FAIL(ctx, "plb_delete_outside: width must be 1 or 2");
+        A.p[a] = h_arrs[a], A.w[a] = h_width[a], A.off[a] = A.W, A.W += h_width[a];
+    }
+    const double2* x = (const double2*)h_arrs[0];
+    PLB_CUDA(ctx, cudaMemsetAsync(w->counts, 0, 8 * sizeof(int), ctx->stream));
+    k_del_list<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, x, Lz, Lx, w->idx[0], w->cap_idx, w->counts);
+    PLB_LAUNCHED(ctx);
+    int hc[5];
+    PLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 32, w->counts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(hc, ctx->h_pinned + 32, sizeof(int));
+    const long long n_del = hc[0];
+    if (n_del == 0) return 0;
+    if (n_del > w->cap_idx) {
+        // more than an eighth of the cloud is outside: list them all (rare: a second pass with a full-size list)
+        PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int d = 0; d < 2; d++) {
+            cudaFree(w->idx[d]);
+            w->idx[d] = nullptr;
+            PLB_CUDA(ctx, cudaMalloc(&w->idx[d], (size_t)(n_del + 1024) * sizeof(int)));
+        }
+        w->cap_idx = n_del + 1024;
+        PLB_CUDA(ctx, cudaMemsetAsync(w->counts, 0, 8 * sizeof(int), ctx->stream));
+        k_del_list<<<plb_grid_for(ctx, M, 256, 8), 256, 0, ctx->stream>>>(M, x, Lz, Lx, w->idx[0], w->cap_idx, w->counts);
+        PLB_LAUNCHED(ctx);
+    }
+    const long long M_new = M - n_del;
+    if ((long long)n_del + 2 > w->cap_low) {
+        PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (w->low) cudaFree(w->low);
+        if (w->tail) cudaFree(w->tail);
+        w->low = w->tail = nullptr;
+        const size_t want = (size_t)n_del + n_del / 4 + 1024;
+        PLB_CUDA(ctx, cudaMalloc(&w->low, want * sizeof(int)));
+        PLB_CUDA(ctx, cudaMalloc(&w->tail, want * sizeof(int)));
+        w->cap_low = (long long)want;
+    }
+    k_mig_low_holes<<<plb_grid_for(ctx, n_del, 256, 4), 256, 0, ctx->stream>>>((int)n_del, w->idx[0], 0, w->idx[1], M_new, w->low,
+                                                                            w->counts);
+    PLB_LAUNCHED(ctx);
+    k_del_tail<<<plb_grid_for(ctx, M - M_new, 256, 4), 256, 0, ctx->stream>>>(M_new, M, x, Lz, Lx, w->tail, w->counts);
+    PLB_LAUNCHED(ctx);
+    PLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 32, w->counts + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(hc, ctx->h_pinned + 32, 2 * sizeof(int));
+    if (hc[0] != hc[1]) PLB_FAIL(ctx, "plb_delete_outside: internal: %d holes below the new end, %d survivors beyond it", hc[0], hc[1]);
+    if (hc[0] > 0) {
+        k_mig_fill<<<plb_grid_for(ctx, hc[0], 256, 4), 256, 0, ctx->stream>>>(hc[0], w->low, w->tail, A);
+        PLB_LAUNCHED(ctx);
+    }
+    *h_M_new = M_new;
     return 0;
 }
 

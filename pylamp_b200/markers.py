@@ -48,20 +48,41 @@ def fence_count(tr_x, nx, L, eps=EPS, want_kelem=True):
 
 
 def delete_outside(s):
-    """With the fence disabled the reference removes every marker that left the box
-    (pylamp2.py:563-581: x <= 0 or x >= L in either direction -> TR__ID = -1 -> np.delete on tr_x,
-    tr_f and trac_vel).  Same set of survivors here; the survivors of the tail are moved into the
-    holes instead of shifting every array (marker order is free: every kernel is order-independent).
-    Device-side torch plumbing (one pass over the coordinates, O(removed) entries moved).
+    """With the fence disabled (or beyond a flow-through wall) the reference removes every marker that left the box
+    (pylamp2.py:563-581: x <= 0 or x >= L in either direction -> TR__ID = -1 -> np.delete on tr_x, tr_f and
+    trac_vel).  Same set of survivors here; the survivors of the tail are moved into the holes instead of shifting
+    every array (marker order is free: every kernel is order-independent).  CUDA state: the library's kernels
+    (plb_delete_outside, csrc/migrate.cu); CPU tensors (host-logic tests): torch indexing.
     Returns the number of markers removed."""
-    from .migrate import compaction_plan
+    from .migrate import _distinct, compaction_plan
     x, L = s.tr_x, s.L
+    M = int(x.shape[0])
+    vel = getattr(s, "trac_vel", None)
+    if vel is not None and vel.shape[0] != M:
+        vel = None
+    uniq, where = _distinct(s.cols)
+    if x.is_cuda:
+        arrays = [x if x.is_contiguous() else x.contiguous()] + [c if c.is_contiguous() else c.contiguous() for c in uniq]
+        if vel is not None:
+            arrays.append(vel if vel.is_contiguous() else vel.contiguous())
+        widths = [1 if t.dim() == 1 else int(t.shape[1]) for t in arrays]
+        M_new = C.c_longlong(0)
+        _ctx(x).call("plb_delete_outside", M, len(arrays), _lib.ptr_array(arrays), _lib.int_array(widths), float(L[IZ]),
+                     float(L[IX]), C.byref(M_new))
+        n = int(M_new.value)
+        arrays = [t[:n] for t in arrays]
+        s.tr_x = arrays[0]
+        new_uniq = arrays[1:1 + len(uniq)]
+        s.cols = [new_uniq[w] for w in where]
+        if vel is not None:
+            s.trac_vel = arrays[-1]
+        return M - n
     outside = (x[:, 0] <= 0) | (x[:, 0] >= L[IZ]) | (x[:, 1] <= 0) | (x[:, 1] >= L[IX])
     holes = torch.nonzero(outside).flatten()
     n = int(holes.numel())
     if n == 0:
         return 0
-    M_new, _, src, dst = compaction_plan(int(x.shape[0]), holes, outside, 0)
+    M_new, _, src, dst = compaction_plan(M, holes, outside, 0)
 
     def cut(t):
         if src.numel():
@@ -69,15 +90,10 @@ def delete_outside(s):
         return t[:M_new]
 
     s.tr_x = cut(s.tr_x)
-    seen, cols = {}, []
-    for c in s.cols:                      # columns may alias each other
-        key = c.data_ptr()
-        if key not in seen:
-            seen[key] = cut(c)
-        cols.append(seen[key])
-    s.cols = cols
-    if getattr(s, "trac_vel", None) is not None:
-        s.trac_vel = cut(s.trac_vel)
+    new_uniq = [cut(c) for c in uniq]
+    s.cols = [new_uniq[w] for w in where]
+    if vel is not None:
+        s.trac_vel = cut(vel)
     return n
 
 
