@@ -968,9 +968,8 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
     const bool ws = t.ws != 0;
     const int b0 = PARTS == 1 ? 0 : (len * part) / PARTS, sub = (PARTS == 1 ? len : (len * (part + 1)) / PARTS) - b0;
     const double2* px = sx + s + b0;
-    const double* cf[NF];
-#pragma unroll
-    for (int f = 0; f < NF; f++) cf[f] = sv + t.col[f] * NM + s + b0;
+    // the fields of a task are staged in consecutive columns (host side): one address, NF immediate offsets
+    const double* cf0 = sv + t.col[0] * NM + s + b0;
     // The lanes of a warp walk different runs.  Each starts at the marker whose shared-memory bank matches its
     // lane number and wraps around, so that the 16 lanes of a memory phase read 16 different banks whatever the
     // run starts are (a linear walk of freshly sorted runs, which start 16 markers apart, would put all lanes
@@ -985,7 +984,7 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
         const double2 pa = px[idx], pb = px[idx2];
         double va[NF], vb[NF];
 #pragma unroll
-        for (int f = 0; f < NF; f++) va[f] = cf[f][idx], vb[f] = cf[f][idx2];
+        for (int f = 0; f < NF; f++) va[f] = cf0[f * NM + idx], vb[f] = cf0[f * NM + idx2];
         double wza[RZ], wxa[RX], wzb[RZ], wxb[RX];
         tf_axis_weights<RZ>(pa.x, tz0, tz1, wza);
         tf_axis_weights<RX>(pa.y, tx0, tx1, wxa);
@@ -996,7 +995,7 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
 #pragma unroll
             for (int c = 0; c < RX; c++) {
                 const double w1 = wxa[c] * wza[r], w2 = wxb[c] * wzb[r];       // :252-255
-                if (ws) W[r * RX + c] += w1, W[r * RX + c] += w2;
+                W[r * RX + c] += w1, W[r * RX + c] += w2;       // (kept even when the weight sums go unused: no selects)
 #pragma unroll
                 for (int f = 0; f < NF; f++) {
                     A[f][r * RX + c] = fma(va[f], w1, A[f][r * RX + c]);
@@ -1010,7 +1009,7 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
         const double2 p = px[idx];
         double v[NF];
 #pragma unroll
-        for (int f = 0; f < NF; f++) v[f] = cf[f][idx];
+        for (int f = 0; f < NF; f++) v[f] = cf0[f * NM + idx];
         double wz[RZ], wx[RX];
         tf_axis_weights<RZ>(p.x, tz0, tz1, wz);
         tf_axis_weights<RX>(p.y, tx0, tx1, wx);
@@ -1019,7 +1018,7 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
 #pragma unroll
             for (int c = 0; c < RX; c++) {
                 const double w = wx[c] * wz[r];
-                if (ws) W[r * RX + c] += w;
+                W[r * RX + c] += w;
 #pragma unroll
                 for (int f = 0; f < NF; f++) A[f][r * RX + c] = fma(v[f], w, A[f][r * RX + c]);
             }
@@ -1060,7 +1059,7 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
             for (int c = 0; c < 4; c++) {
                 if (ws) atomicAdd(t.wsum + o4[c], w4[c]);
 #pragma unroll
-                for (int f = 0; f < NF; f++) atomicAdd(t.acc[f] + o4[c], sv[t.col[f] * NM + s + it] * w4[c]);
+                for (int f = 0; f < NF; f++) atomicAdd(t.acc[f] + o4[c], sv[(t.col[0] + f) * NM + s + it] * w4[c]);
             }
         }
         return;
@@ -1071,7 +1070,7 @@ __device__ __forceinline__ void tf_run(const TFArgs& a, const TFTask& t, const d
         for (int c = 0; c < RX; c++) {
             const long long o = base + (long long)r * t.nxe + c;
             // (3-wide patterns: a destination none of the run's markers reaches keeps exact zeros -- nothing to add)
-            const bool any = (RZ == 2 && RX == 2) || W[r * RX + c] != 0.0 || !ws;
+            const bool any = (RZ == 2 && RX == 2) || W[r * RX + c] != 0.0;
             if (ws && any) atomicAdd(t.wsum + o, W[r * RX + c]);
 #pragma unroll
             for (int f = 0; f < NF; f++)
@@ -1455,20 +1454,22 @@ int plb_trac2grid_fused(plb_ctx* ctx, long long M, const double* d_tr_x, int nz,
             TFTask& t = a.t[a.nt++];
             t.type = type, t.nf = std::min(per, T.k - f0), t.ws = f0 == 0;
             t.lz = T.crop_z0 - (sz_ ? 1 : 0), t.lx = T.crop_x0 - (sx_ ? 1 : 0), t.nxe = T.nxe;
+            // the kernel addresses a task's fields as staged columns col[0], col[0]+1, ...: a single-field task
+            // shares an already staged column; a multi-field task takes a fresh run of columns (a column that
+            // two multi-field tasks share is staged twice -- not a pattern of the time loop)
             for (int f = 0; f < t.nf; f++) {
                 const double* p = T.fields[f0 + f];
                 const bool lg = !(T.scheme[f0 + f] & PLB_AVG_ARITHMETIC);
                 int c = -1;
-                for (int q = 0; q < a.ncol; q++)
-                    if (a.col[q] == p) c = q;
+                if (t.nf == 1)
+                    for (int q = 0; q < a.ncol; q++)
+                        if (a.col[q] == p && lg == (((a.logmask >> q) & 1u) != 0)) c = q;
                 if (c < 0) {
                     if (a.ncol >= TF_MAXC) return 3;
                     c = a.ncol++;
                     a.col[c] = p;
                     if (lg) a.logmask |= 1u << c;
                     aligned = aligned && ((uintptr_t)p & 15) == 0;
-                } else if (lg != (((a.logmask >> c) & 1u) != 0)) {
-                    return 3;                                    // one column, two different transforms
                 }
                 t.col[f] = c;
             }
