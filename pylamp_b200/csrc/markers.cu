@@ -608,22 +608,34 @@ k_grid2trac(long long M, const double2* __restrict__ trx, int method, G2TGrid g,
 // not even matter here) and the local coordinates by a multiplication with the tabulated reciprocal cell size
 // instead of the reference's (x - g0)/((x - g0) + (g1 - x)) (pylamp_trac.py:74-75): four fp64 divisions per marker
 // less; the two forms differ by a rounding error (1e-16 relative), the public plb_grid2trac keeps the reference's.
-__device__ __forceinline__ Cell locate_fast(const G2TGrid& g, const double* __restrict__ riz, const double* __restrict__ rix,
-                                            double sz, double sx, double z, double x) {
-    Cell c;
-    c.ie = (long long)floor((z - g.z0) * sz);
-    c.je = (long long)floor((x - g.x0) * sx);
-    c.bad = (c.ie < 0) || (c.ie > g.nz - 2) || (c.je < 0) || (c.je > g.nxx - 2);
+struct CellF {
+    int o;                // ie * ld + je
+    double dzn, dxn;
+    bool bad;
+};
+
+__device__ __forceinline__ CellF locate_fast(const G2TGrid& g, const double* __restrict__ riz, const double* __restrict__ rix,
+                                             double sz, double sx, double z, double x) {
+    CellF c;
+    int ie = __double2int_rd((z - g.z0) * sz), je = __double2int_rd((x - g.x0) * sx);
+    c.bad = (unsigned)ie > (unsigned)(g.nz - 2) || (unsigned)je > (unsigned)(g.nxx - 2);
     if (c.bad) {                                     // (rare: let the reference's formula decide what is outside)
-        c.ie = cell_of(z, g.z0, g.zlen, g.nz), c.je = cell_of(x, g.x0, g.xlen, g.nxx);
-        c.bad = (c.ie < 0) || (c.ie > g.nz - 2) || (c.je < 0) || (c.je > g.nxx - 2);
-        if (c.bad) c.ie = 0, c.je = 0;
+        const long long a = cell_of(z, g.z0, g.zlen, g.nz), b = cell_of(x, g.x0, g.xlen, g.nxx);
+        c.bad = (a < 0) || (a > g.nz - 2) || (b < 0) || (b > g.nxx - 2);
+        ie = c.bad ? 0 : (int)a, je = c.bad ? 0 : (int)b;
     }
-    c.dz0 = z - g.gz[c.ie], c.dx0 = x - g.gx[c.je];
-    c.dz1 = 0, c.dx1 = 0;
-    c.dzn = c.dz0 * riz[c.ie];
-    c.dxn = c.dx0 * rix[c.je];
+    c.o = ie * g.ld + je;
+    c.dzn = (z - g.gz[ie]) * riz[ie];
+    c.dxn = (x - g.gx[je]) * rix[je];
     return c;
+}
+
+// pylamp_trac.py:92-96 with the products summed by fused multiply-adds
+__device__ __forceinline__ double bilin_fast(const double* __restrict__ f, int ld, const CellF& c) {
+    const double* p = f + c.o;
+    const double f00 = __ldg(p), f01 = __ldg(p + 1), f10 = __ldg(p + ld), f11 = __ldg(p + ld + 1);
+    const double omz = 1 - c.dzn, omx = 1 - c.dxn;
+    return fma(omx * omz, f00, fma(c.dxn * omz, f01, fma(omx * c.dzn, f10, (c.dxn * c.dzn) * f11)));
 }
 
 // EXACT = false: the cell by a multiplication; returns true when the position lies within 1e-7 cells of a face (or
@@ -636,10 +648,15 @@ __device__ __forceinline__ bool vel_at(const double* __restrict__ fz, const doub
                                        const G2TGrid& g, const double* __restrict__ riz,
                                        const double* __restrict__ rix, double sz, double sx, double z, double x,
                                        double& vz, double& vx) {
-    long long ie, je;
-    if (EXACT) ie = cell_of(z, g.z0, g.zlen, g.nz), je = cell_of(x, g.x0, g.xlen, g.nxx);
-    else ie = (long long)floor((z - g.z0) * sz), je = (long long)floor((x - g.x0) * sx);
-    if (ie < 0 || ie > g.nz - 2 || je < 0 || je > g.nxx - 2) {
+    int ie, je;                                            // (the host side checks nz * ld < 2^31)
+    if (EXACT) {
+        const long long a = cell_of(z, g.z0, g.zlen, g.nz), b = cell_of(x, g.x0, g.xlen, g.nxx);
+        ie = a < 0 ? -1 : (a > g.nz ? g.nz : (int)a);
+        je = b < 0 ? -1 : (b > g.nxx ? g.nxx : (int)b);
+    } else {
+        ie = __double2int_rd((z - g.z0) * sz), je = __double2int_rd((x - g.x0) * sx);     // (saturating)
+    }
+    if ((unsigned)ie > (unsigned)(g.nz - 2) || (unsigned)je > (unsigned)(g.nxx - 2)) {
         vz = 0, vx = 0;                                    // defval=0, :361
         return true;
     }
@@ -647,16 +664,22 @@ __device__ __forceinline__ bool vel_at(const double* __restrict__ fz, const doub
     const double hz = gz1 - gz0, hx = gx1 - gx0;
     const double rz = riz[ie], rx = rix[je];          // 1/hz, 1/hx
     const double dzn = (z - gz0) * rz, dxn = (x - gx0) * rx;
-    const double* pz = fz + ie * g.ld + je;
-    const double* px = fx + ie * g.ld + je;
+    const int o = ie * g.ld + je;
+    const double* pz = fz + o;
+    const double* px = fx + o;
     const double z00 = __ldg(pz), z01 = __ldg(pz + 1), z10 = __ldg(pz + g.ld), z11 = __ldg(pz + g.ld + 1);
     const double x00 = __ldg(px), x01 = __ldg(px + 1), x10 = __ldg(px + g.ld), x11 = __ldg(px + g.ld + 1);
     const double c10 = (0.5 * hx * rz) * (z00 - z10 + z11 - z01);
     const double c20 = (0.5 * hz * rx) * (x00 - x01 + x11 - x10);
-    const double w00 = (1 - dxn) * (1 - dzn), w01 = dxn * (1 - dzn), w10 = (1 - dxn) * dzn, w11 = dxn * dzn;
-    vx = w00 * x00 + w01 * x01 + w10 * x10 + w11 * x11 + dxn * (1 - dxn) * c10;
-    vz = w00 * z00 + w01 * z01 + w10 * z10 + w11 * z11 + dzn * (1 - dzn) * c20;
-    return fmin(fmin(dzn, 1.0 - dzn), fmin(dxn, 1.0 - dxn)) < 1e-7;
+    const double omz = 1 - dzn, omx = 1 - dxn;
+    const double w00 = omx * omz, w01 = dxn * omz, w10 = omx * dzn, w11 = dxn * dzn;
+    const double bz = dzn * omz, bx = dxn * omx;
+    // (this file is compiled without fp contraction for the exact index formulas; the sums of products here are
+    // fused by hand: one rounding less per term than the reference's, 1e-16 relative)
+    vx = fma(w00, x00, fma(w01, x01, fma(w10, x10, fma(w11, x11, bx * c10))));
+    vz = fma(w00, z00, fma(w01, z01, fma(w10, z10, fma(w11, z11, bz * c20))));
+    // within ~1e-7 cells of a face (d (1 - d) <= min(d, 1 - d); negative when the multiplication picked a neighbour)
+    return fmin(bz, bx) < 1e-7;
 }
 
 template <bool EXACT>
@@ -666,9 +689,9 @@ __device__ __forceinline__ bool rk4_stages(const double* __restrict__ fz, const 
     const double hdt = 0.5 * dt, sixth_dt = (1.0 / 6.0) * dt;
     double k1z, k1x, k2z, k2x, k3z, k3x, k4z, k4x;
     bool face = vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x, p.y, k1z, k1x);
-    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k1z, p.y + hdt * k1x, k2z, k2x);
-    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x + hdt * k2z, p.y + hdt * k2x, k3z, k3x);
-    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, p.x + dt * k3z, p.y + dt * k3x, k4z, k4x);
+    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, fma(hdt, k1z, p.x), fma(hdt, k1x, p.y), k2z, k2x);
+    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, fma(hdt, k2z, p.x), fma(hdt, k2x, p.y), k3z, k3x);
+    face |= vel_at<EXACT>(fz, fx, g, riz, rix, sz, sx, fma(dt, k3z, p.x), fma(dt, k3x, p.y), k4z, k4x);
     q.x = p.x + sixth_dt * (((k1z + k2z) + k3z) + k4z);   // :385 (unweighted sum)
     q.y = p.y + sixth_dt * (((k1x + k2x) + k3x) + k4x);
     return face;
@@ -684,7 +707,7 @@ struct FenceArgs {
 };
 
 template <bool FENCE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_rk4(long long M, const double2* __restrict__ trx, const double* __restrict__ fz,
       const double* __restrict__ fx, G2TGrid g, const double* __restrict__ riz,
       const double* __restrict__ rix, double dt, double2* __restrict__ xout, double2* __restrict__ vout, FenceArgs fa) {
@@ -826,7 +849,9 @@ k_sub(long long M, const double* __restrict__ a, const double* __restrict__ b,
 // Fused marker temperature update of pylamp2.py:448-475: T1 = T + interp(dT_grid) (:453-455), then the
 // subgrid relaxation Tsg = Told - (Told - T1) exp(-d dt / tau), dT = Tsg - T1 (:472-475) with Told = T.
 // One pass over the markers instead of clone + grid2trac + add + stage 1 (same arithmetic).
-__global__ void __launch_bounds__(256)
+// (both kernels: the streaming loads of a thread's NEXT marker are issued before the gathers of the current one --
+// ncu on the plain loop showed 24 of 32 resident warps waiting on memory per issue slot at 0.58 of the HBM peak)
+__global__ void __launch_bounds__(256, 4)
 k_subgrid_fused1(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ riz,
                  const double* __restrict__ rix, const double* __restrict__ dTg,
                  double dt, double fac, const double* __restrict__ T, const double* __restrict__ cp,
@@ -834,42 +859,60 @@ k_subgrid_fused1(long long M, const double2* __restrict__ trx, G2TGrid g, const 
                  double* __restrict__ dT, unsigned long long* n_outside) {
     const double d = 0.5;
     const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
+    const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned bad_local = 0;
-    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
-         m += (long long)gridDim.x * blockDim.x) {
-        const double2 p = trx[m];
-        const Cell c = locate_fast(g, riz, rix, sz, sx, p.x, p.y);
-        if (c.bad) {
-            bad_local++;
-            continue;
+    long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m < M) {
+        double2 p = trx[m];
+        double told = T[m], vcp = cp[m], vrho = rho[m], vk = k[m];
+        for (;;) {
+            const long long mn = m + stride;
+            const bool more = mn < M;
+            double2 pn = p;
+            double toldn = 0, vcpn = 0, vrhon = 0, vkn = 0;
+            if (more) pn = trx[mn], toldn = T[mn], vcpn = cp[mn], vrhon = rho[mn], vkn = k[mn];
+            const CellF c = locate_fast(g, riz, rix, sz, sx, p.x, p.y);
+            if (c.bad) {
+                bad_local++;
+            } else {
+                const double t1 = told + bilin_fast(dTg, g.ld, c);
+                const double tau = vcp * vrho / (vk * fac);
+                const double tsg = told - (told - t1) * exp(-d * dt / tau);
+                Tsg[m] = tsg;
+                dT[m] = tsg - t1;
+            }
+            if (!more) break;
+            m = mn, p = pn, told = toldn, vcp = vcpn, vrho = vrhon, vk = vkn;
         }
-        const double told = T[m];
-        const double t1 = told + bilin(dTg, g.ld, c);
-        const double tau = cp[m] * rho[m] / (k[m] * fac);
-        const double tsg = told - (told - t1) * exp(-d * dt / tau);
-        Tsg[m] = tsg;
-        dT[m] = tsg - t1;
     }
     bad_local = __reduce_add_sync(0xffffffffu, bad_local);
     if ((threadIdx.x & 31) == 0 && bad_local) atomicAdd(n_outside, (unsigned long long)bad_local);
 }
 
 // T = Tsg - interp(f_sgc), pylamp2.py:479-480
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_subgrid_fused2(long long M, const double2* __restrict__ trx, G2TGrid g, const double* __restrict__ riz,
                  const double* __restrict__ rix, const double* __restrict__ sgc,
                  const double* __restrict__ Tsg, double* __restrict__ T, unsigned long long* n_outside) {
     const double sz = (double)(g.nz - 1) / g.zlen, sx = (double)(g.nxx - 1) / g.xlen;
+    const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned bad_local = 0;
-    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M;
-         m += (long long)gridDim.x * blockDim.x) {
-        const double2 p = trx[m];
-        const Cell c = locate_fast(g, riz, rix, sz, sx, p.x, p.y);
-        if (c.bad) {
-            bad_local++;
-            continue;
+    long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m < M) {
+        double2 p = trx[m];
+        double tsg = Tsg[m];
+        for (;;) {
+            const long long mn = m + stride;
+            const bool more = mn < M;
+            double2 pn = p;
+            double tsgn = 0;
+            if (more) pn = trx[mn], tsgn = Tsg[mn];
+            const CellF c = locate_fast(g, riz, rix, sz, sx, p.x, p.y);
+            if (c.bad) bad_local++;
+            else T[m] = tsg - bilin_fast(sgc, g.ld, c);
+            if (!more) break;
+            m = mn, p = pn, tsg = tsgn;
         }
-        T[m] = Tsg[m] - bilin(sgc, g.ld, c);
     }
     bad_local = __reduce_add_sync(0xffffffffu, bad_local);
     if ((threadIdx.x & 31) == 0 && bad_local) atomicAdd(n_outside, (unsigned long long)bad_local);
@@ -1691,6 +1734,7 @@ int rk4_launch(plb_ctx* ctx, long long M, const double* d_tr_x, const double* d_
                double xlen, double dt, double* d_x_out, double* d_v_out, const FenceArgs* fence) {
     PLB_CUDA(ctx, cudaSetDevice(ctx->device));
     G2TGrid g = {d_gc_z, d_gc_x, nzc, nxc, ld, z0, zlen, x0, xlen};
+    if ((long long)nzc * ld >= (1LL << 31)) PLB_FAIL(ctx, "plb_rk4: velocity fields beyond 2^31 nodes");
     if (fence && fence->count)
         PLB_CUDA(ctx, cudaMemsetAsync(fence->count, 0, (size_t)(fence->nz - 1) * (fence->nxx - 1) * sizeof(long long), ctx->stream));
     if (M <= 0) return 0;
@@ -1833,6 +1877,7 @@ int plb_subgrid_fused(plb_ctx* ctx, int stage, long long M, const double* d_tr_x
     double* recip = (double*)ctx->ws + 8;
     PLB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->stream));
     G2TGrid g = {d_grid_z, d_grid_x, nz, nxx, ld, z0, zlen, x0, xlen};
+    if ((long long)nz * ld >= (1LL << 31)) PLB_FAIL(ctx, "plb_subgrid_fused: field beyond 2^31 nodes");
     if (M > 0) {
         k_axis_recip<<<plb_blocks(nz, 256), 256, 0, ctx->stream>>>(nz, d_grid_z, recip, nullptr);
         PLB_LAUNCHED(ctx);

@@ -73,6 +73,7 @@ struct plb_stokes {
     // full-size planes of centred density gradients Dz | Dx the extra momentum-row terms are built from
     double surf = 0;
     double* surf_d = nullptr;
+    double* wsc_d = nullptr;      // finest level: W_p = sqrt(eta_n)/Kc, sqrt(-diag K_vz), sqrt(-diag K_vx) (k_scale_planes)
     int ai = 3, aj = 2;           // pressure anchor cell (pylamp_stokes.py:525-551: (3,2), or (nz/2, 0) on a flow-through wall)
     double Kc = 0, Kb = 0;
     bool coeffs = false, hierarchy = false;
@@ -343,12 +344,24 @@ k_stokes_op(LevelDev L, SurfArgs sf, double Kc, const double* __restrict__ vz, c
 
 // preconditioner, stage 1: dp = S^-1 r_p with S = Kc^2/eta_n (diagonal), and the right-hand side
 // of the velocity-block solve  bv = r_v - G dp   (r = W^-1 r^ un-scaled on the fly)
-__device__ __forceinline__ double dp_at(const LevelDev& L, double Kc, const double* __restrict__ rp, long long o) {
-    return rp[o] * sqrt(L.etan[o]) / Kc;        // (rp/W_p) / (Kc^2/eta) = rp * sqrt(eta)/Kc
+// The three scalings depend on the coefficients only: tabulated once per plb_stokes_set_coeffs instead of five square
+// roots and three divisions per node and Krylov iteration (ncu: k_precond_rhs was bound by exactly those -- issue
+// slots 67 % busy at 2.6 TB/s).  wp = sqrt(eta_n)/Kc where a pressure lives, sdz / sdx = sqrt(-diag) on the momentum rows.
+__global__ void __launch_bounds__(BX* BY)
+k_scale_planes(LevelDev L, int row0, double invKc, double* __restrict__ wp, double* __restrict__ sdz,
+               double* __restrict__ sdx) {
+    const int j = blockIdx.x * BX + threadIdx.x, i = row0 + blockIdx.y * BY + threadIdx.y;
+    if (i >= L.i1 || j >= L.nxx) return;
+    const long long o = (long long)i * L.ld + j;
+    wp[o] = (i <= L.nz - 2 && j <= L.nxx - 2) ? sqrt(L.etan[o]) * invKc : 0.0;
+    if (i < L.i0) return;                       // (the halo row below: only its pressure scaling is read)
+    sdz[o] = is_vz_row(L, i, j) ? sqrt(-vz_coef(L, i, j).diag) : 0.0;
+    sdx[o] = is_vx_row(L, i, j) ? sqrt(-vx_coef(L, i, j).diag) : 0.0;
 }
 
 __global__ void __launch_bounds__(BX* BY)
-k_precond_rhs(LevelDev L, double Kc, const double* __restrict__ rz, const double* __restrict__ rx,
+k_precond_rhs(LevelDev L, double Kc, const double* __restrict__ wp, const double* __restrict__ sdz,
+              const double* __restrict__ sdx, const double* __restrict__ rz, const double* __restrict__ rx,
               const double* __restrict__ rp, double* __restrict__ zp, double* __restrict__ bvz,
               double* __restrict__ bvx) {
     const int j = blockIdx.x * BX + threadIdx.x, i = L.i0 + blockIdx.y * BY + threadIdx.y;
@@ -358,33 +371,27 @@ k_precond_rhs(LevelDev L, double Kc, const double* __restrict__ rz, const double
     if (is_interior(L, i, j) && i <= nz - 3 && j <= nxx - 3) {
         // interior fast path (no corner cell here): all loads up front
         const double r0 = rp[o], rM = rp[o - ld], rW = rp[o - 1];
-        const double e0 = L.etan[o], eM = L.etan[o - ld], eW = L.etan[o - 1];
-        const double rzv = rz[o], rxv = rx[o];
-        const Rows2 q = rows_interior<false>(L, nullptr, nullptr, i, j);
-        const double d0 = r0 * sqrt(e0) / Kc, dM = rM * sqrt(eM) / Kc, dW = rW * sqrt(eW) / Kc;
+        const double w0 = wp[o], wM = wp[o - ld], wW = wp[o - 1];
+        const double rzv = rz[o], rxv = rx[o], sz = sdz[o], sx = sdx[o];
+        const double d0 = r0 * w0, dM = rM * wM, dW = rW * wW;     // (rp/W_p) / (Kc^2/eta) = rp * sqrt(eta)/Kc
         zp[o] = d0;
-        bvz[o] = is_vz_row(L, i, j) ? rzv * sqrt(-q.dz) + 2 * Kc * L.idzc[i] * (d0 - dM) : 0.0;
-        bvx[o] = is_vx_row(L, i, j) ? rxv * sqrt(-q.dx) + 2 * Kc * L.idxc[j] * (d0 - dW) : 0.0;
+        bvz[o] = is_vz_row(L, i, j) ? rzv * sz + 2 * Kc * L.idzc[i] * (d0 - dM) : 0.0;
+        bvx[o] = is_vx_row(L, i, j) ? rxv * sx + 2 * Kc * L.idxc[j] * (d0 - dW) : 0.0;
         return;
     }
     double dp = 0;
     if (i <= nz - 2 && j <= nxx - 2) {
         bool corner = (i == 0 || i == nz - 2) && (j == 0 || j == nxx - 2);
         // corner pressures are slaves of their x-neighbour (pylamp_stokes.py:358-369)
-        dp = corner ? dp_at(L, Kc, rp, j == 0 ? o + 1 : o - 1) : dp_at(L, Kc, rp, o);
+        const long long q = corner ? (j == 0 ? o + 1 : o - 1) : o;
+        dp = rp[q] * wp[q];
     }
     zp[o] = dp;
     double b = 0;
-    if (is_vz_row(L, i, j)) {
-        VzCoef c = vz_coef(L, i, j);
-        b = rz[o] * sqrt(-c.diag) + 2 * Kc * L.idzc[i] * (dp_at(L, Kc, rp, o) - dp_at(L, Kc, rp, o - ld));
-    }
+    if (is_vz_row(L, i, j)) b = rz[o] * sdz[o] + 2 * Kc * L.idzc[i] * (rp[o] * wp[o] - rp[o - ld] * wp[o - ld]);
     bvz[o] = b;
     b = 0;
-    if (is_vx_row(L, i, j)) {
-        VxCoef c = vx_coef(L, i, j);
-        b = rx[o] * sqrt(-c.diag) + 2 * Kc * L.idxc[j] * (dp_at(L, Kc, rp, o) - dp_at(L, Kc, rp, o - 1));
-    }
+    if (is_vx_row(L, i, j)) b = rx[o] * sdx[o] + 2 * Kc * L.idxc[j] * (rp[o] * wp[o] - rp[o - 1] * wp[o - 1]);
     bvx[o] = b;
 }
 
@@ -615,6 +622,7 @@ k_stokes_op_tile(LevelDev L, SurfArgs sf, int row_lo, int row_hi, double Kc, con
     const int j = j00 + tx;
     const double idx_j = (j < L.nxx) ? L.idx[j] : 0.0, idx_m = (j >= 1 && j < L.nxx) ? L.idx[j - 1] : 0.0;
     const double idxc_j = (j < L.nxx) ? L.idxc[j] : 0.0, idxc_p = (j + 1 < L.nxx) ? L.idxc[j + 1] : 0.0;
+    const double invKc = 1.0 / Kc;
     __pipeline_wait_prior(0);
     __syncthreads();
 #pragma unroll 1
@@ -663,7 +671,7 @@ k_stokes_op_tile(LevelDev L, SurfArgs sf, int row_lo, int row_hi, double Kc, con
         if (SURF) a += sf.cx * sq;
         ox[o] = is_vx_row(L, i, j) ? (RESID ? vbx - a : a) * rsqrt(-t.dgx) : 0.0;
         a = Kc * (idx_j * (t.x0P - t.x00) + L.idz[i] * (t.zP0 - t.z00));
-        op[o] = is_p_row(L, i, j) ? (RESID ? vbp - a : a) * (sqrt(en) / Kc) : 0.0;
+        op[o] = is_p_row(L, i, j) ? (RESID ? vbp - a : a) * (sqrt(en) * invKc) : 0.0;
     }
 }
 
@@ -1513,7 +1521,7 @@ void plb_stokes_destroy(plb_stokes* op) {
     for (Level& L : op->lv) free_level(L);
     plb_fgmres_free(&op->kry);
     if (op->graph_exec) cudaGraphExecDestroy(op->graph_exec);
-    double* ptrs[] = {op->d_scal, op->cinv, op->probes, op->gjM, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->zv, op->surf_d};
+    double* ptrs[] = {op->d_scal, op->cinv, op->probes, op->gjM, op->xs, op->r3, op->b3, op->t3, op->gz_d, op->gx_d, op->zv, op->surf_d, op->wsc_d};
     for (double* p : ptrs) if (p) cudaFree(p);
     for (double* p : op->hist) if (p) cudaFree(p);
     plb_reduce_ws_free(&op->rws);
@@ -1582,6 +1590,15 @@ int plb_stokes_set_coeffs(plb_stokes* op, const double* d_etas, const double* d_
     op->Kc = 2 * mineta / (avgdx + avgdz);
     op->Kb = 4 * mineta / ((avgdx + avgdz) * (avgdx + avgdz));
     op->coeffs = true, op->hierarchy = false;
+    // scalings of the preconditioner's first stage (own rows; the pressure scaling also on the halo row below)
+    if (!op->wsc_d && zalloc(ctx, &op->wsc_d, 3 * L.full)) return 2;
+    {
+        const int row0 = L.i0 > 0 ? L.i0 - 1 : 0;
+        const dim3 g((L.nxx + BX - 1) / BX, (L.i1 - row0 + BY - 1) / BY);
+        k_scale_planes<<<g, block2d(), 0, ctx->stream>>>(L.dev(), row0, 1.0 / op->Kc, op->wsc_d, op->wsc_d + L.full,
+                                                       op->wsc_d + 2 * L.full);
+        PLB_LAUNCHED(ctx);
+    }
     return 0;
 }
 
@@ -1821,8 +1838,8 @@ int plb_stokes_solve(plb_stokes* op, const double* d_rhs, double rtol, int maxit
         if (halo(op, L, const_cast<double*>(rr) + 2 * P, 1)) return 2;
         {
             plb_prof_scope prof_(ctx, PLB_K_PRECRHS, 80.0 * (double)P);
-            k_precond_rhs<<<g, blk, 0, ctx->stream>>>(D, Kc, C3(rr, 0), C3(rr, 1), C3(rr, 2), V3(z, 2), L.sh(L.b),
-                                                      L.sh(L.b + P));
+            k_precond_rhs<<<g, blk, 0, ctx->stream>>>(D, Kc, op->wsc_d, op->wsc_d + L.full, op->wsc_d + 2 * L.full, C3(rr, 0),
+                                                      C3(rr, 1), C3(rr, 2), V3(z, 2), L.sh(L.b), L.sh(L.b + P));
             PLB_LAUNCHED(ctx);
             PLB_CUDA(ctx, cudaMemsetAsync(z, 0, sizeof(double) * 2 * P, ctx->stream));
         }

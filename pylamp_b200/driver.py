@@ -187,8 +187,12 @@ def timestep(s, o, want_kelem=True, phases=False):
     ph = s.phases = _Phases(phases)
     ph.mark("start")
     s.it += 1
-    if o.resort_every and s.it > 1 and (s.it - 1) % o.resort_every == 0:
-        s.tr_x, s.cols, _ = markers.sort_by_cell(s.tr_x, s.cols, s.nx, s.L, consume=True)
+    # (first on the second step: the sort's slot table and spare arrays, kept on the state, exist from the start
+    # of a run -- a first sort deep inside a run allocates ~8 GB at 2.7e8 markers, measured +70 ms in that step)
+    if o.resort_every and s.it >= 2 and (s.it - 2) % o.resort_every == 0:
+        if getattr(s, "sort_ws", None) is None:
+            s.sort_ws = {}
+        s.tr_x, s.cols, _ = markers.sort_by_cell(s.tr_x, s.cols, s.nx, s.L, consume=True, ws=s.sort_ws)
     nx, grid, gridmp = s.nx, s.grid, s.gridmp
     cols, tr_x = s.cols, s.tr_x
     # marker property update, pylamp2.py:291-303

@@ -149,7 +149,7 @@ def subgrid_stage2(Tsg, back, T_out):
     _ctx(Tsg).call("plb_subgrid_stage2", Tsg.shape[0], Tsg.data_ptr(), back.data_ptr(), T_out.data_ptr())
 
 
-def sort_by_cell(tr_x, cols, nx, L, extra=(), want_cell_start=False, consume=False):
+def sort_by_cell(tr_x, cols, nx, L, extra=(), want_cell_start=False, consume=False, ws=None):
     """Physically re-order the marker arrays by cell index (cell-major, like the setups generate
     them) with the device counting sort of csrc/sort.cu (plb_sort_plan + one plb_permute per distinct
     array).  The results of every kernel are order-independent (up to fp64 summation order in
@@ -158,20 +158,28 @@ def sort_by_cell(tr_x, cols, nx, L, extra=(), want_cell_start=False, consume=Fal
     Returns (tr_x, cols, extra) as new tensors (+ the (ncell+1,) int32 first-slot table if asked).
     `extra`: further (M,) or (M,2) float64 tensors to carry along (e.g. marker velocities).
     `consume=True`: the input tensors may be overwritten (each permuted array's old storage becomes the
-    next array's destination: one spare array instead of a second copy of the whole cloud)."""
+    next array's destination: one spare array instead of a second copy of the whole cloud).
+    `ws` (a dict the caller keeps between calls, with consume=True): the slot table and the spare arrays
+    stay allocated from one sort to the next -- nothing is allocated in a time loop's later sorts."""
     ctx = _ctx(tr_x)
     M = tr_x.shape[0]
     nz, nxx = int(nx[IZ]), int(nx[IX])
-    dest = torch.empty(M, dtype=torch.int32, device=tr_x.device)
+    keep = ws if (ws is not None and consume) else None
+    dest = keep.get("dest") if keep is not None else None
+    if dest is None or dest.shape[0] != M or dest.device != tr_x.device:
+        dest = torch.empty(M, dtype=torch.int32, device=tr_x.device)
+        if keep is not None:
+            keep["dest"] = dest
     start = torch.empty((nz - 1) * (nxx - 1) + 1, dtype=torch.int32, device=tr_x.device) if want_cell_start else None
     ctx.call("plb_sort_plan", M, tr_x.data_ptr(), nz, nxx, float(L[IZ]), float(L[IX]), dest.data_ptr(),
              start.data_ptr() if want_cell_start else None)
-    spare = {}          # the array permuted last becomes the next one's destination (one spare per shape)
+    # the array permuted last becomes the next one's destination (one spare per shape)
+    spare = keep.setdefault("spare", {}) if keep is not None else {}
 
     def perm(t):
         width = 1 if t.dim() == 1 else int(t.shape[1])
         out = spare.pop(width, None) if consume else None
-        if out is None or out.shape[0] != M or out.data_ptr() == t.data_ptr():
+        if out is None or out.shape != t.shape or out.device != t.device or out.data_ptr() == t.data_ptr():
             out = torch.empty_like(t)
         ctx.call("plb_permute", M, dest.data_ptr(), t.data_ptr(), out.data_ptr(), width)
         if consume:
