@@ -79,7 +79,10 @@ def trac2grid_device(ctx, tr_x_d, cols_d, schemes, grid, out_d, minmax=None):
     k = len(cols_d)
     M = tr_x_d.shape[0]
     if minmax is None:
-        minmax = marker_minmax(tr_x_d, ctx) if M > 0 else [0, 0, 0, 0]
+        # (several ranks: the extent is all-reduced -- a rank without markers must take part)
+        minmax = marker_minmax(tr_x_d, ctx) if (M > 0 or ctx.comm_info()[1] > 1) else [0, 0, 0, 0]
+        if not all(np.isfinite(minmax)):
+            minmax = [0, 0, 0, 0]
     gz, gx = _axis_np(grid[IZ]), _axis_np(grid[IX])
     axz, lz, rz = _extended_axis(gz, minmax[0], minmax[1])
     axx, lx, rx = _extended_axis(gx, minmax[2], minmax[3])
