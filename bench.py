@@ -234,12 +234,15 @@ def run_b200(args):
 
     # ---- e2e: the same step through host buffers (rank-local) ----
     e2e = None
-    if args.e2e_steps > 0 and not (world > 1 and args.marker_ownership == "slab"):   # slab clouds change size
+    if args.e2e_steps > 0:
         e2e = run_e2e(torch, driver, s, o, args.e2e_steps)
-        if world > 1:
+        if world > 1:                            # time: the slowest rank; bytes: the whole job's
             t = torch.tensor([e2e["ms"]], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e["ms"] = float(t.item())
+            b = torch.tensor([e2e["h2d"], e2e["d2h"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            e2e["h2d"], e2e["d2h"] = int(b[0].item()), int(b[1].item())
 
     if world > 1:
         # nothing collective happens after this point: the other ranks must not wait for rank 0's report
@@ -323,41 +326,56 @@ def run_e2e(torch, driver, s, o, nsteps):
     marker coordinates and marker temperature go from pinned host memory to the device, the step runs, and the new
     coordinates, marker temperature, marker velocities and the velocity / pressure / temperature grids come back
     (the constant material columns -- rho0, alpha, Ea, eta0, k, Cp, H, material id -- are uploaded once with the
-    set-up, like the grids' axes).  Step n+1 can only start from what step n returned, so upload -> step ->
-    download of (coordinates, temperature) is a serial chain; the outputs that are not fed back (marker velocities,
-    grids) are downloaded on a second stream while the next step's upload runs (PCIe is full duplex).  Everything
-    is inside the timed region; both streams are drained before the clock stops."""
+    set-up, like the grids' axes; on several GPUs they migrate with their markers on the device).  Step n+1 can only
+    start from what step n returned, so upload -> step -> download of (coordinates, temperature) is a serial chain;
+    the outputs that are not fed back (marker velocities, grids) are downloaded on a second stream while the next
+    step's upload runs (PCIe is full duplex).  Everything is inside the timed region; both streams are drained
+    before the clock stops.  With slab-owned markers a rank's marker count changes from step to step: the pinned
+    buffers have head-room and every copy moves the rows in use (bytes counted per step from those rows)."""
     from pylamp_b200.pylamp_const import TR_TMP
-    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
-    h_x, h_T = pin(s.tr_x), pin(s.cols[TR_TMP])
-    h_v = torch.empty(s.tr_x.shape, dtype=torch.float64, pin_memory=True)
+    M0 = int(s.tr_x.shape[0])
+    cap = M0 + M0 // 4 + 1024
+    h_x = torch.empty((cap, 2), dtype=torch.float64, pin_memory=True)
+    h_T = torch.empty(cap, dtype=torch.float64, pin_memory=True)
+    h_v = torch.empty((cap, 2), dtype=torch.float64, pin_memory=True)
+    h_x[:M0].copy_(s.tr_x)
+    h_T[:M0].copy_(s.cols[TR_TMP])
     h_grids = [torch.empty(tuple(s.nx), dtype=torch.float64, pin_memory=True) for _ in range(4)]
-    h2d = (h_x.numel() + h_T.numel()) * 8
-    d2h = (h_x.numel() + h_T.numel() + h_v.numel() + 4 * h_grids[0].numel()) * 8
+    h2d = d2h = 0
     side = torch.cuda.Stream()
     main = torch.cuda.current_stream()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(nsteps):
-        s.tr_x.copy_(h_x, non_blocking=True)
-        s.cols[TR_TMP].copy_(h_T, non_blocking=True)
+        M = int(s.tr_x.shape[0])                 # rows this rank holds (= what the last download wrote)
+        s.tr_x.copy_(h_x[:M], non_blocking=True)
+        s.cols[TR_TMP].copy_(h_T[:M], non_blocking=True)
+        h2d += 3 * M * 8
         driver.timestep(s, o, want_kelem=False)
+        M = int(s.tr_x.shape[0])
+        if M > cap:
+            raise RuntimeError("e2e: a rank's marker count outgrew the host buffers (%d > %d)" % (M, cap))
         done = torch.cuda.Event()
         done.record(main)
-        outs = (s.trac_vel, s.newvel[0], s.newvel[1], s.newpres, s.newtemp)
+        vel = s.trac_vel if (s.trac_vel is not None and s.trac_vel.shape[0] == M) else None
+        outs = [(h_grids[0], s.newvel[0]), (h_grids[1], s.newvel[1]), (h_grids[2], s.newpres), (h_grids[3], s.newtemp)]
+        if vel is not None:
+            outs.append((h_v[:M], vel))
         with torch.cuda.stream(side):
             side.wait_event(done)
-            for h, d in zip([h_v] + h_grids, outs):
+            for h, d in outs:
                 d.record_stream(side)            # the next step replaces these tensors while the copy may still run
                 h.copy_(d, non_blocking=True)
-        h_x.copy_(s.tr_x, non_blocking=True)
-        h_T.copy_(s.cols[TR_TMP], non_blocking=True)
+                d2h += d.numel() * 8
+        h_x[:M].copy_(s.tr_x, non_blocking=True)
+        h_T[:M].copy_(s.cols[TR_TMP], non_blocking=True)
+        d2h += 3 * M * 8
         main.synchronize()                       # the next step starts from h_x, h_T
     side.synchronize()
     ev1.record()
     torch.cuda.synchronize()
-    return {"ms": ev0.elapsed_time(ev1) / nsteps, "h2d": int(h2d), "d2h": int(d2h)}
+    return {"ms": ev0.elapsed_time(ev1) / nsteps, "h2d": int(h2d // nsteps), "d2h": int(d2h // nsteps)}
 
 
 def main():
