@@ -1,5 +1,5 @@
 """Does the slab-distributed Stokes solve need the same number of iterations as the single-GPU one?
-torchrun, 2+ GPUs:  python -m torch.distributed.run --nproc-per-node 2 scripts/check_slab_iters.py [ncell=2048] [nsteps=10]
+torchrun, 2+ GPUs:  python -m torch.distributed.run --nproc-per-node 2 scripts/check_slab_iters.py [ncell=2048] [nsteps=10] [shift_cells=0.3]
 Steps the analytic C4-type fields (setups.convection_fields) through nsteps time levels with bench.py's solver
 settings, first on every rank alone, then slab-distributed, and prints iterations / relres per step for both."""
 import os
@@ -18,11 +18,12 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+shift = float(sys.argv[3]) if len(sys.argv) > 3 else 0.3      # cells per step the fields move
 dev = torch.device("cuda", local)
 ctx = _lib.default_context(local)
 cache = {}
 for t in range(-nsteps, 1):
-    nx, L, grid, gridmp, es, en, rho = setups.convection_fields(ncell, t)
+    nx, L, grid, gridmp, es, en, rho = setups.convection_fields(ncell, t, shift_cells=shift)
     cache[t] = [torch.as_tensor(a).to(dev) for a in (es, en, rho)]
 
 
