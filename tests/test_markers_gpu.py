@@ -504,3 +504,40 @@ def test_delete_outside_on_device_matches_reference_block():
     nx = [9, 7]
     _, count = markers.cell_index_count(s.tr_x, nx, s.L, want_kelem=False)
     assert int(count.sum().item()) == want_x.shape[0]
+
+
+@pytest.mark.parametrize("frac_outside", [0.0, 0.02, 0.6, 1.0])
+def test_delete_outside_kernels_any_fraction(frac_outside):
+    """plb_delete_outside (list / tail survivors / fill) against NumPy's boolean mask for clouds with none, a few,
+    most (the second listing pass: more than an eighth of the cloud) and all markers beyond the box
+    (pylamp2.py:563-581: x <= 0 or x >= L); shared zero column, (M,2) velocities."""
+    import types
+    from pylamp_b200 import markers
+    rng = np.random.default_rng(int(100 * frac_outside) + 3)
+    M, L = 300_001, [2.0, 3.0]
+    x = rng.uniform(1e-3, 1.0, (M, 2)) * (np.array(L) - 2e-3)
+    out = rng.random(M) < frac_outside
+    side = rng.integers(0, 4, M)
+    x[out & (side == 0), 0] = -rng.random(int((out & (side == 0)).sum()))
+    x[out & (side == 1), 0] = L[0] + rng.random(int((out & (side == 1)).sum()))
+    x[out & (side == 2), 1] = 0.0                                     # exactly on the wall: outside
+    x[out & (side == 3), 1] = L[1]
+    ident = np.arange(M, dtype=np.float64)
+    temp = rng.random(M)
+    vel = rng.standard_normal((M, 2))
+    zero = torch.zeros(M, dtype=torch.float64, device="cuda")
+    s = types.SimpleNamespace(L=L, tr_x=torch.as_tensor(x.copy()).cuda(),
+                              cols=[torch.as_tensor(ident).cuda(), zero, torch.as_tensor(temp).cuda(), zero],
+                              trac_vel=torch.as_tensor(vel.copy()).cuda())
+    n = markers.delete_outside(s)
+    keep = ~((x[:, 0] <= 0) | (x[:, 0] >= L[0]) | (x[:, 1] <= 0) | (x[:, 1] >= L[1]))
+    assert n == M - int(keep.sum()) and s.tr_x.shape[0] == int(keep.sum())
+    got_id = s.cols[0].cpu().numpy()
+    order = np.argsort(got_id)
+    assert np.array_equal(got_id[order], ident[keep])
+    assert np.array_equal(s.tr_x.cpu().numpy()[order], x[keep])
+    assert np.array_equal(s.cols[2].cpu().numpy()[order], temp[keep])
+    assert np.array_equal(s.trac_vel.cpu().numpy()[order], vel[keep])
+    assert s.cols[1].data_ptr() == s.cols[3].data_ptr() and s.cols[1].shape[0] == int(keep.sum())
+    assert markers.delete_outside(s) == 0                             # idempotent
+
