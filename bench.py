@@ -11,7 +11,9 @@ Ra=1e6, Arrhenius viscosity clipped to [1e17,1e23], 4096^2 cells (4097^2 nodes),
 (2.7e8 markers), coupled Stokes + energy + marker advection, synthetic fields generated in HBM.
 Prints ONE JSON line (contract in the task statement).  `value` times the device-resident driver;
 `e2e` times the same step through host buffers (pinned host -> device marker/field upload and
-device -> host result download inside the timed region).
+device -> host result download inside the timed region).  The CPU arm (`--impl reference`, `cpu_baseline`) times a
+bounded sample of the same workload (256^2 cells) and scales it to the workload's unit in proportion to the cell count
+(`cpu_sample_scaled`: a lower bound on the CPU time; the measured sample numbers are in the same object).
 """
 import argparse
 import json
@@ -112,6 +114,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def workload_name(ncell, per_side):
+    return ("C4 thermal convection Ra=1e6, Arrhenius viscosity clipped [1e17,1e23], "
+            "%d^2 cells, %d markers/cell, Stokes+energy+MIC advection" % (ncell, per_side ** 2))
+
+
+def cpu_sample_scaled(sec, sample_ncell, sample_markers, ncell):
+    """The CPU path cannot run the workload itself (SuperLU at 4096^2: days, > host RAM), so a time step of a bounded
+    SAMPLE of it is timed -- the same setup on sample_ncell^2 cells -- and scaled to the metric's unit, time steps of the
+    ncell^2 workload per second, in proportion to the cell count.  Proportional scaling is a LOWER bound on the CPU
+    time: the measured law of the direct solve is x12 per doubling of the side / x23 for x4 the cells
+    (256^2 -> 512^2, profiles/r02_SUMMARY.md), i.e. super-linear.  Returns (seconds per workload step, factor, text)."""
+    factor = (float(ncell) / float(sample_ncell)) ** 2
+    text = ("measured: %.3f s per step of the same C4 setup on %d^2 cells (%d markers) = %.4g timesteps/s of the sample, "
+            "1 of the host's %d cores (the NumPy/SuperLU path is single-threaded); scaled to the %d^2-cell workload in "
+            "proportion to the cell count (x%.0f): a lower bound on the CPU time -- SuperLU grows x12 per doubling of "
+            "the side (BASELINE.md: 0.15/0.95/11.2/140.6 s per solve at 64^2/128^2/256^2/512^2) and cannot run 4096^2 "
+            "(days, > host RAM)" % (sec, sample_ncell, sample_markers, 1.0 / sec, os.cpu_count() or 0, ncell, factor))
+    return sec * factor, factor, text
+
+
 def cpu_reference_steps(ncell, nsteps, warmup):
     """The reference algorithm (oracle restatement of pylamp2.py's loop body with scipy spsolve)
     on the host CPU: returns (seconds per step list, nx, markers, per-phase timers)."""
@@ -134,21 +156,22 @@ def run_reference(args):
         return
     ncell = args.ref_ncell
     times, nx, M, timers = cpu_reference_steps(ncell, args.steps, args.warmup)
-    sec = float(np.mean(times))
+    sec_sample = float(np.mean(times))
+    sec, factor, sample = cpu_sample_scaled(sec_sample, ncell, M, args.ncell)
     cores = 1
-    sample = ("same C4 convection setup at %d^2 cells (%d markers) instead of 4096^2: scipy SuperLU needs "
-              "days and > host RAM at 4096^2 (BASELINE.md: 0.15/0.95/11.2/140.6 s per solve at 64^2/128^2/256^2/512^2, "
-              "x12 per doubling); the NumPy/SuperLU path is single-threaded: 1 of the host's %d cores is used"
-              % (ncell, M, os.cpu_count() or 0))
+    W = args.ncell
     line = {"impl": "reference", "metric": "timesteps_per_s", "value": 1.0 / sec, "unit": "timesteps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "C4 thermal convection Ra=1e6 (Stokes+energy+MIC), CPU sample at %d^2 cells, "
-                                   "16 markers/cell" % ncell, "grid_nodes": nx, "markers": M},
-            "stokes_dof_per_s": 3.0 * nx[0] * nx[1] / sec,
+            # the workload of the GPU arm; what was actually run is the bounded sample described in cpu_baseline
+            "config": {"workload": workload_name(W, args.per_side), "grid_nodes": [W + 1, W + 1],
+                       "markers": W * W * args.per_side ** 2, "stokes_dof": 3 * (W + 1) * (W + 1),
+                       "sample_grid_nodes": nx, "sample_markers": M, "sample_scale_factor": factor},
+            "stokes_dof_per_s": 3.0 * nx[0] * nx[1] / sec_sample,          # measured on the sample (size-independent unit)
             "cpu_baseline": {"value": 1.0 / sec, "unit": "timesteps/s", "cores": cores, "host_cores": os.cpu_count(),
-                             "kind": "port", "sample": sample,
+                             "kind": "port", "sample": sample, "sample_timesteps_per_s": 1.0 / sec_sample,
+                             "sample_ms_per_step": sec_sample * 1e3, "scale_factor": factor,
                              "phases_s": {k: v / args.steps for k, v in timers.items()}},
             "e2e": {"value": 1.0 / sec, "unit": "timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -283,8 +306,7 @@ def run_b200(args):
     line = {"metric": "timesteps_per_s", "value": value, "unit": "timesteps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 thermal convection Ra=1e6, Arrhenius viscosity clipped [1e17,1e23], "
-                                   "%d^2 cells, %d markers/cell, Stokes+energy+MIC advection" % (ncell, args.per_side ** 2),
+            "config": {"workload": workload_name(ncell, args.per_side),
                        "grid_nodes": nx, "markers": M, "stokes_dof": 3 * N,
                        "parallelism": "1 GPU" if world == 1 else
                        "%d GPUs, one problem in z-slabs: %s" %
@@ -311,12 +333,13 @@ def run_b200(args):
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": args.e2e_steps}
     if world == 1 and args.cpu_ncell > 0:
         times, cnx, cM, timers = cpu_reference_steps(args.cpu_ncell, 2, 0)
-        sec = float(np.mean(times))
+        sec_sample = float(np.mean(times))
+        sec, factor, sample = cpu_sample_scaled(sec_sample, args.cpu_ncell, cM, ncell)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "timesteps/s", "cores": 1, "host_cores": os.cpu_count(),
-                                "kind": "port",
-                                "sample": "2 steps of the same C4 setup at %d^2 cells (%d markers); the reference "
-                                          "cannot run 4096^2 (SuperLU: days, > host RAM)" % (args.cpu_ncell, cM),
-                                "stokes_dof_per_s": 3.0 * cnx[0] * cnx[1] / sec,
+                                "kind": "port", "sample": "2 steps; " + sample,
+                                "sample_timesteps_per_s": 1.0 / sec_sample, "sample_ms_per_step": sec_sample * 1e3,
+                                "scale_factor": factor,
+                                "stokes_dof_per_s": 3.0 * cnx[0] * cnx[1] / sec_sample,
                                 "phases_s": {k: v / 2 for k, v in timers.items()}}
     print(json.dumps(line), flush=True)
 

@@ -29,6 +29,12 @@ def test_reference_arm_json_line():
     e = d["e2e"]
     assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and d["vs_baseline"] is None
+    # same config as the GPU arm's default workload; the value is the bounded sample's, scaled in proportion to the cells
+    import bench
+    assert d["config"]["workload"] == bench.workload_name(4096, 4) and d["config"]["grid_nodes"] == [4097, 4097]
+    assert d["config"]["sample_grid_nodes"] == [25, 25]
+    f = cb["scale_factor"]
+    assert abs(f - (4096 / 24) ** 2) < 1e-6 and abs(cb["sample_timesteps_per_s"] / f - d["value"]) < 1e-12 * d["value"] + 1e-18
 
 
 def test_reference_arm_other_ranks_silent():
