@@ -191,8 +191,8 @@ def run_b200(args):
     if world > 1:
         ctx.init_comm()           # NCCL communicator of the slab solver / marker-parallel trac2grid
     ncell = args.ncell
-    nx, L, tr_x, cols, opts = setups.convection_device(ncell=ncell, per_side=args.per_side, device="cuda:%d" % local,
-                                                       rank=rank, world=world)
+    nx, L, tr_x, cols, opts = setups.convection_device(ncell=ncell, per_side=args.per_side, seed=args.seed,
+                                                       device="cuda:%d" % local, rank=rank, world=world)
     s = driver.State(nx, L, tr_x, cols, device=local)
     o = driver.Options(**opts)
     o.heat_rtol = args.heat_rtol
@@ -429,6 +429,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="label of the JSON line: 'strong' = the 4096^2 problem on N GPUs (default); 'weak' when --ncell is "
                          "chosen per N so that the work per GPU stays fixed (SURVEY 8d C5: 4096, 5632, 8192, 11264 cells)")
+    ap.add_argument("--seed", type=int, default=11, help="seed of the marker jitter (rank r uses seed + 1000 r)")
     ap.add_argument("--cpu-ncell", type=int, default=256, help="CPU-baseline sample size (0 = skip)")
     ap.add_argument("--ref-ncell", type=int, default=256, help="--impl reference sample size")
     args = ap.parse_args()
