@@ -181,11 +181,14 @@ def convection_device(ncell=4096, per_side=4, seed=11, Ra=1e6, Lbox=1e6, device=
     of host arrays otherwise).  Same lattice/ordering/physics; the jitter comes from torch's RNG,
     so positions differ from the NumPy generator's (benchmarks only -- parity tests use `convection`).
     With world > 1 each rank generates the markers of its share of the cell rows (marker-parallel
-    ranks: the cell-major order makes every share a contiguous z-slab of the cloud).
+    ranks: the cell-major order makes every share a contiguous z-slab of the cloud) -- the SAME markers the
+    one-rank call generates: every rank draws the whole cloud's jitter from the same seed and keeps its rows, so
+    that N ranks hold one problem, not another realisation of it (the Stokes iteration counts of the benchmark
+    depend on the realisation: profiles/r02_SUMMARY.md section 8).
     Returns (nx, L, tr_x (M,2) cuda, cols list of 13 (M,) cuda tensors, opts)."""
     import torch
     g = torch.Generator(device=device)
-    g.manual_seed(seed + 1000 * rank)
+    g.manual_seed(seed)
     nx, L = [ncell + 1, ncell + 1], [Lbox, Lbox]
     ns = ncell * per_side
     dev = torch.device(device)
@@ -201,7 +204,15 @@ def convection_device(ncell=4096, per_side=4, seed=11, Ra=1e6, Lbox=1e6, device=
     tr_x = torch.empty((M, 2), dtype=torch.float64, device=dev)
     tr_x[:, 0] = z.reshape(-1)
     tr_x[:, 1] = x.reshape(-1)
-    tr_x += (torch.rand((M, 2), generator=g, dtype=torch.float64, device=dev) - 0.5) * (0.5 / ns)
+    if world == 1:
+        jitter = torch.rand((M, 2), generator=g, dtype=torch.float64, device=dev)
+    else:
+        per_row = ncell * per_side * per_side
+        whole = torch.rand((ncell * per_row, 2), generator=g, dtype=torch.float64, device=dev)
+        jitter = whole[r0 * per_row:r1 * per_row].clone()
+        del whole
+    tr_x += (jitter - 0.5) * (0.5 / ns)
+    del jitter
     rho0, alpha, k, cp, Ea = 3300.0, 3.5e-5, 4.0, 1250.0, 120e3
     dT = 1623.0 - 273.0
     eta0 = rho0 * G[IZ] * alpha * dT * Lbox ** 3 / ((k / (rho0 * cp)) * Ra)

@@ -132,3 +132,19 @@ def test_delete_outside_logic_on_cpu_tensors():
     assert np.array_equal(s.trac_vel.numpy()[order], want_v)
     assert s.cols[O.TR_MRK].data_ptr() == s.cols[O.TR_IHT].data_ptr()
     assert markers.delete_outside(s) == 0                             # idempotent
+
+
+def test_benchmark_cloud_is_one_realisation_for_any_rank_count():
+    """setups.convection_device: the slabs N ranks generate are the rows of the cloud one rank generates (same jitter
+    stream), so `bench.py --gpus N` times ONE problem -- the Stokes iteration counts depend on the realisation."""
+    import torch
+    from pylamp_b200 import setups
+    from pylamp_b200.pylamp_const import TR_TMP
+    nx, L, x1, c1, _ = setups.convection_device(ncell=24, per_side=4, device="cpu")
+    for world in (2, 3, 4):
+        parts = [setups.convection_device(ncell=24, per_side=4, device="cpu", rank=r, world=world) for r in range(world)]
+        assert torch.equal(torch.cat([p[2] for p in parts]), x1)
+        assert torch.equal(torch.cat([p[3][TR_TMP] for p in parts]), c1[TR_TMP])
+    _, _, x2, _, _ = setups.convection_device(ncell=24, per_side=4, seed=12, device="cpu")
+    assert not torch.equal(x1, x2)
+
